@@ -1,0 +1,184 @@
+/*
+ * mppi_b200.h -- C ABI of libmppi_b200.so, the B200 (sm_100a) MPPI control step.
+ *
+ * The reference (cold-deuu/Quadrotor_Manipulator_MPPI) has no FFI layer: its hot path is
+ * the Python classes `mppi_solver/mppi.py:MPPI` (arm) and `mppi_solver/drone_mppi.py:MPPI`
+ * (drone) that the ROS nodes call (kinova.py:182, drone.py:164-165).  This header is the
+ * native boundary a maintainer binds instead (ctypes stub in INTEGRATION.md); the Python
+ * drop-in classes in quadrotor_manipulator_mppi_b200/mppi_solver/ sit directly on it.
+ * Each entry point names the reference code it replaces.  Paths are relative to
+ * src/mav_mppi/scripts/ of the reference.
+ *
+ * Conventions
+ *   - plain C types only; "device" pointers are CUDA device pointers of the handle's device,
+ *     16-byte aligned; "host" pointers are ordinary host memory.
+ *   - every call returns mppi_status_t; mppi_last_error(h) gives the text.
+ *   - there is NO CPU fallback: a non-sm_100 device is MPPI_ERR_WRONG_ARCH.
+ *   - noise layout is [T][K][nu] (the reference's sampler emits [K][T][nu],
+ *     sampling/standard_normal_noise.py:24; the caller transposes).
+ *   - one stepping thread per handle; mppi_set_state() may be called from another thread
+ *     (the rospy subscriber thread, kinova.py:106-116) -- it only touches a mutex-guarded
+ *     host staging slot that the next step snapshots.
+ */
+#ifndef MPPI_B200_H_
+#define MPPI_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPPI_ABI_VERSION 1
+#define MPPI_MAX_NU 12          /* controls per horizon step (whole body = 11)            */
+#define MPPI_MAX_HORIZON 256
+#define MPPI_MAX_JOINTS 8       /* revolute joints in the arm chain                      */
+#define MPPI_STATE_FLOATS 32    /* state vector slot, layout per model below             */
+#define MPPI_OUT_FLOATS 64      /* per-step outputs + statistics, layout below           */
+#define MPPI_MAX_SAVGOL 31
+
+typedef enum {
+    MPPI_OK = 0,
+    MPPI_ERR_INVALID_ARG = 1,
+    MPPI_ERR_WRONG_ARCH = 2,    /* device is not compute capability 10.x                 */
+    MPPI_ERR_CUDA = 3,
+    MPPI_ERR_UNSUPPORTED = 4
+} mppi_status_t;
+
+/* Models.  state[] / out[] layouts:
+ *  DRONE3 (drone_mppi.py, live nu=3 point mass): state = x[3], v[3]
+ *          out = x_des[3], v_des[3]                              (drone_mppi.py:169-170)
+ *  ARM7   (mppi.py, Kinova j2s7s300 nu=7):       state = q[7], qdot[7], base[7] (xyz + quat xyzw)
+ *          out = qdes[7], vdes[7]                                (mppi.py:157-158, incl. the
+ *                                                                 `_qddot * dt` term)
+ *  QUAD4  (rigid body nu=4; restated from the dead draft drone_mppi.py:57-83, PARITY UNPINNED):
+ *          state = p[3], rpy[3], v[3], w[3];  u = F, tau_xyz;  out = next state[12]
+ *  WB11   (whole body nu=11, not in the reference, PARITY UNPINNED):
+ *          state = p, rpy, v, w (12), q[7], qdot[7]; u = F, tau_xyz, qdd[7]
+ *          out = qdes[7], vdes[7]; out[16..27] = next base state[12]
+ *  Common tail of out[]: [28..39] u_new[0][:] (first updated control), [40..51] u_nom[0][:] (the
+ *  previous first control, i.e. the reference's `_qddot`), then the MPPI_OUT_* scalars below.  */
+typedef enum {
+    MPPI_MODEL_DRONE3 = 0,
+    MPPI_MODEL_ARM7 = 1,
+    MPPI_MODEL_QUAD4 = 2,
+    MPPI_MODEL_WB11 = 3
+} mppi_model_t;
+
+#define MPPI_OUT_BASE 16        /* WB11: next base state                                 */
+#define MPPI_OUT_U0_NEW 28
+#define MPPI_OUT_U0_OLD 40
+#define MPPI_OUT_REACH 52       /* ARM7/WB11: L1 position error of FK(qdes) to the target (check_reach, mppi.py:95-120) */
+#define MPPI_OUT_RHO 53         /* minimum cost                                          */
+#define MPPI_OUT_ETA 54         /* sum of unnormalised weights                           */
+#define MPPI_OUT_ESS 55         /* effective sample size (sum w)^2 / sum w^2             */
+#define MPPI_OUT_STEP 56        /* low 24 bits of the step counter used                  */
+
+/* Replaces the hard-coded constructor constants of mppi.py:37-42,75,
+ * sampling/standard_normal_noise.py:17, drone_mppi.py:16-19,32,34 and
+ * cost/cost_manager.py:30-33.  mppi_default_config() fills the reference's values.      */
+typedef struct mppi_config {
+    int32_t abi_version;        /* MPPI_ABI_VERSION                                      */
+    int32_t model;              /* mppi_model_t                                          */
+    int32_t n_samples;          /* K held by THIS handle (the local shard)               */
+    int32_t n_horizon;          /* T                                                     */
+    int32_t savgol_window;      /* odd; 9 arm/whole body, 5 drone/quad (mppi.py:149, drone_mppi.py:160) */
+    int32_t savgol_polyorder;   /* 2                                                     */
+    int32_t device;             /* CUDA device ordinal                                   */
+    int32_t n_joints;           /* revolute joints of the arm chain (7), see mppi_set_chain */
+    int64_t k_offset;           /* global index of this shard's first sample (Philox addressing) */
+    uint64_t seed;              /* Philox key                                            */
+    float dt;                   /* 0.01                                                  */
+    float lambda_;              /* 0.1                                                   */
+    float sigma[MPPI_MAX_NU];   /* per-input noise std (the reference's Sigma = sigma*I multiplies z: std = sigma) */
+    /* cost weights: ARM7/WB11 [0..3] = stage pos, stage ori, terminal pos, terminal ori
+     *               DRONE3/QUAD4 [4..5] = stage, terminal (squared distance); WB11 uses [0..5] */
+    float cost_w[8];
+    float quad_params[6];       /* mass, 1/Ixx, 1/Iyy, 1/Izz, k_d, g_z                   */
+    float target_pos[3];        /* mppi.py:71                                            */
+    float target_quat[4];       /* xyzw, mppi.py:72                                      */
+    float drone_target[3];      /* drone_mppi.py:141                                     */
+    float reserved[5];
+} mppi_config_t;
+
+typedef struct mppi_ctx *mppi_handle_t;
+
+/* Reference defaults for `model` (K, T, sigma, lambda, dt, weights, targets).           */
+mppi_status_t mppi_default_config(int32_t model, mppi_config_t *cfg);
+
+/* MPPI.__init__ (mppi.py:28-93 / drone_mppi.py:8-37): allocates every scratch buffer;
+ * nothing is allocated on the step path.                                                */
+mppi_status_t mppi_create(const mppi_config_t *cfg, mppi_handle_t *out);
+mppi_status_t mppi_destroy(mppi_handle_t h);
+const char *mppi_last_error(mppi_handle_t h);   /* h may be NULL: last create() error     */
+int32_t mppi_abi_version(void);
+
+/* URDFparser chain (robot/urdfparser.py:110-163) as constants: for each joint of the chain
+ * from the absolute root to the end link, in order: type (0 fixed, 1 revolute/continuous),
+ * origin xyz[3], origin rpy[3], axis[3].  The library folds it to  C0 Rz(q1) C1 ... Rz(qn) Cn.
+ * mppi_create() pre-loads the j2s7s300 chain of aerial_manipulator_gpu.urdf.            */
+mppi_status_t mppi_set_chain(mppi_handle_t h, int32_t n_chain_joints, const int32_t *types,
+                             const float *xyz, const float *rpy, const float *axis);
+
+/* Re-reads the mutable hyper-parameters of cfg (sigma, lambda_, dt, cost_w, quad_params); model,
+ * sizes, device, seed and k_offset are fixed at creation.                                */
+mppi_status_t mppi_update_config(mppi_handle_t h, const mppi_config_t *cfg);
+
+/* target_pose / hard-coded drone target (mppi.py:70-72, drone_mppi.py:141).             */
+mppi_status_t mppi_set_target(mppi_handle_t h, const float *target_pos, const float *target_quat_xyzw,
+                              const float *drone_target);
+
+/* update_joint (mppi.py:196-200) / set_state (drone_mppi.py:179-183): thread-safe staging of
+ * the measured state (host floats, layout per model); snapshotted at the next step.     */
+mppi_status_t mppi_set_state(mppi_handle_t h, const float *state_host, int32_t n);
+
+/* compute_control_input (mppi.py:122-169 / drone_mppi.py:140-176), device-pointer form.
+ *   d_u_nom  [T][nu]   nominal controls = u_prev (warm start, NOT shifted: SURVEY F4)
+ *   d_noise  [T][K][nu] injected noise, or NULL -> in-kernel Philox4x32-10(seed, step_counter)
+ *   d_cost_out [K] or NULL  per-sample costs S
+ *   d_u_new  [T][nu]   updated controls (may alias d_u_nom)
+ *   d_out    [MPPI_OUT_FLOATS] or NULL
+ * Asynchronous on `stream` (a cudaStream_t passed as void*).                             */
+mppi_status_t mppi_step(mppi_handle_t h, const float *d_u_nom, const float *d_noise,
+                        uint64_t step_counter, float *d_cost_out, float *d_u_new, float *d_out,
+                        void *stream);
+
+/* The same step split at the two points where K-sharded replicas exchange data:
+ *   mppi_rollout   : fused noise + rollout + cost -> S[K], local cost minimum
+ *   (allreduce-MIN over mppi_rho_ptr: one int32, order-preserving encoding of the float)
+ *   mppi_weight    : exp((rho-S)/lambda) weights, weighted-noise sums -> mppi_wsum_ptr
+ *   (allreduce-SUM over mppi_wsum_ptr: T*nu + 2 floats: sums, eta, sum of squared weights)
+ *   mppi_finalize  : normalise, Savitzky-Golay, u += w_eps, outputs                     */
+mppi_status_t mppi_rollout(mppi_handle_t h, const float *d_u_nom, const float *d_noise,
+                           uint64_t step_counter, float *d_cost_out, void *stream);
+mppi_status_t mppi_weight(mppi_handle_t h, const float *d_noise, uint64_t step_counter, void *stream);
+mppi_status_t mppi_finalize(mppi_handle_t h, const float *d_u_nom, uint64_t step_counter,
+                            float *d_u_new, float *d_out, void *stream);
+int32_t *mppi_rho_ptr(mppi_handle_t h);         /* device, 1 x int32                     */
+float *mppi_wsum_ptr(mppi_handle_t h);          /* device, mppi_wsum_count() floats      */
+int32_t mppi_wsum_count(mppi_handle_t h);
+float *mppi_cost_ptr(mppi_handle_t h);          /* device, S[K] of the last rollout      */
+
+/* Host-buffer form (what a non-torch caller uses; also the end-to-end timing path):
+ * copies state (if given) and u_inout to the device, steps, copies u_new / out / costs back
+ * and synchronises.  noise_host may be NULL (Philox).                                   */
+mppi_status_t mppi_step_host(mppi_handle_t h, const float *state_host, int32_t n_state,
+                             float *u_inout_host, const float *noise_host, uint64_t step_counter,
+                             float *cost_out_host, float *out_host);
+
+/* Writes the Philox noise of (seed, step_counter) for this shard to d_noise [T][K][nu]:
+ * the exact values the in-kernel generator uses (equivalence checks).                   */
+mppi_status_t mppi_generate_noise(mppi_handle_t h, uint64_t step_counter, float *d_noise, void *stream);
+
+/* Measured FP32 FFMA throughput of the device (TFLOP/s), the roofline denominator of the
+ * fused rollout kernel (MEASURED_PEAKS.json has no FP32 entry).                         */
+mppi_status_t mppi_measure_fp32_peak(int32_t device, float *tflops_out);
+
+/* Algorithmic FLOP per rollout-step (one sample, one horizon step) used for roofline.achieved
+ * (dense-constant derivation).                      */
+double mppi_algorithmic_flops_per_rollout_step(int32_t model);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPPI_B200_H_ */

@@ -647,14 +647,15 @@ void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t
 
 /* Box-Muller on two 32-bit words, same bit recipe as the device code:
  *   u1 = 2 - as_float(0x3f800000 | x>>9)  in (0,1];   r = sqrt(-2 ln u1)
- *   th = int32(y) * (pi / 2^31)           in [-pi,pi); (r cos th, r sin th)             */
+ *   th = (as_float(0x3f800000 | y>>9) - 1.5) * 2pi   in [-pi,pi); (r cos th, r sin th)  */
 static void box_muller(uint32_t x, uint32_t y, float *n0, float *n1)
 {
     union { uint32_t u; float f; } b;
     b.u = 0x3f800000u | (x >> 9);
     float u1 = 2.0f - b.f;
     float r = sqrtf(-2.0f * logf(u1));
-    float th = (float)(int32_t)y * 1.4629180792671596e-9f;
+    b.u = 0x3f800000u | (y >> 9);
+    float th = (b.f - 1.5f) * 6.28318530717958647692f;
     *n0 = r * cosf(th);
     *n1 = r * sinf(th);
 }

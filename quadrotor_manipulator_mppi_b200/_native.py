@@ -1,0 +1,133 @@
+"""ctypes binding of libmppi_b200.so (include/mppi_b200.h).
+
+There is no CPU fallback anywhere in this package: if the shared library is missing it
+is built with nvcc; if that is impossible, or if a call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+MPPI_MAX_NU = 12
+MPPI_STATE_FLOATS = 32
+MPPI_OUT_FLOATS = 64
+MPPI_OUT_BASE, MPPI_OUT_U0_NEW, MPPI_OUT_U0_OLD = 16, 28, 40
+MPPI_OUT_REACH, MPPI_OUT_RHO, MPPI_OUT_ETA, MPPI_OUT_ESS, MPPI_OUT_STEP = 52, 53, 54, 55, 56
+MODEL_DRONE3, MODEL_ARM7, MODEL_QUAD4, MODEL_WB11 = 0, 1, 2, 3
+MODEL_NU = {MODEL_DRONE3: 3, MODEL_ARM7: 7, MODEL_QUAD4: 4, MODEL_WB11: 11}
+MODEL_STATE = {MODEL_DRONE3: 6, MODEL_ARM7: 21, MODEL_QUAD4: 12, MODEL_WB11: 26}
+ABI_VERSION = 1
+
+EXPORTS = [
+    "mppi_abi_version", "mppi_last_error", "mppi_default_config", "mppi_create", "mppi_destroy",
+    "mppi_update_config", "mppi_set_chain", "mppi_set_target", "mppi_set_state", "mppi_step", "mppi_rollout", "mppi_weight",
+    "mppi_finalize", "mppi_rho_ptr", "mppi_wsum_ptr", "mppi_wsum_count", "mppi_cost_ptr",
+    "mppi_step_host", "mppi_generate_noise", "mppi_measure_fp32_peak",
+    "mppi_algorithmic_flops_per_rollout_step",
+]
+
+
+class MppiConfig(C.Structure):
+    """Mirror of mppi_config_t."""
+    _fields_ = [
+        ("abi_version", C.c_int32), ("model", C.c_int32), ("n_samples", C.c_int32), ("n_horizon", C.c_int32),
+        ("savgol_window", C.c_int32), ("savgol_polyorder", C.c_int32), ("device", C.c_int32), ("n_joints", C.c_int32),
+        ("k_offset", C.c_int64), ("seed", C.c_uint64),
+        ("dt", C.c_float), ("lambda_", C.c_float),
+        ("sigma", C.c_float * MPPI_MAX_NU), ("cost_w", C.c_float * 8), ("quad_params", C.c_float * 6),
+        ("target_pos", C.c_float * 3), ("target_quat", C.c_float * 4), ("drone_target", C.c_float * 3),
+        ("reserved", C.c_float * 5),
+    ]
+
+
+_lib = None
+_fp = C.POINTER(C.c_float)
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load():
+    """Load (building first if needed) the shared library and declare its prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if not os.path.exists(path):
+        _build.build()          # raises if nvcc is unavailable
+    lib = C.CDLL(path)
+    vp, u64, i32 = C.c_void_p, C.c_uint64, C.c_int32
+    lib.mppi_abi_version.restype = i32
+    lib.mppi_last_error.restype = C.c_char_p
+    lib.mppi_last_error.argtypes = [vp]
+    lib.mppi_default_config.argtypes = [i32, C.POINTER(MppiConfig)]
+    lib.mppi_create.argtypes = [C.POINTER(MppiConfig), C.POINTER(vp)]
+    lib.mppi_destroy.argtypes = [vp]
+    lib.mppi_update_config.argtypes = [vp, C.POINTER(MppiConfig)]
+    lib.mppi_set_chain.argtypes = [vp, i32, C.POINTER(i32), _fp, _fp, _fp]
+    lib.mppi_set_target.argtypes = [vp, _fp, _fp, _fp]
+    lib.mppi_set_state.argtypes = [vp, _fp, i32]
+    lib.mppi_step.argtypes = [vp, vp, vp, u64, vp, vp, vp, vp]
+    lib.mppi_rollout.argtypes = [vp, vp, vp, u64, vp, vp]
+    lib.mppi_weight.argtypes = [vp, vp, u64, vp]
+    lib.mppi_finalize.argtypes = [vp, vp, u64, vp, vp, vp]
+    lib.mppi_rho_ptr.restype = vp
+    lib.mppi_rho_ptr.argtypes = [vp]
+    lib.mppi_wsum_ptr.restype = vp
+    lib.mppi_wsum_ptr.argtypes = [vp]
+    lib.mppi_wsum_count.restype = i32
+    lib.mppi_wsum_count.argtypes = [vp]
+    lib.mppi_cost_ptr.restype = vp
+    lib.mppi_cost_ptr.argtypes = [vp]
+    lib.mppi_step_host.argtypes = [vp, _fp, i32, _fp, _fp, u64, _fp, _fp]
+    lib.mppi_generate_noise.argtypes = [vp, u64, vp, vp]
+    lib.mppi_measure_fp32_peak.argtypes = [i32, _fp]
+    lib.mppi_algorithmic_flops_per_rollout_step.restype = C.c_double
+    lib.mppi_algorithmic_flops_per_rollout_step.argtypes = [i32]
+    for name in EXPORTS:
+        if name not in ("mppi_abi_version", "mppi_last_error", "mppi_rho_ptr", "mppi_wsum_ptr", "mppi_wsum_count",
+                        "mppi_cost_ptr", "mppi_algorithmic_flops_per_rollout_step"):
+            getattr(lib, name).restype = i32
+    if lib.mppi_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"libmppi_b200.so ABI {lib.mppi_abi_version()} != binding ABI {ABI_VERSION}; rebuild")
+    _lib = lib
+    return lib
+
+
+class MppiError(RuntimeError):
+    pass
+
+
+_STATUS = {1: "invalid argument", 2: "wrong architecture (sm_100a only, no CPU fallback)", 3: "CUDA error",
+           4: "unsupported"}
+
+
+def check(rc: int, handle=None):
+    if rc != 0:
+        msg = load().mppi_last_error(handle)
+        raise MppiError(f"libmppi_b200: {_STATUS.get(rc, rc)}: {msg.decode() if msg else ''}")
+
+
+def default_config(model: int) -> MppiConfig:
+    cfg = MppiConfig()
+    check(load().mppi_default_config(model, C.byref(cfg)))
+    return cfg
+
+
+def fptr(np_array):
+    """float* of a C-contiguous float32 numpy array (kept alive by the caller)."""
+    return np_array.ctypes.data_as(_fp)
+
+
+def measure_fp32_peak(device: int = 0) -> float:
+    out = C.c_float()
+    check(load().mppi_measure_fp32_peak(device, C.byref(out)))
+    return float(out.value)
+
+
+def algorithmic_flops(model: int) -> float:
+    """Algorithmic FLOP per rollout-step; the single figure roofline.achieved uses."""
+    return float(load().mppi_algorithmic_flops_per_rollout_step(model))

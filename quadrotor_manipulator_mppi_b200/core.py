@@ -1,0 +1,192 @@
+"""NativeSolver: one MPPI shard on one B200, the object the drop-in classes wrap.
+
+It owns the library handle, the warm-start buffers and the step counter, and it is
+where the [K][T][nu] -> [T][K][nu] transpose of injected reference-layout noise lives
+(SURVEY F12).  All arithmetic is in libmppi_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+
+import numpy as np
+import torch
+
+from . import _native, ops
+
+
+class _DevView:
+    """Zero-copy torch view of library-owned device memory (via __cuda_array_interface__)."""
+
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def _require_cuda(device) -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("quadrotor_manipulator_mppi_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError(f"device {dev} is not CUDA; there is no CPU fallback")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+class NativeSolver:
+    def __init__(self, model: int, *, n_samples=None, n_horizon=None, dt=None, lam=None, sigma=None,
+                 seed: int = 0, device=None, k_offset: int = 0, savgol_window=None, cost_w=None,
+                 quad_params=None, target_pos=None, target_quat=None, drone_target=None):
+        self.device = _require_cuda(device)
+        self._lib = _native.load()
+        cfg = _native.default_config(model)
+        if n_samples is not None:
+            cfg.n_samples = int(n_samples)
+        if n_horizon is not None:
+            cfg.n_horizon = int(n_horizon)
+        if dt is not None:
+            cfg.dt = float(dt)
+        if lam is not None:
+            cfg.lambda_ = float(lam)
+        if savgol_window is not None:
+            cfg.savgol_window = int(savgol_window)
+        self.nu = _native.MODEL_NU[model]
+        if sigma is not None:
+            sig = np.broadcast_to(np.asarray(sigma, np.float32), (self.nu,))
+            for i in range(self.nu):
+                cfg.sigma[i] = float(sig[i])
+        for name, val in (("cost_w", cost_w), ("quad_params", quad_params), ("target_pos", target_pos),
+                          ("target_quat", target_quat), ("drone_target", drone_target)):
+            if val is not None:
+                arr = getattr(cfg, name)
+                for i, v in enumerate(val):
+                    arr[i] = float(v)
+        cfg.seed = int(seed) & (2 ** 64 - 1)
+        cfg.k_offset = int(k_offset)
+        cfg.device = self.device.index
+        self.cfg = cfg
+        self.model = model
+        self.K, self.T = cfg.n_samples, cfg.n_horizon
+        h = C.c_void_p()
+        _native.check(self._lib.mppi_create(C.byref(cfg), C.byref(h)))
+        self.handle = h.value
+        self.step_counter = 0
+        # warm start: two buffers, alternated so a caller holding last step's u_prev keeps valid data
+        self._u = [torch.zeros(self.T, self.nu, device=self.device), torch.zeros(self.T, self.nu, device=self.device)]
+        self._cur = 0
+        self._outs = [torch.zeros(_native.MPPI_OUT_FLOATS, device=self.device) for _ in range(4)]
+        self._out_i = 0
+        self._out_host = torch.zeros(_native.MPPI_OUT_FLOATS, pin_memory=True)
+        self._state_np = np.zeros(_native.MODEL_STATE[model], np.float32)
+        self._state_lock = threading.Lock()
+        self.costs = torch.as_tensor(_DevView(self._lib.mppi_cost_ptr(self.handle), self.K, "<f4"), device=self.device)
+        self.rho_enc = torch.as_tensor(_DevView(self._lib.mppi_rho_ptr(self.handle), 1, "<i4"), device=self.device)
+        self.wsum = torch.as_tensor(_DevView(self._lib.mppi_wsum_ptr(self.handle), self._lib.mppi_wsum_count(self.handle),
+                                             "<f4"), device=self.device)
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self):
+        if getattr(self, "handle", None):
+            self._lib.mppi_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ state / warm start
+    @property
+    def u_prev(self) -> torch.Tensor:
+        return self._u[self._cur]
+
+    @u_prev.setter
+    def u_prev(self, value):
+        t = torch.as_tensor(value, dtype=torch.float32).to(self.device)
+        if tuple(t.shape) != (self.T, self.nu):
+            raise ValueError(f"u_prev must have shape {(self.T, self.nu)}, got {tuple(t.shape)}")
+        self._u[self._cur].copy_(t)
+
+    def set_state(self, state) -> None:
+        """Thread-safe: may be called from a subscriber thread while another thread steps."""
+        st = np.ascontiguousarray(state, dtype=np.float32).reshape(-1)
+        with self._state_lock:
+            self._state_np[:] = st      # raises on a length mismatch
+            _native.check(self._lib.mppi_set_state(self.handle, _native.fptr(self._state_np), st.size), self.handle)
+
+    def set_target(self, pos=None, quat=None, drone_target=None) -> None:
+        def p(v, n):
+            if v is None:
+                return None
+            a = np.ascontiguousarray(np.asarray(v, np.float32).reshape(-1))
+            assert a.size == n
+            return a
+        a, b, c = p(pos, 3), p(quat, 4), p(drone_target, 3)
+        _native.check(self._lib.mppi_set_target(self.handle, None if a is None else _native.fptr(a),
+                                                None if b is None else _native.fptr(b),
+                                                None if c is None else _native.fptr(c)), self.handle)
+
+    def set_chain(self, types, xyz, rpy, axis) -> None:
+        t = np.ascontiguousarray(types, np.int32)
+        x, r, a = (np.ascontiguousarray(v, np.float32).reshape(-1, 3) for v in (xyz, rpy, axis))
+        _native.check(self._lib.mppi_set_chain(self.handle, int(t.size), t.ctypes.data_as(C.POINTER(C.c_int32)),
+                                               _native.fptr(x), _native.fptr(r), _native.fptr(a)), self.handle)
+
+    # ------------------------------------------------------------------ noise
+    def prepare_noise(self, noise, layout: str = "tkn"):
+        """Injected noise -> contiguous float32 [T][K][nu] on the device ("ktn" = reference layout)."""
+        if noise is None:
+            return None
+        n = torch.as_tensor(noise, dtype=torch.float32).to(self.device)
+        if layout == "ktn":
+            n = n.permute(1, 0, 2)
+        elif layout != "tkn":
+            raise ValueError("layout must be 'tkn' or 'ktn'")
+        if tuple(n.shape) != (self.T, self.K, self.nu):
+            raise ValueError(f"noise must be [T={self.T}][K={self.K}][nu={self.nu}], got {tuple(n.shape)}")
+        return n.contiguous()
+
+    def generate_noise(self, step_counter=None) -> torch.Tensor:
+        """The Philox noise the in-kernel generator uses for `step_counter`, as [T][K][nu]."""
+        out = torch.empty(self.T, self.K, self.nu, device=self.device)
+        ops.generate_noise(self.handle, self.step_counter if step_counter is None else int(step_counter), out)
+        return out
+
+    # ------------------------------------------------------------------ stepping
+    def step_async(self, noise=None, step_counter=None) -> torch.Tensor:
+        """One control step, asynchronous on the current stream.  Returns the device `out` vector."""
+        sc = self.step_counter if step_counter is None else int(step_counter)
+        nxt = self._cur ^ 1
+        out = self._outs[self._out_i]
+        self._out_i = (self._out_i + 1) & 3
+        ops.step(self.handle, self._u[self._cur], noise, sc, self._u[nxt], out, None)
+        self._cur = nxt
+        self.step_counter = sc + 1
+        return out
+
+    def step(self, noise=None, step_counter=None) -> np.ndarray:
+        """One control step; returns the `out` vector on the host (pinned copy + stream sync)."""
+        out = self.step_async(noise, step_counter)
+        self._out_host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self._out_host.numpy()
+
+    # ---- the three phases, for K-sharded replicas (see sharded.py)
+    def rollout(self, noise=None, step_counter=None):
+        sc = self.step_counter if step_counter is None else int(step_counter)
+        ops.rollout(self.handle, self._u[self._cur], noise, sc, None)
+
+    def weight(self, noise=None, step_counter=None):
+        sc = self.step_counter if step_counter is None else int(step_counter)
+        ops.weight(self.handle, noise, sc, self.device)
+
+    def finalize(self, step_counter=None) -> torch.Tensor:
+        sc = self.step_counter if step_counter is None else int(step_counter)
+        nxt = self._cur ^ 1
+        out = self._outs[self._out_i]
+        self._out_i = (self._out_i + 1) & 3
+        ops.finalize(self.handle, self._u[self._cur], sc, self._u[nxt], out)
+        self._cur = nxt
+        self.step_counter = sc + 1
+        return out

@@ -1,0 +1,669 @@
+// mppi_b200.cu -- C ABI (include/mppi_b200.h) over the sm_100a kernels.
+//
+// Build:  nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+//         (see quadrotor_manipulator_mppi_b200/build.py).  No CPU path exists in this file: every entry point
+// either launches on the device or returns an error.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "mppi_kernels.cuh"
+
+using namespace mppi;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Mat4 { double m[16]; };
+
+Mat4 mat4_identity() { Mat4 r{}; r.m[0] = r.m[5] = r.m[10] = r.m[15] = 1.0; return r; }
+Mat4 mat4_mul(const Mat4 &a, const Mat4 &b)
+{
+    Mat4 r{};
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            double acc = 0.0;
+            for (int k = 0; k < 4; ++k) acc += a.m[4 * i + k] * b.m[4 * k + j];
+            r.m[4 * i + j] = acc;
+        }
+    return r;
+}
+Mat4 mat4_transpose_rot(const Mat4 &a)   // inverse of a pure rotation
+{
+    Mat4 r = mat4_identity();
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) r.m[4 * i + j] = a.m[4 * j + i];
+    return r;
+}
+// URDF origin -> homogeneous transform, R = Rz(yaw) Ry(pitch) Rx(roll) (robot/transformation_matrix.py:4-35).
+// The reference evaluates sin/cos on float32-rounded rpy, so e.g. cos(pi/2) is -4.37e-8, not 0:
+// the same residues are kept here by rounding the inputs to float first.
+Mat4 origin_transform(const float *xyz, const float *rpy)
+{
+    const double r = rpy[0], p = rpy[1], y = rpy[2];
+    const double cr = std::cos(r), sr = std::sin(r), cp = std::cos(p), sp = std::sin(p), cy = std::cos(y), sy = std::sin(y);
+    Mat4 T = mat4_identity();
+    T.m[0] = cy * cp; T.m[1] = cy * sp * sr - sy * cr; T.m[2] = cy * sp * cr + sy * sr; T.m[3] = xyz[0];
+    T.m[4] = sy * cp; T.m[5] = sy * sp * sr + cy * cr; T.m[6] = sy * sp * cr - cy * sr; T.m[7] = xyz[1];
+    T.m[8] = -sp;     T.m[9] = cp * sr;                T.m[10] = cp * cr;               T.m[11] = xyz[2];
+    return T;
+}
+// Rotation A with A z = axis (unit).  Rot(axis, q) = A Rz(q) A^T.
+Mat4 align_z_to(const double ax[3])
+{
+    Mat4 A = mat4_identity();
+    const double c = ax[2];
+    if (c > 1.0 - 1e-14) return A;
+    if (c < -1.0 + 1e-14) { A.m[5] = -1.0; A.m[10] = -1.0; return A; }   // pi about x
+    const double vx = -ax[1], vy = ax[0];          // z cross axis
+    const double k = 1.0 / (1.0 + c);
+    A.m[0] = 1.0 - k * vy * vy;  A.m[1] = k * vx * vy;        A.m[2] = vy;
+    A.m[4] = k * vx * vy;        A.m[5] = 1.0 - k * vx * vx;  A.m[6] = -vx;
+    A.m[8] = -vy;                A.m[9] = vx;                 A.m[10] = 1.0 - k * (vx * vx + vy * vy);
+    return A;
+}
+
+// j2s7s300 chain of aerial_manipulation/urdf/aerial_manipulator_gpu.urdf, world -> link_7
+// (:67-74 fixed joint_base, :100-106 ... :358-364 joint_1..7).  These are the URDF's numbers.
+constexpr double kPiD = 3.141592653589793, kHalfPiD = 1.5707963267948966;
+const int32_t kKinovaTypes[8] = {0, 1, 1, 1, 1, 1, 1, 1};
+const float kKinovaXyz[8][3] = {{0, 0, 0}, {0, 0, 0.15675f}, {0, 0.0016f, -0.11875f}, {0, -0.205f, 0}, {0, 0, -0.205f},
+                                {0, 0.2073f, -0.0114f}, {0, 0, -0.10375f}, {0, 0.10375f, 0}};
+const float kKinovaRpy[8][3] = {{(float)kPiD, 0, 0}, {0, (float)kPiD, 0}, {(float)-kHalfPiD, 0, (float)kPiD}, {(float)-kHalfPiD, 0, 0},
+                                {(float)kHalfPiD, 0, (float)kPiD}, {(float)-kHalfPiD, 0, (float)kPiD},
+                                {(float)kHalfPiD, 0, (float)kPiD}, {(float)-kHalfPiD, 0, (float)kPiD}};
+const float kKinovaAxis[8][3] = {{0, 0, 0}, {0, 0, 1}, {0, 0, 1}, {0, 0, 1}, {0, 0, 1}, {0, 0, 1}, {0, 0, 1}, {0, 0, 1}};
+
+int model_nu(int model)
+{
+    switch (model) {
+        case MPPI_MODEL_DRONE3: return 3;
+        case MPPI_MODEL_ARM7: return 7;
+        case MPPI_MODEL_QUAD4: return 4;
+        case MPPI_MODEL_WB11: return 11;
+        default: return -1;
+    }
+}
+int model_state_floats(int model)
+{
+    switch (model) {
+        case MPPI_MODEL_DRONE3: return 6;
+        case MPPI_MODEL_ARM7: return 21;
+        case MPPI_MODEL_QUAD4: return 12;
+        case MPPI_MODEL_WB11: return 26;
+        default: return -1;
+    }
+}
+
+// Savitzky-Golay smoothing taps: row 0 of (A^T A)^-1 A^T (filter/svg_filter.py:52-55), in double.
+bool savgol_taps(int window, int polyorder, float *taps)
+{
+    const int h = window / 2, n = polyorder + 1;
+    if (window % 2 != 1 || window > MPPI_MAX_SAVGOL || polyorder >= window || n > 6 || window < 1) return false;
+    double M[6][12];
+    for (int r = 0; r < n; ++r)
+        for (int c = 0; c < n; ++c) {
+            double acc = 0.0;
+            for (int x = -h; x <= h; ++x) acc += std::pow((double)x, r) * std::pow((double)x, c);
+            M[r][c] = acc; M[r][n + c] = (r == c) ? 1.0 : 0.0;
+        }
+    for (int p = 0; p < n; ++p) {
+        int best = p;
+        for (int r = p + 1; r < n; ++r) if (std::fabs(M[r][p]) > std::fabs(M[best][p])) best = r;
+        if (std::fabs(M[best][p]) < 1e-300) return false;
+        if (best != p) for (int c = 0; c < 2 * n; ++c) std::swap(M[p][c], M[best][c]);
+        const double piv = M[p][p];
+        for (int c = 0; c < 2 * n; ++c) M[p][c] /= piv;
+        for (int r = 0; r < n; ++r) if (r != p) {
+            const double f = M[r][p];
+            for (int c = 0; c < 2 * n; ++c) M[r][c] -= f * M[p][c];
+        }
+    }
+    for (int x = -h; x <= h; ++x) {
+        double acc = 0.0;
+        for (int c = 0; c < n; ++c) acc += M[0][n + c] * std::pow((double)x, c);
+        taps[x + h] = (float)acc;
+    }
+    return true;
+}
+
+}  // namespace
+
+struct mppi_ctx {
+    mppi_config_t cfg{};
+    StepParams P{};
+    DynBlock dyn{};                 // host copy; passed by value at launch
+    std::mutex state_mu;            // guards staged_state (set_state may come from another thread)
+    float staged_state[MPPI_STATE_FLOATS]{};
+    int nu = 0;
+    int num_sms = 148;
+    // device scratch (allocated once in mppi_create)
+    float *d_cost = nullptr;        // [K]
+    int32_t *d_rho = nullptr;       // order-preserving min (signed int32 encoding)
+    uint32_t *d_counter = nullptr;  // last-block-done counter
+    float *d_part = nullptr;        // [max_parts][T*nu+2]
+    float *d_wsum = nullptr;        // [T*nu+2]
+    float *d_u = nullptr;           // [T*nu]   (host-buffer API)
+    float *d_out = nullptr;         // [MPPI_OUT_FLOATS]
+    float *d_noise = nullptr;       // host-buffer API with injected noise, grown on demand
+    size_t d_noise_bytes = 0;
+    float *h_pinned = nullptr;      // pinned staging for the host-buffer API
+    size_t h_pinned_floats = 0;
+    int max_parts = 0;
+    cudaStream_t own_stream = nullptr;
+    std::string err;
+};
+
+namespace {
+
+mppi_status_t fail(mppi_handle_t h, mppi_status_t code, const std::string &msg)
+{
+    if (h) h->err = msg; else g_create_error = msg;
+    return code;
+}
+#define MPPI_CUDA(h, call)                                                                             \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess)                                                                         \
+            return fail(h, MPPI_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));        \
+    } while (0)
+
+void set_target_locked(mppi_ctx *h, const float *pos, const float *quat, const float *drone_target)
+{
+    if (pos) for (int i = 0; i < 3; ++i) { h->cfg.target_pos[i] = pos[i]; h->dyn.target_pos[i] = pos[i]; }
+    if (quat) {
+        // quaternion_to_matrix, xyzw, normalising through two_s (utils/rotation_conversions.py:45-75)
+        for (int i = 0; i < 4; ++i) h->cfg.target_quat[i] = quat[i];
+        const float i = quat[0], j = quat[1], k = quat[2], r = quat[3];
+        const float two_s = 2.0f / (i * i + j * j + k * k + r * r);
+        float *R = h->dyn.target_R;
+        R[0] = 1.0f - two_s * (j * j + k * k); R[1] = two_s * (i * j - k * r); R[2] = two_s * (i * k + j * r);
+        R[3] = two_s * (i * j + k * r); R[4] = 1.0f - two_s * (i * i + k * k); R[5] = two_s * (j * k - i * r);
+        R[6] = two_s * (i * k - j * r); R[7] = two_s * (j * k + i * r); R[8] = 1.0f - two_s * (i * i + j * j);
+    }
+    if (drone_target) for (int i = 0; i < 3; ++i) { h->cfg.drone_target[i] = drone_target[i]; h->dyn.drone_target[i] = drone_target[i]; }
+}
+
+mppi_status_t set_chain_impl(mppi_ctx *h, int n, const int32_t *types, const float *xyz, const float *rpy, const float *axis)
+{
+    ChainDev ch{};
+    Mat4 C = mat4_identity();
+    int nrev = 0;
+    for (int j = 0; j < n; ++j) {
+        C = mat4_mul(C, origin_transform(xyz + 3 * j, rpy + 3 * j));
+        if (types[j] == 0) continue;
+        if (types[j] != 1) return fail(h, MPPI_ERR_UNSUPPORTED, "only fixed and revolute/continuous joints are supported");
+        if (nrev >= MPPI_MAX_JOINTS) return fail(h, MPPI_ERR_INVALID_ARG, "too many revolute joints");
+        double ax[3] = {axis[3 * j], axis[3 * j + 1], axis[3 * j + 2]};
+        double nrm = std::sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);
+        if (nrm < 1e-12) { ax[0] = 1; ax[1] = 0; ax[2] = 0; nrm = 1; }    // transformation_matrix.py:63-66
+        for (double &a : ax) a /= nrm;
+        const Mat4 A = align_z_to(ax);
+        C = mat4_mul(C, A);
+        for (int r = 0; r < 3; ++r) {
+            for (int c = 0; c < 3; ++c) ch.R[nrev][3 * r + c] = (float)C.m[4 * r + c];
+            ch.t[nrev][r] = (float)C.m[4 * r + 3];
+        }
+        ++nrev;
+        C = mat4_transpose_rot(A);
+    }
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) ch.R[nrev][3 * r + c] = (float)C.m[4 * r + c];
+        ch.t[nrev][r] = (float)C.m[4 * r + 3];
+    }
+    double dev = 0.0;
+    const Mat4 I = mat4_identity();
+    for (int i = 0; i < 16; ++i) dev = std::fmax(dev, std::fabs(C.m[i] - I.m[i]));
+    ch.n = nrev;
+    ch.last_identity = dev < 1e-12;
+    if (nrev != 7) return fail(h, MPPI_ERR_UNSUPPORTED, "the arm kernels are built for 7 revolute joints");
+    h->P.chain = ch;
+    return MPPI_OK;
+}
+
+template <int MODEL>
+mppi_status_t launch_rollout(mppi_ctx *h, const float *d_u_nom, const float *d_noise, float *d_cost, cudaStream_t st)
+{
+    constexpr int NU = ModelNu<MODEL>::value;
+    const int grid = (h->P.K + kRolloutThreads - 1) / kRolloutThreads;
+    const size_t smem = (size_t)h->P.T * NU * sizeof(float);
+    if (d_noise)
+        rollout_cost_kernel<MODEL, false><<<grid, kRolloutThreads, smem, st>>>(h->P, h->dyn, d_u_nom, d_noise, d_cost, h->d_rho);
+    else
+        rollout_cost_kernel<MODEL, true><<<grid, kRolloutThreads, smem, st>>>(h->P, h->dyn, d_u_nom, nullptr, d_cost, h->d_rho);
+    MPPI_CUDA(h, cudaGetLastError());
+    return MPPI_OK;
+}
+
+template <int MODEL>
+mppi_status_t launch_weight(mppi_ctx *h, const float *d_noise, bool fuse, const float *d_u_nom, float *d_u_new,
+                            float *d_out, cudaStream_t st)
+{
+    constexpr int NU = ModelNu<MODEL>::value;
+    constexpr int NCH = (NU + 3) / 4;
+    const int K = h->P.K, T = h->P.T;
+    const size_t fin_floats = (size_t)2 * T * NU + NU;
+    if (!d_noise) {
+        const int TC = T * NCH;
+        int R = 512 / TC;
+        if (R < 1) R = 1;
+        int threads = ((TC * R + 31) / 32) * 32;
+        if (threads > 1024) return fail(h, MPPI_ERR_UNSUPPORTED, "horizon too long for the Philox weighting kernel");
+        int blocks = (K + 255) / 256;
+        if (blocks > 2 * h->num_sms) blocks = 2 * h->num_sms;
+        if (blocks > h->max_parts) blocks = h->max_parts;
+        if (blocks < 1) blocks = 1;
+        const int chunk = (K + blocks - 1) / blocks;
+        blocks = (K + chunk - 1) / chunk;
+        size_t smem_floats = (size_t)kWeightTile + (size_t)R * TC * 4;
+        if (smem_floats < fin_floats) smem_floats = fin_floats;
+        weight_philox_kernel<MODEL><<<blocks, threads, smem_floats * sizeof(float), st>>>(
+            h->P, h->dyn, h->d_cost, h->d_rho, chunk, h->d_part, h->d_counter, h->d_wsum, fuse ? 1 : 0, d_u_nom, d_u_new, d_out);
+    } else {
+        const bool vec4 = ((size_t)K * NU) % 4 == 0 && (reinterpret_cast<uintptr_t>(d_noise) & 15u) == 0;
+        int chunk = 4096;
+        while (chunk > 128 && (long long)((K + chunk - 1) / chunk) * T < 4LL * h->num_sms) chunk >>= 1;
+        int blocks = (K + chunk - 1) / chunk;
+        if (blocks > h->max_parts) { chunk = ((K + h->max_parts - 1) / h->max_parts + 127) / 128 * 128; blocks = (K + chunk - 1) / chunk; }
+        size_t smem_floats = (size_t)chunk;
+        if (smem_floats < (size_t)32 * NU * 4) smem_floats = (size_t)32 * NU * 4;
+        if (smem_floats < fin_floats) smem_floats = fin_floats;
+        if (smem_floats * sizeof(float) > 48 * 1024) return fail(h, MPPI_ERR_UNSUPPORTED, "weighting scratch exceeds 48 KB of shared memory");
+        dim3 grid(blocks, T);
+        if (vec4)
+            weight_injected_kernel<MODEL, 4><<<grid, 32 * NU, smem_floats * sizeof(float), st>>>(
+                h->P, h->dyn, h->d_cost, d_noise, h->d_rho, chunk, h->d_part, h->d_counter, h->d_wsum, fuse ? 1 : 0, d_u_nom, d_u_new, d_out);
+        else
+            weight_injected_kernel<MODEL, 1><<<grid, 32 * NU, smem_floats * sizeof(float), st>>>(
+                h->P, h->dyn, h->d_cost, d_noise, h->d_rho, chunk, h->d_part, h->d_counter, h->d_wsum, fuse ? 1 : 0, d_u_nom, d_u_new, d_out);
+    }
+    MPPI_CUDA(h, cudaGetLastError());
+    return MPPI_OK;
+}
+
+template <int MODEL>
+mppi_status_t launch_finalize(mppi_ctx *h, const float *d_u_nom, float *d_u_new, float *d_out, cudaStream_t st)
+{
+    constexpr int NU = ModelNu<MODEL>::value;
+    const size_t smem = ((size_t)2 * h->P.T * NU + NU) * sizeof(float);
+    finalize_kernel<MODEL><<<1, 256, smem, st>>>(h->P, h->dyn, h->d_wsum, d_u_nom, d_u_new, d_out, h->d_rho);
+    MPPI_CUDA(h, cudaGetLastError());
+    return MPPI_OK;
+}
+
+#define MPPI_DISPATCH(h, fn, ...)                                                      \
+    switch ((h)->cfg.model) {                                                          \
+        case MPPI_MODEL_DRONE3: return fn<MPPI_MODEL_DRONE3>(__VA_ARGS__);             \
+        case MPPI_MODEL_ARM7:   return fn<MPPI_MODEL_ARM7>(__VA_ARGS__);               \
+        case MPPI_MODEL_QUAD4:  return fn<MPPI_MODEL_QUAD4>(__VA_ARGS__);              \
+        case MPPI_MODEL_WB11:   return fn<MPPI_MODEL_WB11>(__VA_ARGS__);               \
+        default: return fail(h, MPPI_ERR_INVALID_ARG, "unknown model");                \
+    }
+
+// Snapshot the staged state + step counter into the by-value dynamic block.
+void snapshot(mppi_ctx *h, uint64_t step_counter)
+{
+    {
+        std::lock_guard<std::mutex> lk(h->state_mu);
+        std::memcpy(h->dyn.state, h->staged_state, sizeof(h->dyn.state));
+    }
+    h->dyn.step_lo = (uint32_t)step_counter;
+    h->dyn.step_hi = (uint32_t)(step_counter >> 32);
+}
+
+mppi_status_t rollout_dispatch(mppi_ctx *h, const float *u, const float *n, float *c, cudaStream_t st) { MPPI_DISPATCH(h, launch_rollout, h, u, n, c, st) }
+mppi_status_t weight_dispatch(mppi_ctx *h, const float *n, bool fuse, const float *u, float *un, float *o, cudaStream_t st) { MPPI_DISPATCH(h, launch_weight, h, n, fuse, u, un, o, st) }
+mppi_status_t finalize_dispatch(mppi_ctx *h, const float *u, float *un, float *o, cudaStream_t st) { MPPI_DISPATCH(h, launch_finalize, h, u, un, o, st) }
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+}  // namespace
+
+// ============================================================================ C ABI
+extern "C" {
+
+int32_t mppi_abi_version(void) { return MPPI_ABI_VERSION; }
+
+const char *mppi_last_error(mppi_handle_t h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+mppi_status_t mppi_default_config(int32_t model, mppi_config_t *cfg)
+{
+    if (!cfg || model_nu(model) < 0) return fail(nullptr, MPPI_ERR_INVALID_ARG, "bad model / null config");
+    std::memset(cfg, 0, sizeof(*cfg));
+    cfg->abi_version = MPPI_ABI_VERSION;
+    cfg->model = model;
+    cfg->dt = 0.01f;                 // mppi.py:42, drone_mppi.py:18
+    cfg->lambda_ = 0.1f;             // mppi.py:75, drone_mppi.py:34
+    cfg->savgol_polyorder = 2;
+    cfg->n_joints = 7;
+    const float arm_w[4] = {50.f, 30.f, 40.f, 30.f};     // cost/cost_manager.py:30-33
+    const float tp[3] = {0.1029f, 0.4055f, 1.6498f};     // mppi.py:71
+    const float tq[4] = {-0.5f, -0.5f, 0.5f, -0.5f};     // mppi.py:72 (xyzw)
+    const float dtg[3] = {1.0f, 2.0f, 3.4f};             // drone_mppi.py:141
+    std::memcpy(cfg->target_pos, tp, sizeof(tp));
+    std::memcpy(cfg->target_quat, tq, sizeof(tq));
+    std::memcpy(cfg->drone_target, dtg, sizeof(dtg));
+    std::memcpy(cfg->cost_w, arm_w, sizeof(arm_w));
+    cfg->cost_w[4] = 100.f; cfg->cost_w[5] = 20.f;        // drone_mppi.py:93,105
+    // aerial_manipulation/src/controller.cpp:159-161,488-490; k_d is undefined in the draft -> 0
+    const float qp[6] = {14.7f, 1.0f / 1.57f, 1.0f / 3.93f, 1.0f / 2.59f, 0.0f, -9.81f};
+    std::memcpy(cfg->quad_params, qp, sizeof(qp));
+    switch (model) {
+        case MPPI_MODEL_DRONE3:
+            cfg->n_samples = 1000; cfg->n_horizon = 32; cfg->savgol_window = 5;       // drone_mppi.py:16-17,160
+            for (int i = 0; i < 3; ++i) cfg->sigma[i] = 30.0f;                        // drone_mppi.py:32
+            break;
+        case MPPI_MODEL_ARM7:
+            cfg->n_samples = 100; cfg->n_horizon = 32; cfg->savgol_window = 9;        // mppi.py:40-41,149
+            for (int i = 0; i < 7; ++i) cfg->sigma[i] = 0.1f;                         // standard_normal_noise.py:17
+            break;
+        case MPPI_MODEL_QUAD4:
+            cfg->n_samples = 1000; cfg->n_horizon = 32; cfg->savgol_window = 5;
+            cfg->sigma[0] = 30.0f * 14.7f;                                            // acceleration std 30 -> thrust
+            cfg->sigma[1] = cfg->sigma[2] = cfg->sigma[3] = 1.0f;
+            break;
+        case MPPI_MODEL_WB11:
+            cfg->n_samples = 1000; cfg->n_horizon = 32; cfg->savgol_window = 9;
+            cfg->quad_params[0] = 14.7f + 5.5f;                                       // controller.cpp:159
+            cfg->sigma[0] = 30.0f * (14.7f + 5.5f);
+            cfg->sigma[1] = cfg->sigma[2] = cfg->sigma[3] = 1.0f;
+            for (int i = 4; i < 11; ++i) cfg->sigma[i] = 0.1f;
+            break;
+    }
+    return MPPI_OK;
+}
+
+mppi_status_t mppi_create(const mppi_config_t *cfg, mppi_handle_t *out)
+{
+    if (!cfg || !out) return fail(nullptr, MPPI_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    if (cfg->abi_version != MPPI_ABI_VERSION) return fail(nullptr, MPPI_ERR_INVALID_ARG, "abi_version mismatch");
+    const int nu = model_nu(cfg->model);
+    if (nu < 0) return fail(nullptr, MPPI_ERR_INVALID_ARG, "unknown model");
+    if (cfg->n_samples < 1 || cfg->n_samples > (1 << 26)) return fail(nullptr, MPPI_ERR_INVALID_ARG, "n_samples out of range [1, 2^26]");
+    if (cfg->n_horizon < 1 || cfg->n_horizon > MPPI_MAX_HORIZON) return fail(nullptr, MPPI_ERR_INVALID_ARG, "n_horizon out of range [1, 256]");
+    if (!(cfg->dt > 0.f) || !(cfg->lambda_ > 0.f)) return fail(nullptr, MPPI_ERR_INVALID_ARG, "dt and lambda must be positive");
+    if (cfg->n_horizon <= cfg->savgol_window / 2)      // svg_filter.py:47-48 raises for the same condition
+        return fail(nullptr, MPPI_ERR_INVALID_ARG, "horizon shorter than the Savitzky-Golay padding");
+    float taps[MPPI_MAX_SAVGOL];
+    if (!savgol_taps(cfg->savgol_window, cfg->savgol_polyorder, taps))
+        return fail(nullptr, MPPI_ERR_INVALID_ARG, "bad Savitzky-Golay window / polyorder");
+
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(nullptr, MPPI_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(ce) + " (there is no CPU fallback)");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, MPPI_ERR_INVALID_ARG, "device ordinal out of range");
+    cudaDeviceProp prop{};
+    ce = cudaGetDeviceProperties(&prop, cfg->device);
+    if (ce != cudaSuccess) return fail(nullptr, MPPI_ERR_CUDA, cudaGetErrorString(ce));
+    if (prop.major != 10)
+        return fail(nullptr, MPPI_ERR_WRONG_ARCH, std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
+                                                      std::to_string(prop.minor) + "; this library is built for sm_100a only");
+
+    mppi_ctx *h = new (std::nothrow) mppi_ctx();
+    if (!h) return fail(nullptr, MPPI_ERR_CUDA, "out of host memory");
+    h->cfg = *cfg;
+    h->nu = nu;
+    h->num_sms = prop.multiProcessorCount;
+    StepParams &P = h->P;
+    P.K = cfg->n_samples; P.T = cfg->n_horizon; P.nu = nu; P.nch = (nu + 3) / 4;
+    P.k_offset = cfg->k_offset;
+    P.seed_lo = (uint32_t)cfg->seed; P.seed_hi = (uint32_t)(cfg->seed >> 32);
+    P.dt = cfg->dt;
+    P.dt2 = (float)((double)cfg->dt * (double)cfg->dt);        // python dt**2 on floats
+    P.inv_lambda = (float)(1.0 / (double)cfg->lambda_);        // (-1.0 / _lambda), mppi.py:187
+    P.sg_window = cfg->savgol_window; P.sg_half = cfg->savgol_window / 2;
+    std::memcpy(P.sigma, cfg->sigma, sizeof(P.sigma));
+    std::memcpy(P.cost_w, cfg->cost_w, sizeof(P.cost_w));
+    std::memcpy(P.quad, cfg->quad_params, sizeof(P.quad));
+    std::memcpy(P.taps, taps, sizeof(taps));
+    set_target_locked(h, cfg->target_pos, cfg->target_quat, cfg->drone_target);
+    if (set_chain_impl(h, 8, kKinovaTypes, &kKinovaXyz[0][0], &kKinovaRpy[0][0], &kKinovaAxis[0][0]) != MPPI_OK) {
+        g_create_error = h->err; delete h; return MPPI_ERR_INVALID_ARG;
+    }
+    // identity attitude for the default base quaternion (arm) so a step before set_state is well defined
+    if (cfg->model == MPPI_MODEL_ARM7) h->staged_state[20] = 1.0f;
+
+    DeviceGuard guard(cfg->device);
+    const size_t row = (size_t)P.T * nu + 2;
+    h->max_parts = 4 * h->num_sms > 1024 ? 4 * h->num_sms : 1024;
+    auto cleanup = [&](cudaError_t e, const char *what) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(e);
+        mppi_destroy(h);
+        return MPPI_ERR_CUDA;
+    };
+    cudaError_t e;
+    if ((e = cudaMalloc(&h->d_cost, (size_t)P.K * sizeof(float))) != cudaSuccess) return cleanup(e, "cudaMalloc(cost)");
+    if ((e = cudaMalloc(&h->d_rho, 16)) != cudaSuccess) return cleanup(e, "cudaMalloc(rho)");
+    h->d_counter = reinterpret_cast<uint32_t *>(h->d_rho + 1);
+    if ((e = cudaMalloc(&h->d_part, (size_t)h->max_parts * row * sizeof(float))) != cudaSuccess) return cleanup(e, "cudaMalloc(partials)");
+    if ((e = cudaMalloc(&h->d_wsum, row * sizeof(float))) != cudaSuccess) return cleanup(e, "cudaMalloc(wsum)");
+    if ((e = cudaMalloc(&h->d_u, (size_t)P.T * nu * sizeof(float))) != cudaSuccess) return cleanup(e, "cudaMalloc(u)");
+    if ((e = cudaMalloc(&h->d_out, MPPI_OUT_FLOATS * sizeof(float))) != cudaSuccess) return cleanup(e, "cudaMalloc(out)");
+    h->h_pinned_floats = (size_t)P.T * nu + MPPI_OUT_FLOATS;
+    if ((e = cudaMallocHost(&h->h_pinned, h->h_pinned_floats * sizeof(float))) != cudaSuccess) return cleanup(e, "cudaMallocHost");
+    if ((e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return cleanup(e, "cudaStreamCreate");
+    const int32_t init[4] = {kRhoInit, 0, 0, 0};
+    if ((e = cudaMemcpy(h->d_rho, init, sizeof(init), cudaMemcpyHostToDevice)) != cudaSuccess) return cleanup(e, "cudaMemcpy(init)");
+    if ((e = cudaMemset(h->d_out, 0, MPPI_OUT_FLOATS * sizeof(float))) != cudaSuccess) return cleanup(e, "cudaMemset(out)");
+    *out = h;
+    return MPPI_OK;
+}
+
+mppi_status_t mppi_destroy(mppi_handle_t h)
+{
+    if (!h) return MPPI_OK;
+    {
+        DeviceGuard guard(h->cfg.device);
+        cudaDeviceSynchronize();
+        cudaFree(h->d_cost); cudaFree(h->d_rho); cudaFree(h->d_part); cudaFree(h->d_wsum);
+        cudaFree(h->d_u); cudaFree(h->d_out); cudaFree(h->d_noise);
+        if (h->h_pinned) cudaFreeHost(h->h_pinned);
+        if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    }
+    delete h;
+    return MPPI_OK;
+}
+
+mppi_status_t mppi_set_chain(mppi_handle_t h, int32_t n, const int32_t *types, const float *xyz, const float *rpy, const float *axis)
+{
+    if (!h || !types || !xyz || !rpy || !axis || n < 1 || n > 64) return fail(h, MPPI_ERR_INVALID_ARG, "bad chain arguments");
+    return set_chain_impl(h, n, types, xyz, rpy, axis);
+}
+
+mppi_status_t mppi_update_config(mppi_handle_t h, const mppi_config_t *cfg)
+{
+    if (!h || !cfg) return fail(h, MPPI_ERR_INVALID_ARG, "null config");
+    if (!(cfg->dt > 0.f) || !(cfg->lambda_ > 0.f)) return fail(h, MPPI_ERR_INVALID_ARG, "dt and lambda must be positive");
+    h->cfg.dt = cfg->dt; h->cfg.lambda_ = cfg->lambda_;
+    std::memcpy(h->cfg.sigma, cfg->sigma, sizeof(cfg->sigma));
+    std::memcpy(h->cfg.cost_w, cfg->cost_w, sizeof(cfg->cost_w));
+    std::memcpy(h->cfg.quad_params, cfg->quad_params, sizeof(cfg->quad_params));
+    StepParams &P = h->P;
+    P.dt = cfg->dt;
+    P.dt2 = (float)((double)cfg->dt * (double)cfg->dt);
+    P.inv_lambda = (float)(1.0 / (double)cfg->lambda_);
+    std::memcpy(P.sigma, cfg->sigma, sizeof(P.sigma));
+    std::memcpy(P.cost_w, cfg->cost_w, sizeof(P.cost_w));
+    std::memcpy(P.quad, cfg->quad_params, sizeof(P.quad));
+    return MPPI_OK;
+}
+
+mppi_status_t mppi_set_target(mppi_handle_t h, const float *pos, const float *quat, const float *drone_target)
+{
+    if (!h) return MPPI_ERR_INVALID_ARG;
+    if (quat && !(quat[0] * quat[0] + quat[1] * quat[1] + quat[2] * quat[2] + quat[3] * quat[3] > 0.f))
+        return fail(h, MPPI_ERR_INVALID_ARG, "zero target quaternion");
+    set_target_locked(h, pos, quat, drone_target);
+    return MPPI_OK;
+}
+
+mppi_status_t mppi_set_state(mppi_handle_t h, const float *state_host, int32_t n)
+{
+    if (!h || !state_host) return fail(h, MPPI_ERR_INVALID_ARG, "null state");
+    if (n != model_state_floats(h->cfg.model))
+        return fail(h, MPPI_ERR_INVALID_ARG, "state length " + std::to_string(n) + " != " + std::to_string(model_state_floats(h->cfg.model)));
+    std::lock_guard<std::mutex> lk(h->state_mu);
+    std::memcpy(h->staged_state, state_host, (size_t)n * sizeof(float));
+    return MPPI_OK;
+}
+
+int32_t *mppi_rho_ptr(mppi_handle_t h) { return h ? h->d_rho : nullptr; }
+float *mppi_wsum_ptr(mppi_handle_t h) { return h ? h->d_wsum : nullptr; }
+int32_t mppi_wsum_count(mppi_handle_t h) { return h ? h->P.T * h->nu + 2 : 0; }
+float *mppi_cost_ptr(mppi_handle_t h) { return h ? h->d_cost : nullptr; }
+
+mppi_status_t mppi_rollout(mppi_handle_t h, const float *d_u_nom, const float *d_noise, uint64_t step_counter,
+                           float *d_cost_out, void *stream)
+{
+    if (!h || !d_u_nom) return fail(h, MPPI_ERR_INVALID_ARG, "null u_nom");
+    DeviceGuard guard(h->cfg.device);
+    cudaStream_t st = (cudaStream_t)stream;
+    snapshot(h, step_counter);
+    mppi_status_t rc = rollout_dispatch(h, d_u_nom, d_noise, h->d_cost, st);
+    if (rc != MPPI_OK) return rc;
+    if (d_cost_out && d_cost_out != h->d_cost)
+        MPPI_CUDA(h, cudaMemcpyAsync(d_cost_out, h->d_cost, (size_t)h->P.K * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return MPPI_OK;
+}
+
+mppi_status_t mppi_weight(mppi_handle_t h, const float *d_noise, uint64_t step_counter, void *stream)
+{
+    if (!h) return MPPI_ERR_INVALID_ARG;
+    DeviceGuard guard(h->cfg.device);
+    h->dyn.step_lo = (uint32_t)step_counter; h->dyn.step_hi = (uint32_t)(step_counter >> 32);
+    return weight_dispatch(h, d_noise, false, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+mppi_status_t mppi_finalize(mppi_handle_t h, const float *d_u_nom, uint64_t step_counter, float *d_u_new, float *d_out, void *stream)
+{
+    if (!h || !d_u_nom || !d_u_new) return fail(h, MPPI_ERR_INVALID_ARG, "null u buffers");
+    DeviceGuard guard(h->cfg.device);
+    h->dyn.step_lo = (uint32_t)step_counter; h->dyn.step_hi = (uint32_t)(step_counter >> 32);
+    return finalize_dispatch(h, d_u_nom, d_u_new, d_out, (cudaStream_t)stream);
+}
+
+mppi_status_t mppi_step(mppi_handle_t h, const float *d_u_nom, const float *d_noise, uint64_t step_counter,
+                        float *d_cost_out, float *d_u_new, float *d_out, void *stream)
+{
+    if (!h || !d_u_nom || !d_u_new) return fail(h, MPPI_ERR_INVALID_ARG, "null u buffers");
+    DeviceGuard guard(h->cfg.device);
+    cudaStream_t st = (cudaStream_t)stream;
+    snapshot(h, step_counter);
+    mppi_status_t rc = rollout_dispatch(h, d_u_nom, d_noise, h->d_cost, st);
+    if (rc != MPPI_OK) return rc;
+    if (d_cost_out && d_cost_out != h->d_cost)
+        MPPI_CUDA(h, cudaMemcpyAsync(d_cost_out, h->d_cost, (size_t)h->P.K * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return weight_dispatch(h, d_noise, true, d_u_nom, d_u_new, d_out ? d_out : h->d_out, st);
+}
+
+mppi_status_t mppi_step_host(mppi_handle_t h, const float *state_host, int32_t n_state, float *u_inout_host,
+                             const float *noise_host, uint64_t step_counter, float *cost_out_host, float *out_host)
+{
+    if (!h || !u_inout_host) return fail(h, MPPI_ERR_INVALID_ARG, "null u buffer");
+    DeviceGuard guard(h->cfg.device);
+    if (state_host) {
+        mppi_status_t rc = mppi_set_state(h, state_host, n_state);
+        if (rc != MPPI_OK) return rc;
+    }
+    cudaStream_t st = h->own_stream;
+    const size_t nu_floats = (size_t)h->P.T * h->nu;
+    std::memcpy(h->h_pinned, u_inout_host, nu_floats * sizeof(float));
+    MPPI_CUDA(h, cudaMemcpyAsync(h->d_u, h->h_pinned, nu_floats * sizeof(float), cudaMemcpyHostToDevice, st));
+    const float *d_noise = nullptr;
+    if (noise_host) {
+        const size_t bytes = nu_floats * (size_t)h->P.K * sizeof(float);
+        if (bytes > h->d_noise_bytes) {
+            cudaFree(h->d_noise); h->d_noise = nullptr; h->d_noise_bytes = 0;
+            MPPI_CUDA(h, cudaMalloc(&h->d_noise, bytes));
+            h->d_noise_bytes = bytes;
+        }
+        MPPI_CUDA(h, cudaMemcpyAsync(h->d_noise, noise_host, bytes, cudaMemcpyHostToDevice, st));
+        d_noise = h->d_noise;
+    }
+    mppi_status_t rc = mppi_step(h, h->d_u, d_noise, step_counter, nullptr, h->d_u, h->d_out, st);
+    if (rc != MPPI_OK) return rc;
+    MPPI_CUDA(h, cudaMemcpyAsync(h->h_pinned, h->d_u, nu_floats * sizeof(float), cudaMemcpyDeviceToHost, st));
+    MPPI_CUDA(h, cudaMemcpyAsync(h->h_pinned + nu_floats, h->d_out, MPPI_OUT_FLOATS * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (cost_out_host)
+        MPPI_CUDA(h, cudaMemcpyAsync(cost_out_host, h->d_cost, (size_t)h->P.K * sizeof(float), cudaMemcpyDeviceToHost, st));
+    MPPI_CUDA(h, cudaStreamSynchronize(st));
+    std::memcpy(u_inout_host, h->h_pinned, nu_floats * sizeof(float));
+    if (out_host) std::memcpy(out_host, h->h_pinned + nu_floats, MPPI_OUT_FLOATS * sizeof(float));
+    return MPPI_OK;
+}
+
+mppi_status_t mppi_generate_noise(mppi_handle_t h, uint64_t step_counter, float *d_noise, void *stream)
+{
+    if (!h || !d_noise) return fail(h, MPPI_ERR_INVALID_ARG, "null noise buffer");
+    DeviceGuard guard(h->cfg.device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint32_t lo = (uint32_t)step_counter, hi = (uint32_t)(step_counter >> 32);
+    const int grid = h->num_sms * 8;
+    switch (h->nu) {
+        case 3: generate_noise_kernel<3><<<grid, 256, 0, st>>>(h->P, lo, hi, d_noise); break;
+        case 4: generate_noise_kernel<4><<<grid, 256, 0, st>>>(h->P, lo, hi, d_noise); break;
+        case 7: generate_noise_kernel<7><<<grid, 256, 0, st>>>(h->P, lo, hi, d_noise); break;
+        case 11: generate_noise_kernel<11><<<grid, 256, 0, st>>>(h->P, lo, hi, d_noise); break;
+        default: return fail(h, MPPI_ERR_INVALID_ARG, "bad nu");
+    }
+    MPPI_CUDA(h, cudaGetLastError());
+    return MPPI_OK;
+}
+
+mppi_status_t mppi_measure_fp32_peak(int32_t device, float *tflops_out)
+{
+    if (!tflops_out) return MPPI_ERR_INVALID_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+        return fail(nullptr, MPPI_ERR_CUDA, "no such CUDA device");
+    DeviceGuard guard(device);
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(nullptr, MPPI_ERR_CUDA, "cudaGetDeviceProperties");
+    float *d = nullptr;
+    if (cudaMalloc(&d, 64) != cudaSuccess) return fail(nullptr, MPPI_ERR_CUDA, "cudaMalloc");
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    float best = 0.f;
+    for (int rep = 0; rep < 6; ++rep) {
+        cudaEventRecord(e0);
+        ffma_probe_kernel<<<blocks, threads>>>(d, iters, 0.999f, 0.001f);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * 64.0 * (double)iters * blocks * threads;
+        const float tf = (float)(flops / (ms * 1e-3) / 1e12);
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(nullptr, MPPI_ERR_CUDA, cudaGetErrorString(e));
+    *tflops_out = best;
+    return MPPI_OK;
+}
+
+double mppi_algorithmic_flops_per_rollout_step(int32_t model)
+{
+    // rollout + cost, dense URDF constants, FMA = 2 FLOP, transcendentals excluded.
+    switch (model) {
+        case MPPI_MODEL_DRONE3: return 40.0;
+        case MPPI_MODEL_QUAD4: return 90.0;
+        case MPPI_MODEL_ARM7: return 840.0;
+        case MPPI_MODEL_WB11: return 1000.0;
+        default: return 0.0;
+    }
+}
+
+}  // extern "C"

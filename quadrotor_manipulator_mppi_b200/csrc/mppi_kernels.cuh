@@ -1,0 +1,531 @@
+// mppi_kernels.cuh -- the kernels of one MPPI control step.
+//
+//   K2  rollout_cost_kernel   : noise (in-kernel Philox or injected [T][K][nu]) + rollout +
+//                               forward kinematics + cost, one thread per sample, state in
+//                               registers over the horizon loop; S[K] and the cost minimum
+//                               are the only things written.
+//   K3  weight_philox_kernel  : w = exp((rho-S)/lambda), weighted-noise sums with the noise
+//       weight_injected_kernel  regenerated (compute-bound) or re-read (HBM-bound, float4).
+//                               The last block to finish reduces the per-block partials in a
+//                               fixed order and, on a single GPU, runs K4 in place.
+//   K4  finalize              : normalise, Savitzky-Golay, u += w_eps, controller outputs.
+#pragma once
+#include "mppi_device.cuh"
+
+namespace mppi {
+
+constexpr int kRolloutThreads = 128;
+constexpr int kWeightTile = 2048;       // samples whose weights are staged in smem at a time
+
+// ------------------------------------------------------------------------------------------
+// K2: fused noise + rollout + FK + cost.
+// Replaces S/mppi_solver/mppi.py:129-140 (sampling, get_sample_joint, compute_fk_gpu,
+// CostManager.compute_all_cost) and S/mppi_solver/drone_mppi.py:143-151.
+// ------------------------------------------------------------------------------------------
+template <int MODEL, bool PHILOX>
+__global__ void __launch_bounds__(kRolloutThreads)
+rollout_cost_kernel(const __grid_constant__ StepParams P, const __grid_constant__ DynBlock D,
+                    const float *__restrict__ u_nom, const float *__restrict__ noise,
+                    float *__restrict__ cost_out, int32_t *__restrict__ rho_enc)
+{
+    constexpr int NU = ModelNu<MODEL>::value;
+    constexpr int NCH = (NU + 3) / 4;
+    constexpr bool HAS_ARM = (MODEL == MPPI_MODEL_ARM7 || MODEL == MPPI_MODEL_WB11);
+    constexpr bool HAS_QUAD = (MODEL == MPPI_MODEL_QUAD4 || MODEL == MPPI_MODEL_WB11);
+    constexpr int ARM0 = (MODEL == MPPI_MODEL_WB11) ? 4 : 0;     // first arm input
+    constexpr int QOFF = (MODEL == MPPI_MODEL_WB11) ? 12 : 0;    // arm q in the state vector
+
+    extern __shared__ __align__(16) float s_unom[];              // [T][NU]
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ float s_wmin[kRolloutThreads / 32];
+
+    // ---- stage the nominal control sequence: one TMA bulk copy + scalar tail
+    const int n_u = P.T * NU;
+    const uint32_t bulk_bytes = (static_cast<uint32_t>(n_u) * 4u) & ~15u;
+    const bool bulk_ok = bulk_bytes > 0 && ((reinterpret_cast<uintptr_t>(u_nom) & 15u) == 0);
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (bulk_ok) {
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&s_bar, bulk_bytes);
+            tma_bulk_g2s(s_unom, u_nom, bulk_bytes, &s_bar);
+        }
+        for (int j = (bulk_bytes >> 2) + threadIdx.x; j < n_u; j += blockDim.x) s_unom[j] = u_nom[j];
+        mbar_wait(&s_bar, 0);
+    } else {
+        for (int j = threadIdx.x; j < n_u; j += blockDim.x) s_unom[j] = u_nom[j];
+    }
+    __syncthreads();
+
+    const int k_raw = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = k_raw < P.K;
+    const int k = active ? k_raw : P.K - 1;
+    const uint32_t kg = static_cast<uint32_t>(P.k_offset + k);
+
+    // ---- per-sample state in registers
+    float cum_v[HAS_ARM ? 7 : 3], cum_q[HAS_ARM ? 7 : 3], vprev[HAS_ARM ? 7 : 3];
+    QuadState qs;
+    float R0[9], p0[3];          // chain root pose composed with C0 (loop-invariant for ARM7)
+    if constexpr (MODEL == MPPI_MODEL_DRONE3) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { cum_v[i] = 0.f; cum_q[i] = 0.f; vprev[i] = D.state[3 + i]; }
+    }
+    if constexpr (HAS_ARM) {
+#pragma unroll
+        for (int i = 0; i < 7; ++i) { cum_v[i] = 0.f; cum_q[i] = 0.f; vprev[i] = D.state[QOFF + 7 + i]; }
+    }
+    if constexpr (MODEL == MPPI_MODEL_ARM7) {
+        quat_matrix(&D.state[14], R0);                       // base xyz+quat -> B (S/robot/urdf_fk.py:30-55)
+        p0[0] = D.state[14]; p0[1] = D.state[15]; p0[2] = D.state[16];
+        compose_const(R0, p0, P.chain.R[0], P.chain.t[0]);
+    }
+    if constexpr (HAS_QUAD) quad_load(qs, D.state);
+
+    float S = 0.f, comp = 0.f;       // Kahan-compensated running cost
+    float Sd = 0.f;                  // squared-distance stage cost (drone / quad part)
+    float term_d = 0.f;
+
+    for (int t = 0; t < P.T; ++t) {
+        // ---- controls of this step: v = u + noise  (S/mppi_solver/mppi.py:130)
+        float a[NU];
+        if constexpr (PHILOX) {
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                float n4[4];
+                normal4(kg, static_cast<uint32_t>(t * NCH + c), D.step_lo, D.step_hi, P.seed_lo, P.seed_hi, n4);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (4 * c + j < NU) a[4 * c + j] = __fmul_rn(P.sigma[4 * c + j], n4[j]);
+            }
+        } else {
+            const float *row = noise + (static_cast<size_t>(t) * P.K + k) * NU;
+#pragma unroll
+            for (int i = 0; i < NU; ++i) a[i] = __ldg(row + i);
+        }
+#pragma unroll
+        for (int i = 0; i < NU; ++i) a[i] = __fadd_rn(s_unom[t * NU + i], a[i]);
+
+        const bool last = (t == P.T - 1);
+        if constexpr (MODEL == MPPI_MODEL_DRONE3) {
+            // double integrator (S/mppi_solver/drone_mppi.py:46-55) + squared distance (:87-107)
+            float sq = 0.f;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const float dq = fmaf(vprev[i], P.dt, (0.5f * a[i]) * P.dt2);
+                cum_v[i] = fmaf(a[i], P.dt, cum_v[i]);
+                vprev[i] = cum_v[i] + D.state[3 + i];
+                cum_q[i] += dq;
+                const float e = (cum_q[i] + D.state[i]) - D.drone_target[i];
+                sq = fmaf(e, e, sq);
+            }
+            if (last) term_d = sq; else Sd += sq;
+        }
+        if constexpr (HAS_QUAD) {
+            quad_advance(qs, a[0], a[1], a[2], a[3], P.dt, P.quad);
+            const float ex = qs.p[0] - D.drone_target[0], ey = qs.p[1] - D.drone_target[1], ez = qs.p[2] - D.drone_target[2];
+            const float sq = fmaf(ex, ex, fmaf(ey, ey, ez * ez));
+            if (last) term_d = sq; else Sd += sq;
+        }
+        if constexpr (HAS_ARM) {
+            // S/sampling/standard_normal_noise.py:32-50
+            float cq[7], sq[7];
+#pragma unroll
+            for (int i = 0; i < 7; ++i) {
+                const float ai = a[ARM0 + i];
+                const float dq = fmaf(vprev[i], P.dt, (0.5f * ai) * P.dt2);
+                cum_v[i] = fmaf(ai, P.dt, cum_v[i]);
+                vprev[i] = cum_v[i] + D.state[QOFF + 7 + i];
+                cum_q[i] += dq;
+                sincosf(cum_q[i] + D.state[QOFF + i], &sq[i], &cq[i]);
+            }
+            float R[9], p[3];
+            if constexpr (MODEL == MPPI_MODEL_ARM7) {
+#pragma unroll
+                for (int i = 0; i < 9; ++i) R[i] = R0[i];
+                p[0] = p0[0]; p[1] = p0[1]; p[2] = p0[2];
+            } else {
+                // moving base T(p_t, rpy_t) (S/robot/transformation_matrix.py:148-187)
+                rpy_matrix(qs.sphi, qs.cphi, qs.sth, qs.cth, qs.spsi, qs.cpsi, R);
+                p[0] = qs.p[0]; p[1] = qs.p[1]; p[2] = qs.p[2];
+                compose_const(R, p, P.chain.R[0], P.chain.t[0]);
+            }
+            fk_chain<7>(P.chain, cq, sq, R, p);
+            float pos, ori;
+            pose_terms(R, p, D, pos, ori);
+            // S/cost/cost_manager.py:30-33,78-89
+            const float c = last ? fmaf(P.cost_w[2], pos, P.cost_w[3] * ori)
+                                 : fmaf(P.cost_w[0], pos, P.cost_w[1] * ori);
+            const float y = c - comp;
+            const float tS = S + y;
+            comp = (tS - S) - y;
+            S = tS;
+        }
+    }
+    if constexpr (MODEL == MPPI_MODEL_DRONE3 || MODEL == MPPI_MODEL_QUAD4) {
+        S = fmaf(Sd, P.cost_w[4], term_d * P.cost_w[5]);
+    } else if constexpr (MODEL == MPPI_MODEL_WB11) {
+        S = S + fmaf(Sd, P.cost_w[4], term_d * P.cost_w[5]);
+    }
+
+    if (active) cost_out[k] = S;
+    // ---- block minimum -> one atomicMin on the order-preserving encoding
+    float m = warp_min(active ? S : __int_as_float(0x7f800000));
+    if ((threadIdx.x & 31) == 0) s_wmin[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float bm = s_wmin[0];
+#pragma unroll
+        for (int w = 1; w < kRolloutThreads / 32; ++w) bm = fminf(bm, s_wmin[w]);
+        atomicMin(rho_enc, encode_ordered(bm));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: finalize (device function, run by one block).
+// S/mppi_solver/mppi.py:148-158, drone_mppi.py:158-170, S/filter/svg_filter.py:13-90.
+//   wsum = [T*nu] raw weighted-noise sums, eta, sum w^2     scratch = 2*T*nu + nu floats of smem
+// ------------------------------------------------------------------------------------------
+template <int MODEL>
+__device__ void finalize_block(const StepParams &P, const DynBlock &D, const float *wsum,
+                               const float *u_nom, float *u_new, float *out, int32_t *rho_enc,
+                               float *scratch)
+{
+    constexpr int NU = ModelNu<MODEL>::value;
+    const int n = P.T * NU;
+    float *raw = scratch, *un = scratch + n, *u0_old = scratch + 2 * n;
+    const float eta = wsum[n], eta2 = wsum[n + 1];
+    const float inv_eta = 1.0f / eta;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) raw[j] = wsum[j] * inv_eta;
+    if (threadIdx.x < NU) u0_old[threadIdx.x] = u_nom[threadIdx.x];
+    __syncthreads();
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        const int t = j / NU, i = j - t * NU;
+        float acc = 0.f;
+        for (int jj = -P.sg_half; jj <= P.sg_half; ++jj) {
+            int s = t + jj;
+            s = (s < 0) ? (-s - 1) : s;                   // data[:h].flip(0)
+            s = (s >= P.T) ? (2 * P.T - 1 - s) : s;       // data[-h:].flip(0)
+            acc = fmaf(P.taps[jj + P.sg_half], raw[s * NU + i], acc);
+        }
+        const float v = u_nom[j] + acc;                   // u += w_eps
+        un[j] = v;
+        u_new[j] = v;
+    }
+    __syncthreads();
+    if (out != nullptr && threadIdx.x == 0) {
+        const float dt = P.dt;
+        if constexpr (MODEL == MPPI_MODEL_DRONE3) {
+            for (int i = 0; i < 3; ++i) {
+                out[i] = D.state[i] + D.state[3 + i] * dt + 0.5f * un[i] * P.dt2;      // drone_mppi.py:170
+                out[3 + i] = D.state[3 + i] + dt * un[i];                                // :169
+            }
+        } else if constexpr (MODEL == MPPI_MODEL_ARM7) {
+            for (int i = 0; i < 7; ++i) {
+                out[i] = D.state[i] + u0_old[i] * dt + 0.5f * un[i] * dt * dt;          // mppi.py:158 (F11)
+                out[7 + i] = D.state[7 + i] + un[i] * dt;                                // mppi.py:157
+            }
+        } else {
+            QuadState qs;
+            quad_load(qs, D.state);
+            quad_advance(qs, un[0], un[1], un[2], un[3], dt, P.quad);
+            const int o = (MODEL == MPPI_MODEL_WB11) ? MPPI_OUT_BASE : 0;
+            for (int i = 0; i < 3; ++i) { out[o + i] = qs.p[i]; out[o + 3 + i] = qs.rpy[i]; out[o + 6 + i] = qs.v[i]; out[o + 9 + i] = qs.w[i]; }
+            if constexpr (MODEL == MPPI_MODEL_WB11) {
+                for (int i = 0; i < 7; ++i) {
+                    out[i] = D.state[12 + i] + u0_old[4 + i] * dt + 0.5f * un[4 + i] * dt * dt;
+                    out[7 + i] = D.state[19 + i] + un[4 + i] * dt;
+                }
+            }
+        }
+        if constexpr (MODEL == MPPI_MODEL_ARM7 || MODEL == MPPI_MODEL_WB11) {
+            // check_reach (mppi.py:95-120): L1 position error of FK(base, qdes) to the target
+            float cq[7], sq[7], R[9], p[3];
+            for (int i = 0; i < 7; ++i) sincosf(out[i], &sq[i], &cq[i]);
+            if constexpr (MODEL == MPPI_MODEL_ARM7) {
+                quat_matrix(&D.state[14], R);
+                p[0] = D.state[14]; p[1] = D.state[15]; p[2] = D.state[16];
+            } else {
+                float sr, cr, sp, cp, sy, cy;
+                sincosf(D.state[3], &sr, &cr); sincosf(D.state[4], &sp, &cp); sincosf(D.state[5], &sy, &cy);
+                rpy_matrix(sr, cr, sp, cp, sy, cy, R);
+                p[0] = D.state[0]; p[1] = D.state[1]; p[2] = D.state[2];
+            }
+            compose_const(R, p, P.chain.R[0], P.chain.t[0]);
+            fk_chain<7>(P.chain, cq, sq, R, p);
+            out[MPPI_OUT_REACH] = fabsf(p[0] - D.target_pos[0]) + fabsf(p[1] - D.target_pos[1]) + fabsf(p[2] - D.target_pos[2]);
+        }
+        for (int i = 0; i < NU; ++i) { out[MPPI_OUT_U0_NEW + i] = un[i]; out[MPPI_OUT_U0_OLD + i] = u0_old[i]; }
+        out[MPPI_OUT_RHO] = decode_ordered(*rho_enc);
+        out[MPPI_OUT_ETA] = eta;
+        out[MPPI_OUT_ESS] = eta * eta / eta2;
+        out[MPPI_OUT_STEP] = static_cast<float>(D.step_lo & 0xffffffu);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *rho_enc = kRhoInit;          // re-arm the minimum for the next step
+}
+
+template <int MODEL>
+__global__ void __launch_bounds__(256)
+finalize_kernel(const __grid_constant__ StepParams P, const __grid_constant__ DynBlock D,
+                const float *__restrict__ wsum, const float *u_nom, float *u_new, float *out,
+                int32_t *rho_enc)
+{
+    extern __shared__ __align__(16) float s_fin[];
+    finalize_block<MODEL>(P, D, wsum, u_nom, u_new, out, rho_enc, s_fin);
+}
+
+// Last-block-done: every block publishes its partial row, the last one to arrive sums the rows
+// in index order (deterministic) into wsum and optionally finalizes.
+template <int MODEL>
+__device__ void reduce_partials_and_finalize(const StepParams &P, const DynBlock &D, const float *part,
+                                             int n_parts, uint32_t *counter, float *wsum, bool fuse,
+                                             const float *u_nom, float *u_new, float *out,
+                                             int32_t *rho_enc, float *scratch)
+{
+    constexpr int NU = ModelNu<MODEL>::value;
+    __shared__ bool s_last;
+    const int row = P.T * NU + 2;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t total = gridDim.x * gridDim.y;
+        s_last = (atomicAdd(counter, 1u) == total - 1u);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int j = threadIdx.x; j < row; j += blockDim.x) {
+        float acc = 0.f;
+        int b = 0;
+        for (; b + 4 <= n_parts; b += 4) {
+            const float v0 = __ldcg(part + static_cast<size_t>(b) * row + j);
+            const float v1 = __ldcg(part + static_cast<size_t>(b + 1) * row + j);
+            const float v2 = __ldcg(part + static_cast<size_t>(b + 2) * row + j);
+            const float v3 = __ldcg(part + static_cast<size_t>(b + 3) * row + j);
+            acc = ((acc + v0) + v1) + v2 + v3;
+        }
+        for (; b < n_parts; ++b) acc += __ldcg(part + static_cast<size_t>(b) * row + j);
+        wsum[j] = acc;
+    }
+    if (threadIdx.x == 0) *counter = 0u;
+    __syncthreads();
+    if (fuse) finalize_block<MODEL>(P, D, wsum, u_nom, u_new, out, rho_enc, scratch);
+}
+
+// ------------------------------------------------------------------------------------------
+// K3 (Philox): thread = (horizon step t, Philox chunk c) x R sub-ranges of the block's sample
+// chunk; the noise is regenerated from its address, zero-weight samples are skipped (exact:
+// w == 0.0f contributes 0).  part[b][T*nu+2].
+// S/mppi_solver/mppi.py:143-148,173-193.
+// ------------------------------------------------------------------------------------------
+template <int MODEL>
+__global__ void __launch_bounds__(1024)
+weight_philox_kernel(const __grid_constant__ StepParams P, const __grid_constant__ DynBlock D,
+                     const float *__restrict__ S, int32_t *rho_enc, int chunk,
+                     float *__restrict__ part, uint32_t *counter, float *wsum, int fuse,
+                     const float *u_nom, float *u_new, float *out)
+{
+    constexpr int NU = ModelNu<MODEL>::value;
+    constexpr int NCH = (NU + 3) / 4;
+    extern __shared__ __align__(16) float s_dyn[];      // [kWeightTile] weights | reduction / finalize scratch
+    float *s_w = s_dyn;
+    float *s_red = s_dyn + kWeightTile;
+    __shared__ float s_eta[32], s_eta2[32];
+
+    const int TC = P.T * NCH;
+    const int R = blockDim.x / TC;
+    const int tid = threadIdx.x;
+    const bool worker = tid < R * TC;
+    const int r = tid / TC, tc = tid - r * TC;
+    const int c = tc % NCH;
+    const int t = tc / NCH;
+    const float rho = decode_ordered(*rho_enc);
+    const int k0 = blockIdx.x * chunk;
+    const int k1 = min(P.K, k0 + chunk);
+
+    float sg[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sg[j] = (4 * c + j < NU) ? P.sigma[4 * c + j] : 0.f;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float eta = 0.f, eta2 = 0.f;
+
+    for (int base = k0; base < k1; base += kWeightTile) {
+        const int nt = min(kWeightTile, k1 - base);
+        __syncthreads();
+        for (int kk = tid; kk < nt; kk += blockDim.x) {
+            const float w = expf(-P.inv_lambda * (S[base + kk] - rho));
+            s_w[kk] = w;
+            eta += w;
+            eta2 = fmaf(w, w, eta2);
+        }
+        __syncthreads();
+        if (worker) {
+            for (int kk = r; kk < nt; kk += R) {
+                const float w = s_w[kk];
+                if (w == 0.f) continue;
+                float n4[4];
+                normal4(static_cast<uint32_t>(P.k_offset + base + kk), static_cast<uint32_t>(tc),
+                        D.step_lo, D.step_hi, P.seed_lo, P.seed_hi, n4);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[j] = fmaf(w, __fmul_rn(sg[j], n4[j]), acc[j]);
+            }
+        }
+    }
+    // ---- block reductions (fixed order): eta / eta2 over all threads, acc over the R sub-ranges
+    eta = warp_sum(eta);
+    eta2 = warp_sum(eta2);
+    if ((tid & 31) == 0) { s_eta[tid >> 5] = eta; s_eta2[tid >> 5] = eta2; }
+    __syncthreads();
+    if (worker) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s_red[(r * TC + tc) * 4 + j] = acc[j];
+    }
+    __syncthreads();
+    const int row = P.T * NU + 2;
+    float *my = part + static_cast<size_t>(blockIdx.x) * row;
+    if (tid < TC) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (4 * c + j < NU) {
+                float v = 0.f;
+                for (int rr = 0; rr < R; ++rr) v += s_red[(rr * TC + tc) * 4 + j];
+                my[t * NU + 4 * c + j] = v;
+            }
+        }
+    }
+    if (tid == 0) {
+        float e = 0.f, e2 = 0.f;
+        const int nw = (blockDim.x + 31) >> 5;
+        for (int w = 0; w < nw; ++w) { e += s_eta[w]; e2 += s_eta2[w]; }
+        my[row - 2] = e;
+        my[row - 1] = e2;
+    }
+    reduce_partials_and_finalize<MODEL>(P, D, part, gridDim.x, counter, wsum, fuse != 0, u_nom, u_new, out,
+                                        rho_enc, s_dyn);
+}
+
+// ------------------------------------------------------------------------------------------
+// K3 (injected noise [T][K][nu]): HBM-bound re-read.  block = (sample chunk, horizon step t),
+// 32*nu threads; one iteration covers 32*VEC samples = blockDim*VEC contiguous floats, so a
+// thread's VEC components keep the same input index i for the whole loop (coalesced float4).
+// ------------------------------------------------------------------------------------------
+template <int MODEL, int VEC>
+__global__ void __launch_bounds__(32 * ModelNu<MODEL>::value)
+weight_injected_kernel(const __grid_constant__ StepParams P, const __grid_constant__ DynBlock D,
+                       const float *__restrict__ S, const float *__restrict__ noise, int32_t *rho_enc,
+                       int chunk, float *__restrict__ part, uint32_t *counter, float *wsum, int fuse,
+                       const float *u_nom, float *u_new, float *out)
+{
+    constexpr int NU = ModelNu<MODEL>::value;
+    constexpr int NT = 32 * NU;
+    extern __shared__ __align__(16) float s_dyn[];     // weights of the chunk | reduction | finalize scratch
+    float *s_w = s_dyn;
+    __shared__ float s_eta[32], s_eta2[32];
+
+    const int tid = threadIdx.x;
+    const int t = blockIdx.y;
+    const int k0 = blockIdx.x * chunk;
+    const int k1 = min(P.K, k0 + chunk);
+    const int nk = k1 - k0;
+    const float rho = decode_ordered(*rho_enc);
+
+    float eta = 0.f, eta2 = 0.f;
+    for (int kk = tid; kk < nk; kk += NT) {
+        const float w = expf(-P.inv_lambda * (S[k0 + kk] - rho));
+        s_w[kk] = w;
+        eta += w;
+        eta2 = fmaf(w, w, eta2);
+    }
+    __syncthreads();
+
+    int koff[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) koff[v] = (tid * VEC + v) / NU;
+    float acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+    const float *row = noise + (static_cast<size_t>(t) * P.K + k0) * NU + tid * VEC;
+    for (int kb = 0; kb < nk; kb += 32 * VEC) {
+        if constexpr (VEC == 4) {
+            if (kb + koff[3] < nk) {       // whole vector in range
+                const float4 x = __ldcs(reinterpret_cast<const float4 *>(row + static_cast<size_t>(kb) * NU));
+                acc[0] = fmaf(s_w[kb + koff[0]], x.x, acc[0]);
+                acc[1] = fmaf(s_w[kb + koff[1]], x.y, acc[1]);
+                acc[2] = fmaf(s_w[kb + koff[2]], x.z, acc[2]);
+                acc[3] = fmaf(s_w[kb + koff[3]], x.w, acc[3]);
+            } else {
+#pragma unroll
+                for (int v = 0; v < 4; ++v)
+                    if (kb + koff[v] < nk) acc[v] = fmaf(s_w[kb + koff[v]], row[static_cast<size_t>(kb) * NU + v], acc[v]);
+            }
+        } else {
+            if (kb + koff[0] < nk) acc[0] = fmaf(s_w[kb + koff[0]], __ldcs(row + static_cast<size_t>(kb) * NU), acc[0]);
+        }
+    }
+    // ---- reduce the NT*VEC per-thread sums to nu outputs, fixed order
+    __syncthreads();
+    float *s_red = s_dyn;      // reuse (weights no longer needed)
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) s_red[tid * VEC + v] = acc[v];
+    eta = warp_sum(eta);
+    eta2 = warp_sum(eta2);
+    if ((tid & 31) == 0) { s_eta[tid >> 5] = eta; s_eta2[tid >> 5] = eta2; }
+    __syncthreads();
+    const int rowlen = P.T * NU + 2;
+    float *my = part + static_cast<size_t>(blockIdx.x) * rowlen;
+    if (tid < NU) {
+        float v = 0.f;
+        for (int j = tid; j < NT * VEC; j += NU) v += s_red[j];
+        my[t * NU + tid] = v;
+    }
+    if (t == 0 && tid == 0) {
+        float e = 0.f, e2 = 0.f;
+        for (int w = 0; w < NT / 32; ++w) { e += s_eta[w]; e2 += s_eta2[w]; }
+        my[rowlen - 2] = e;
+        my[rowlen - 1] = e2;
+    }
+    reduce_partials_and_finalize<MODEL>(P, D, part, gridDim.x, counter, wsum, fuse != 0, u_nom, u_new, out,
+                                        rho_enc, s_dyn);
+}
+
+// Materialise the Philox noise of one step (equivalence checks, HBM-bound experiments).
+template <int NU>
+__global__ void __launch_bounds__(256)
+generate_noise_kernel(const __grid_constant__ StepParams P, uint32_t step_lo, uint32_t step_hi,
+                      float *__restrict__ noise)
+{
+    constexpr int NCH = (NU + 3) / 4;
+    const long long n = static_cast<long long>(P.T) * P.K * NCH;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < n;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(idx % NCH);
+        const long long tk = idx / NCH;
+        const int k = static_cast<int>(tk % P.K);
+        const int t = static_cast<int>(tk / P.K);
+        float n4[4];
+        normal4(static_cast<uint32_t>(P.k_offset + k), static_cast<uint32_t>(t * NCH + c), step_lo, step_hi,
+                P.seed_lo, P.seed_hi, n4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (4 * c + j < NU) noise[(static_cast<size_t>(t) * P.K + k) * NU + 4 * c + j] = __fmul_rn(P.sigma[4 * c + j], n4[j]);
+    }
+}
+
+// FP32 FFMA throughput probe: 8 independent chains per thread.
+__global__ void __launch_bounds__(256) ffma_probe_kernel(float *out, int iters, float a, float b)
+{
+    float x0 = threadIdx.x, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+            x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+        }
+    }
+    if (x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7 == 12345.678f) out[0] = x0;
+}
+
+}  // namespace mppi

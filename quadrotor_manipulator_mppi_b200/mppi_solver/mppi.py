@@ -1,0 +1,158 @@
+"""Arm MPPI controller (Kinova j2s7s300, nu=7): drop-in for the reference class
+`mppi_solver/mppi.py:27-200`.
+
+Kept from the reference: the no-arg constructor and its defaults (K=100, T=32, dt=0.01,
+sigma=0.1, lambda=0.1; mppi.py:37-42,75, sampling/standard_normal_noise.py:17),
+`update_joint(q_full, v_full)` (mppi.py:196-200), `compute_control_input()` returning
+`(qdes, vdes)` numpy arrays incl. the `_qddot * dt` term (mppi.py:157-162), the
+un-shifted `u_prev` warm start (mppi.py:125,153), `target_pose`, `compute_weights`,
+`check_reach`.  New keyword-only constructor arguments and the `noise=` / `return_costs=`
+hooks replace the monkey-patching the reference needs for the same purpose.
+
+Everything between "state in" and "controls out" runs in libmppi_b200.so on the GPU.
+"""
+from __future__ import annotations
+
+import types
+
+import numpy as np
+import torch
+
+from .. import _native
+from ..core import NativeSolver
+from ..utils.pose import Pose
+
+
+class MPPI:
+    MODEL = _native.MODEL_ARM7
+
+    def __init__(self, *, n_samples: int = 100, n_horizon: int = 32, dt: float = 0.01, sigma=0.1, lam: float = 0.1,
+                 seed: int = 0, device=None, verbose: bool = True):
+        self.n_action = 7
+        self.n_manipulator_dof = 7
+        self.n_mobile_dof = 0
+        self.n_samples = int(n_samples)
+        self.n_horizon = int(n_horizon)
+        self.dt = float(dt)
+        self._lambda = float(lam)
+        self._solver = NativeSolver(self.MODEL, n_samples=n_samples, n_horizon=n_horizon, dt=dt, lam=lam, sigma=sigma,
+                                    seed=seed, device=device)
+        self.device = self._solver.device
+        if verbose:
+            print(f"[MPPI] Using device: {self.device}")                      # mppi.py:33
+        sig = torch.eye(self.n_action, device=self.device) * torch.as_tensor(sigma, dtype=torch.float32, device=self.device)
+        self.sample_gen = types.SimpleNamespace(n_sample=self.n_samples, n_horizon=self.n_horizon,
+                                                n_action=self.n_action, sigma=sig, device=self.device)
+        self.target_pose = Pose()
+        self.target_pose.pose = torch.tensor([0.1029, 0.4055, 1.6498])        # mppi.py:71
+        self.target_pose.orientation = torch.tensor([-0.5, -0.5, 0.5, -0.5])  # mppi.py:72
+        self._target_sent = None
+        self.ee_pose = Pose()
+        self._q64 = np.zeros(7)
+        self._qdot64 = np.zeros(7)
+        self._base64 = np.array([0, 0, 0, 0, 0, 0, 1.0])
+        self._state_dtype = np.float32        # float64 once update_joint() feeds numpy doubles
+        self._push_state()
+        self.qdes = torch.zeros(7)
+        self.vdes = torch.zeros(7)
+        self.last_costs = None
+        self.last_stats = {}
+        self.cnt = 0
+
+    # ------------------------------------------------------------------ reference attribute surface
+    @property
+    def u_prev(self) -> torch.Tensor:
+        return self._solver.u_prev
+
+    @u_prev.setter
+    def u_prev(self, value):
+        self._solver.u_prev = value
+
+    @property
+    def u(self) -> torch.Tensor:
+        return self._solver.u_prev[0]
+
+    @property
+    def _qddot(self) -> torch.Tensor:
+        return self._solver._u[self._solver._cur ^ 1][0]
+
+    @property
+    def _q(self) -> torch.Tensor:
+        return torch.as_tensor(self._q64.astype(self._state_dtype), device=self.device)
+
+    @_q.setter
+    def _q(self, v):
+        self._q64 = np.asarray(torch.as_tensor(v).detach().cpu().numpy(), np.float64).copy()
+        self._push_state()
+
+    @property
+    def _qdot(self) -> torch.Tensor:
+        return torch.as_tensor(self._qdot64.astype(self._state_dtype), device=self.device)
+
+    @_qdot.setter
+    def _qdot(self, v):
+        self._qdot64 = np.asarray(torch.as_tensor(v).detach().cpu().numpy(), np.float64).copy()
+        self._push_state()
+
+    @property
+    def base_pose(self) -> torch.Tensor:
+        return torch.as_tensor(self._base64.astype(self._state_dtype), device=self.device)
+
+    @base_pose.setter
+    def base_pose(self, v):
+        self._base64 = np.asarray(torch.as_tensor(v).detach().cpu().numpy(), np.float64).copy()
+        self._push_state()
+
+    def _push_state(self):
+        self._solver.set_state(np.concatenate([self._q64, self._qdot64, self._base64]))
+
+    def update_joint(self, q_full, v_full):
+        """mppi.py:196-200.  Safe to call from the subscriber thread while a step is running."""
+        q_full = np.asarray(q_full, np.float64)
+        v_full = np.asarray(v_full, np.float64)
+        self._q64 = q_full[7:14].copy()
+        self._qdot64 = v_full[6:13].copy()
+        self._base64 = q_full[:7].copy()
+        self._state_dtype = np.float64
+        self._push_state()
+
+    # ------------------------------------------------------------------ the control step
+    def _sync_target(self):
+        tgt = self.target_pose.as_floats()
+        if tgt != self._target_sent:
+            self._solver.set_target(pos=tgt[:3], quat=tgt[3:])
+            self._target_sent = tgt
+
+    def compute_control_input(self, noise=None, noise_layout: str = "tkn", return_costs: bool = False):
+        """mppi.py:122-169.  `noise`: optional injected noise, [T][K][nu] ("tkn") or the
+        reference's [K][T][nu] ("ktn"); default is in-kernel Philox(seed, step counter)."""
+        self._sync_target()
+        q0 = self._q64.astype(self._state_dtype)
+        qd0 = self._qdot64.astype(self._state_dtype)
+        out = self._solver.step(self._solver.prepare_noise(noise, noise_layout))
+        f32 = np.float32
+        u0 = out[_native.MPPI_OUT_U0_NEW:_native.MPPI_OUT_U0_NEW + 7].copy()
+        qdd = out[_native.MPPI_OUT_U0_OLD:_native.MPPI_OUT_U0_OLD + 7].copy()
+        # mppi.py:157-158 in the reference's own arithmetic (float32 control terms, state dtype sum)
+        vdes = qd0 + u0 * f32(self.dt)
+        qdes = q0 + qdd * f32(self.dt) + f32(0.5) * u0 * f32(self.dt) * f32(self.dt)
+        self.vdes, self.qdes = torch.from_numpy(vdes), torch.from_numpy(qdes)
+        self.last_stats = {"rho": float(out[_native.MPPI_OUT_RHO]), "eta": float(out[_native.MPPI_OUT_ETA]),
+                           "ess": float(out[_native.MPPI_OUT_ESS]), "reach_err": float(out[_native.MPPI_OUT_REACH])}
+        self.cnt += 1
+        if self.last_stats["reach_err"] < 0.005:                               # mppi.py:117,165-166
+            print("Reach !")
+        if return_costs:
+            self.last_costs = self._solver.costs.clone()
+            return qdes, vdes, self.last_costs
+        return qdes, vdes
+
+    def check_reach(self, q_full=None) -> bool:
+        """mppi.py:95-120: the position error of FK(base, qdes) is computed by the finalize kernel."""
+        return self.last_stats.get("reach_err", float("inf")) < 0.005
+
+    def compute_weights(self, S: torch.Tensor, _lambda) -> torch.Tensor:
+        """mppi.py:173-193, kept for API compatibility (the step itself weights on the device)."""
+        rho = S.min()
+        e = torch.exp((-1.0 / _lambda) * (S - rho))
+        return e / e.sum()

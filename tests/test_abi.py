@@ -1,0 +1,66 @@
+"""CPU-side checks of the native boundary: the library builds, loads, exports every symbol
+include/mppi_b200.h declares, and the ctypes mirror of mppi_config_t matches.  No compute calls."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "mppi_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mppi_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_and_exports_header_symbols():
+    from quadrotor_manipulator_mppi_b200 import _native, build
+    path = build.build()
+    assert os.path.exists(path)
+    lib = C.CDLL(path)
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in mppi_b200.h but not exported"
+    assert sorted(_native.EXPORTS) == declared
+
+
+def test_config_struct_mirror_and_defaults():
+    from quadrotor_manipulator_mppi_b200 import _native
+    assert C.sizeof(_native.MppiConfig) == 224
+    arm = _native.default_config(_native.MODEL_ARM7)
+    assert (arm.n_samples, arm.n_horizon, arm.savgol_window) == (100, 32, 9)      # mppi.py:40-41,149
+    assert abs(arm.sigma[0] - 0.1) < 1e-7 and abs(arm.lambda_ - 0.1) < 1e-7 and abs(arm.dt - 0.01) < 1e-9
+    assert list(arm.cost_w)[:4] == [50.0, 30.0, 40.0, 30.0]                      # cost_manager.py:30-33
+    drone = _native.default_config(_native.MODEL_DRONE3)
+    assert (drone.n_samples, drone.n_horizon, drone.savgol_window) == (1000, 32, 5)  # drone_mppi.py:16-17,160
+    assert drone.sigma[0] == 30.0 and list(drone.drone_target) == pytest.approx([1.0, 2.0, 3.4], rel=1e-6)
+    assert _native.algorithmic_flops(_native.MODEL_WB11) == 1000.0
+    with pytest.raises(_native.MppiError):
+        _native.default_config(17)
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path must fail loudly (never route through oracle/)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("has a GPU")
+    from quadrotor_manipulator_mppi_b200.mppi_solver.mppi import MPPI
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        MPPI(verbose=False)
+    from quadrotor_manipulator_mppi_b200 import _native
+    h = C.c_void_p()
+    cfg = _native.default_config(_native.MODEL_ARM7)
+    rc = _native.load().mppi_create(C.byref(cfg), C.byref(h))
+    assert rc == 3 and b"no CPU fallback" in _native.load().mppi_last_error(None)
+
+
+def test_product_package_never_imports_oracle():
+    pkg = os.path.join(ROOT, "quadrotor_manipulator_mppi_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "libmppi_oracle" not in src, f
