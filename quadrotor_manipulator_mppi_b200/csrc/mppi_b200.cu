@@ -154,6 +154,7 @@ struct mppi_ctx {
     float *h_pinned = nullptr;      // pinned staging for the host-buffer API
     size_t h_pinned_floats = 0;
     int max_parts = 0;
+    bool baked_fk = false;          // runtime chain == compile-time FkKinova tables
     cudaStream_t own_stream = nullptr;
     std::string err;
 };
@@ -220,6 +221,12 @@ mppi_status_t set_chain_impl(mppi_ctx *h, int n, const int32_t *types, const flo
     for (int i = 0; i < 16; ++i) dev = std::fmax(dev, std::fabs(C.m[i] - I.m[i]));
     ch.n = nrev;
     ch.last_identity = dev < 1e-12;
+    bool baked = (nrev == FkKinova::kJoints);
+    for (int j = 0; baked && j <= nrev; ++j) {
+        for (int i = 0; i < 9; ++i) baked = baked && std::fabs(ch.R[j][i] - FkKinova::R[j][i]) < 1e-6f;
+        for (int i = 0; i < 3; ++i) baked = baked && std::fabs(ch.t[j][i] - FkKinova::t[j][i]) < 1e-6f;
+    }
+    h->baked_fk = baked;
     if (nrev != 7) return fail(h, MPPI_ERR_UNSUPPORTED, "the arm kernels are built for 7 revolute joints");
     h->P.chain = ch;
     return MPPI_OK;
@@ -231,10 +238,18 @@ mppi_status_t launch_rollout(mppi_ctx *h, const float *d_u_nom, const float *d_n
     constexpr int NU = ModelNu<MODEL>::value;
     const int grid = (h->P.K + kRolloutThreads - 1) / kRolloutThreads;
     const size_t smem = (size_t)h->P.T * NU * sizeof(float);
-    if (d_noise)
-        rollout_cost_kernel<MODEL, false><<<grid, kRolloutThreads, smem, st>>>(h->P, h->dyn, d_u_nom, d_noise, d_cost, h->d_rho);
-    else
-        rollout_cost_kernel<MODEL, true><<<grid, kRolloutThreads, smem, st>>>(h->P, h->dyn, d_u_nom, nullptr, d_cost, h->d_rho);
+    constexpr bool HAS_ARM = (MODEL == MPPI_MODEL_ARM7 || MODEL == MPPI_MODEL_WB11);
+    if (HAS_ARM && h->baked_fk) {        // FK unrolled from the URDF constants (fk_tables_gen.cuh)
+        if (d_noise)
+            rollout_cost_kernel<MODEL, false, HAS_ARM><<<grid, kRolloutThreads, smem, st>>>(h->P, h->dyn, d_u_nom, d_noise, d_cost, h->d_rho);
+        else
+            rollout_cost_kernel<MODEL, true, HAS_ARM><<<grid, kRolloutThreads, smem, st>>>(h->P, h->dyn, d_u_nom, nullptr, d_cost, h->d_rho);
+    } else {                             // any other chain: constants from the kernel parameter block
+        if (d_noise)
+            rollout_cost_kernel<MODEL, false, false><<<grid, kRolloutThreads, smem, st>>>(h->P, h->dyn, d_u_nom, d_noise, d_cost, h->d_rho);
+        else
+            rollout_cost_kernel<MODEL, true, false><<<grid, kRolloutThreads, smem, st>>>(h->P, h->dyn, d_u_nom, nullptr, d_cost, h->d_rho);
+    }
     MPPI_CUDA(h, cudaGetLastError());
     return MPPI_OK;
 }
@@ -418,6 +433,10 @@ mppi_status_t mppi_create(const mppi_config_t *cfg, mppi_handle_t *out)
     P.K = cfg->n_samples; P.T = cfg->n_horizon; P.nu = nu; P.nch = (nu + 3) / 4;
     P.k_offset = cfg->k_offset;
     P.seed_lo = (uint32_t)cfg->seed; P.seed_hi = (uint32_t)(cfg->seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        P.rkeys[2 * r] = P.seed_lo + (uint32_t)r * 0x9E3779B9u;
+        P.rkeys[2 * r + 1] = P.seed_hi + (uint32_t)r * 0xBB67AE85u;
+    }
     P.dt = cfg->dt;
     P.dt2 = (float)((double)cfg->dt * (double)cfg->dt);        // python dt**2 on floats
     P.inv_lambda = (float)(1.0 / (double)cfg->lambda_);        // (-1.0 / _lambda), mppi.py:187

@@ -9,6 +9,7 @@
 #include <stdint.h>
 
 #include "mppi_b200.h"
+#include "fk_tables_gen.cuh"
 
 namespace mppi {
 
@@ -29,6 +30,7 @@ struct StepParams {
     int K, T, nu, nch;           // nch = ceil(nu/4) Philox calls per (sample, step)
     long long k_offset;          // global index of local sample 0
     unsigned seed_lo, seed_hi;
+    unsigned rkeys[20];          // Philox round keys: seed + r * (0x9E3779B9, 0xBB67AE85)
     float dt, dt2, inv_lambda;
     int sg_window, sg_half;
     float sigma[MPPI_MAX_NU];
@@ -61,25 +63,32 @@ template <> struct ModelNu<MPPI_MODEL_WB11>   { static constexpr int value = 11;
 // never has to exist in HBM; explicit _rn intrinsics keep the two call sites bit-identical
 // regardless of how the surrounding code is contracted into FMAs.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k)
+// The ten round keys (key + r * Weyl constants) depend only on the seed: the host expands them
+// once into StepParams::rkeys, so a round is 2 IMAD.WIDE + 2 LOP3 with constant-bank operands.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, const uint32_t *rk)
 {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
         const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
-        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-        k.x += 0x9E3779B9u;
-        k.y += 0xBB67AE85u;
+        c = make_uint4(hi1 ^ c.y ^ rk[2 * r], lo1, hi0 ^ c.w ^ rk[2 * r + 1], lo0);
     }
     return c;
 }
 
-// u1 = 2 - [1,2) in (0,1];  theta = ([1,2) - 1.5) * 2pi in [-pi,pi);  MUFU lg2 / sin / cos.
+// u1 = 2 - [1,2) in (0,1];  theta = ([1,2) - 1.5) * 2pi in [-pi,pi);  MUFU lg2 / sqrt / sin / cos.
+// r = sqrt(-2 ln u1) = sqrt(lg2(u1) * (-2 ln 2)); sqrt.approx maps 0 -> 0 (u1 == 1).
+__device__ __forceinline__ float sqrt_approx(float x)
+{
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ void box_muller(uint32_t x, uint32_t y, float &n0, float &n1)
 {
     const float u1 = __fsub_rn(2.0f, __uint_as_float(0x3f800000u | (x >> 9)));
     const float th = __fmul_rn(__fsub_rn(__uint_as_float(0x3f800000u | (y >> 9)), 1.5f), kTwoPi);
-    const float r = __fsqrt_rn(__fmul_rn(-2.0f, __logf(u1)));
+    const float r = sqrt_approx(__fmul_rn(__log2f(u1), -1.3862943611198906f));
     float s, c;
     __sincosf(th, &s, &c);
     n0 = __fmul_rn(r, c);
@@ -89,9 +98,9 @@ __device__ __forceinline__ void box_muller(uint32_t x, uint32_t y, float &n0, fl
 // Four standard normals for inputs 4*chunk..4*chunk+3 of (global sample kg, horizon step t):
 // counter = (kg, t*nch + chunk, step_lo, step_hi), key = seed.
 __device__ __forceinline__ void normal4(uint32_t kg, uint32_t tc, uint32_t step_lo, uint32_t step_hi,
-                                        uint32_t seed_lo, uint32_t seed_hi, float n[4])
+                                        const uint32_t *rkeys, float n[4])
 {
-    const uint4 r = philox4x32_10(make_uint4(kg, tc, step_lo, step_hi), make_uint2(seed_lo, seed_hi));
+    const uint4 r = philox4x32_10(make_uint4(kg, tc, step_lo, step_hi), rkeys);
     box_muller(r.x, r.y, n[0], n[1]);
     box_muller(r.z, r.w, n[2], n[3]);
 }
@@ -150,6 +159,89 @@ __device__ __forceinline__ void compose_const(float R[9], float p[3], const floa
         R[3 * r]     = fmaf(a, Cr[0], fmaf(b, Cr[3], c * Cr[6]));
         R[3 * r + 1] = fmaf(a, Cr[1], fmaf(b, Cr[4], c * Cr[7]));
         R[3 * r + 2] = fmaf(a, Cr[2], fmaf(b, Cr[5], c * Cr[8]));
+    }
+}
+
+// sin and cos of x to ~1 ulp (max abs error 1.4e-7) without the libm slow path: reduce by pi
+// (2-term Cody-Waite under FMA) to r in [-pi/2, pi/2], near-minimax polynomials in r^2, one sign
+// flip.  Valid for |x| < ~1e4 (joint and Euler angles here stay within a few turns).
+__device__ __forceinline__ void sincos_pi(float x, float &s, float &c)
+{
+    const float kf = fmaf(x, 0.318309886183790672f, 12582912.0f);       // 1.5 * 2^23: rint in the low bits
+    const int n = __float_as_int(kf);
+    const float k = kf - 12582912.0f;
+    float r = fmaf(k, -3.14159274101257324f, x);
+    r = fmaf(k, 8.742278000372485e-8f, r);
+    const float z = r * r;
+    float ps = fmaf(2.634697921166662e-06f, z, -0.00019822725153062493f);
+    ps = fmaf(ps, z, 0.008333242498338223f);
+    ps = fmaf(ps, z, -0.1666666567325592f);
+    float pc = fmaf(-2.62966580066859e-07f, z, 2.4774544726824388e-05f);
+    pc = fmaf(pc, z, -0.0013888651737943292f);
+    pc = fmaf(pc, z, 0.0416666604578495f);
+    pc = fmaf(pc, z, -0.5f);
+    const float sr = fmaf(ps, z * r, r);
+    const float cr = fmaf(pc, z, 1.0f);
+    const int flip = n << 31;                                             // odd multiple of pi: negate both
+    s = __int_as_float(__float_as_int(sr) ^ flip);
+    c = __int_as_float(__float_as_int(cr) ^ flip);
+}
+
+// ---- FK with compile-time constants (tables from tools/gen_fk_tables.py) -------------------
+// acc (+)= x * k where k is a constant expression: zero terms vanish, +-1 become add / sub.
+#define MPPI_CTERM(acc, have, x, k)                                                                   \
+    if constexpr ((k) != 0.0f) {                                                                      \
+        if constexpr (!(have)) acc = ((k) == 1.0f) ? (x) : ((k) == -1.0f) ? -(x) : (x) * (k);         \
+        else acc = ((k) == 1.0f) ? acc + (x) : ((k) == -1.0f) ? acc - (x) : fmaf((x), (k), acc);      \
+    }
+
+template <class Tab, int J, int COL>
+__device__ __forceinline__ float tab_rot_col(float a, float b, float c)
+{
+    constexpr float k0 = Tab::R[J][COL], k1 = Tab::R[J][3 + COL], k2 = Tab::R[J][6 + COL];
+    constexpr bool h1 = (k0 != 0.0f), h2 = h1 || (k1 != 0.0f);
+    float acc = 0.0f;
+    MPPI_CTERM(acc, false, a, k0)
+    MPPI_CTERM(acc, h1, b, k1)
+    MPPI_CTERM(acc, h2, c, k2)
+    return acc;
+}
+template <class Tab, int J>
+__device__ __forceinline__ float tab_trans(float a, float b, float c, float p)
+{
+    constexpr float k0 = Tab::t[J][0], k1 = Tab::t[J][1], k2 = Tab::t[J][2];
+    float acc = p;
+    MPPI_CTERM(acc, true, a, k0)
+    MPPI_CTERM(acc, true, b, k1)
+    MPPI_CTERM(acc, true, c, k2)
+    return acc;
+}
+// (R,p) <- (R C_J.R, p + R C_J.t) with C_J from the table
+template <class Tab, int J>
+__device__ __forceinline__ void compose_tab(float R[9], float p[3])
+{
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const float a = R[3 * r], b = R[3 * r + 1], c = R[3 * r + 2];
+        p[r] = tab_trans<Tab, J>(a, b, c, p[r]);
+        R[3 * r] = tab_rot_col<Tab, J, 0>(a, b, c);
+        R[3 * r + 1] = tab_rot_col<Tab, J, 1>(a, b, c);
+        R[3 * r + 2] = tab_rot_col<Tab, J, 2>(a, b, c);
+    }
+}
+template <class Tab, int J = 0>
+__device__ __forceinline__ void fk_tab(const float *cq, const float *sq, float R[9], float p[3])
+{
+    if constexpr (J < Tab::kJoints) {
+        const float c = cq[J], s = sq[J];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const float a = R[3 * r], b = R[3 * r + 1];
+            R[3 * r] = fmaf(c, a, s * b);
+            R[3 * r + 1] = fmaf(c, b, -s * a);
+        }
+        compose_tab<Tab, J + 1>(R, p);
+        fk_tab<Tab, J + 1>(cq, sq, R, p);
     }
 }
 
@@ -226,18 +318,18 @@ __device__ __forceinline__ void quad_advance(QuadState &s, float F, float tx, fl
     s.rpy[2] = wrap_pi(fmaf(dt, dpsi, s.rpy[2]));
     s.v[0] = fmaf(dt, ax, s.v[0]); s.v[1] = fmaf(dt, ay, s.v[1]); s.v[2] = fmaf(dt, az, s.v[2]);
     s.p[0] = fmaf(dt, s.v[0], s.p[0]); s.p[1] = fmaf(dt, s.v[1], s.p[1]); s.p[2] = fmaf(dt, s.v[2], s.p[2]);
-    sincosf(s.rpy[0], &s.sphi, &s.cphi);
-    sincosf(s.rpy[1], &s.sth, &s.cth);
-    sincosf(s.rpy[2], &s.spsi, &s.cpsi);
+    sincos_pi(s.rpy[0], s.sphi, s.cphi);
+    sincos_pi(s.rpy[1], s.sth, s.cth);
+    sincos_pi(s.rpy[2], s.spsi, s.cpsi);
 }
 
 __device__ __forceinline__ void quad_load(QuadState &s, const float *st)
 {
 #pragma unroll
     for (int i = 0; i < 3; ++i) { s.p[i] = st[i]; s.rpy[i] = st[3 + i]; s.v[i] = st[6 + i]; s.w[i] = st[9 + i]; }
-    sincosf(s.rpy[0], &s.sphi, &s.cphi);
-    sincosf(s.rpy[1], &s.sth, &s.cth);
-    sincosf(s.rpy[2], &s.spsi, &s.cpsi);
+    sincos_pi(s.rpy[0], s.sphi, s.cphi);
+    sincos_pi(s.rpy[1], s.sth, s.cth);
+    sincos_pi(s.rpy[2], s.spsi, s.cpsi);
 }
 
 // ------------------------------------------------------------------------------------------

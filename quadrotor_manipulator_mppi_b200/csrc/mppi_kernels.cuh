@@ -22,7 +22,7 @@ constexpr int kWeightTile = 2048;       // samples whose weights are staged in s
 // Replaces S/mppi_solver/mppi.py:129-140 (sampling, get_sample_joint, compute_fk_gpu,
 // CostManager.compute_all_cost) and S/mppi_solver/drone_mppi.py:143-151.
 // ------------------------------------------------------------------------------------------
-template <int MODEL, bool PHILOX>
+template <int MODEL, bool PHILOX, bool BAKED>
 __global__ void __launch_bounds__(kRolloutThreads)
 rollout_cost_kernel(const __grid_constant__ StepParams P, const __grid_constant__ DynBlock D,
                     const float *__restrict__ u_nom, const float *__restrict__ noise,
@@ -80,7 +80,8 @@ rollout_cost_kernel(const __grid_constant__ StepParams P, const __grid_constant_
     if constexpr (MODEL == MPPI_MODEL_ARM7) {
         quat_matrix(&D.state[14], R0);                       // base xyz+quat -> B (S/robot/urdf_fk.py:30-55)
         p0[0] = D.state[14]; p0[1] = D.state[15]; p0[2] = D.state[16];
-        compose_const(R0, p0, P.chain.R[0], P.chain.t[0]);
+        if constexpr (BAKED) compose_tab<FkKinova, 0>(R0, p0);
+        else compose_const(R0, p0, P.chain.R[0], P.chain.t[0]);
     }
     if constexpr (HAS_QUAD) quad_load(qs, D.state);
 
@@ -95,7 +96,7 @@ rollout_cost_kernel(const __grid_constant__ StepParams P, const __grid_constant_
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
                 float n4[4];
-                normal4(kg, static_cast<uint32_t>(t * NCH + c), D.step_lo, D.step_hi, P.seed_lo, P.seed_hi, n4);
+                normal4(kg, static_cast<uint32_t>(t * NCH + c), D.step_lo, D.step_hi, P.rkeys, n4);
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     if (4 * c + j < NU) a[4 * c + j] = __fmul_rn(P.sigma[4 * c + j], n4[j]);
@@ -139,7 +140,7 @@ rollout_cost_kernel(const __grid_constant__ StepParams P, const __grid_constant_
                 cum_v[i] = fmaf(ai, P.dt, cum_v[i]);
                 vprev[i] = cum_v[i] + D.state[QOFF + 7 + i];
                 cum_q[i] += dq;
-                sincosf(cum_q[i] + D.state[QOFF + i], &sq[i], &cq[i]);
+                sincos_pi(cum_q[i] + D.state[QOFF + i], sq[i], cq[i]);
             }
             float R[9], p[3];
             if constexpr (MODEL == MPPI_MODEL_ARM7) {
@@ -150,9 +151,11 @@ rollout_cost_kernel(const __grid_constant__ StepParams P, const __grid_constant_
                 // moving base T(p_t, rpy_t) (S/robot/transformation_matrix.py:148-187)
                 rpy_matrix(qs.sphi, qs.cphi, qs.sth, qs.cth, qs.spsi, qs.cpsi, R);
                 p[0] = qs.p[0]; p[1] = qs.p[1]; p[2] = qs.p[2];
-                compose_const(R, p, P.chain.R[0], P.chain.t[0]);
+                if constexpr (BAKED) compose_tab<FkKinova, 0>(R, p);
+                else compose_const(R, p, P.chain.R[0], P.chain.t[0]);
             }
-            fk_chain<7>(P.chain, cq, sq, R, p);
+            if constexpr (BAKED) fk_tab<FkKinova>(cq, sq, R, p);
+            else fk_chain<7>(P.chain, cq, sq, R, p);
             float pos, ori;
             pose_terms(R, p, D, pos, ori);
             // S/cost/cost_manager.py:30-33,78-89
@@ -368,7 +371,7 @@ weight_philox_kernel(const __grid_constant__ StepParams P, const __grid_constant
                 if (w == 0.f) continue;
                 float n4[4];
                 normal4(static_cast<uint32_t>(P.k_offset + base + kk), static_cast<uint32_t>(tc),
-                        D.step_lo, D.step_hi, P.seed_lo, P.seed_hi, n4);
+                        D.step_lo, D.step_hi, P.rkeys, n4);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[j] = fmaf(w, __fmul_rn(sg[j], n4[j]), acc[j]);
             }
@@ -507,7 +510,7 @@ generate_noise_kernel(const __grid_constant__ StepParams P, uint32_t step_lo, ui
         const int t = static_cast<int>(tk / P.K);
         float n4[4];
         normal4(static_cast<uint32_t>(P.k_offset + k), static_cast<uint32_t>(t * NCH + c), step_lo, step_hi,
-                P.seed_lo, P.seed_hi, n4);
+                P.rkeys, n4);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
             if (4 * c + j < NU) noise[(static_cast<size_t>(t) * P.K + k) * NU + 4 * c + j] = __fmul_rn(P.sigma[4 * c + j], n4[j]);
