@@ -281,13 +281,13 @@ def run_native(args):
     def one_step():
         if world == 1:
             solver.step_async(noise)
-            return 2
+            return 2 if noise is None else 3        # rollout + weighting(+finalize) [+ weights kernel]
         solver.rollout(noise)
         dist.all_reduce(solver.rho_enc, op=dist.ReduceOp.MIN)
         solver.weight(noise)
         dist.all_reduce(solver.wsum, op=dist.ReduceOp.SUM)
         solver.finalize()
-        return 3
+        return 3 if noise is None else 4
 
     def barrier():
         if world > 1:

@@ -147,6 +147,9 @@ struct mppi_ctx {
     uint32_t *d_counter = nullptr;  // last-block-done counter
     float *d_part = nullptr;        // [max_parts][T*nu+2]
     float *d_wsum = nullptr;        // [T*nu+2]
+    float *d_w = nullptr;           // [K] unnormalised weights (injected-noise path)
+    float *d_eta_part = nullptr;    // [<=SMs][2] partial sums of w, w^2
+    int wn_resident = 0;            // resident blocks of the streaming weighting kernel (one wave)
     float *d_u = nullptr;           // [T*nu]   (host-buffer API)
     float *d_out = nullptr;         // [MPPI_OUT_FLOATS]
     float *d_noise = nullptr;       // host-buffer API with injected noise, grown on demand
@@ -155,6 +158,7 @@ struct mppi_ctx {
     size_t h_pinned_floats = 0;
     int max_parts = 0;
     bool baked_fk = false;          // runtime chain == compile-time FkKinova tables
+    size_t rollout_smem[4] = {0, 0, 0, 0};   // tuned dynamic smem per kernel variant (0 = not yet tuned)
     cudaStream_t own_stream = nullptr;
     std::string err;
 };
@@ -232,26 +236,55 @@ mppi_status_t set_chain_impl(mppi_ctx *h, int n, const int32_t *types, const flo
     return MPPI_OK;
 }
 
+// The rollout kernel is issue-bound, so its time is (number of waves) x (blocks resident per SM).
+// Pick the residency o <= o_max that minimises ceil(blocks / (SMs * o)) * o -- i.e. avoid a nearly
+// empty last wave -- and enforce it by padding the dynamic shared memory request.
+template <typename KernelT>
+size_t tuned_rollout_smem(mppi_ctx *h, KernelT kernel, int grid, size_t smem_needed)
+{
+    int omax = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&omax, kernel, kRolloutThreads, smem_needed) != cudaSuccess || omax < 1) {
+        cudaGetLastError();
+        return smem_needed;
+    }
+    auto cost = [&](int o) { return (long long)((grid + (long long)h->num_sms * o - 1) / ((long long)h->num_sms * o)) * o; };
+    int best_o = omax;
+    long long best = cost(omax);
+    for (int o = omax - 1; o >= 5 && o >= omax - 3; --o)
+        if (cost(o) < best) { best = cost(o); best_o = o; }
+    if (best_o == omax) return smem_needed;
+    size_t pad = (size_t)(228 * 1024) / best_o - 1024 - 256;      // 1 KB per block is reserved by the driver
+    pad &= ~(size_t)255;
+    if (pad < smem_needed || pad > 48 * 1024) return smem_needed;
+    int got = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&got, kernel, kRolloutThreads, pad) != cudaSuccess || got != best_o) {
+        cudaGetLastError();
+        return smem_needed;
+    }
+    return pad;
+}
+
 template <int MODEL>
 mppi_status_t launch_rollout(mppi_ctx *h, const float *d_u_nom, const float *d_noise, float *d_cost, cudaStream_t st)
 {
     constexpr int NU = ModelNu<MODEL>::value;
+    constexpr bool HAS_ARM = (MODEL == MPPI_MODEL_ARM7 || MODEL == MPPI_MODEL_WB11);
     const int grid = (h->P.K + kRolloutThreads - 1) / kRolloutThreads;
     const size_t smem = (size_t)h->P.T * NU * sizeof(float);
-    constexpr bool HAS_ARM = (MODEL == MPPI_MODEL_ARM7 || MODEL == MPPI_MODEL_WB11);
-    if (HAS_ARM && h->baked_fk) {        // FK unrolled from the URDF constants (fk_tables_gen.cuh)
-        if (d_noise)
-            rollout_cost_kernel<MODEL, false, HAS_ARM><<<grid, kRolloutThreads, smem, st>>>(h->P, h->dyn, d_u_nom, d_noise, d_cost, h->d_rho);
-        else
-            rollout_cost_kernel<MODEL, true, HAS_ARM><<<grid, kRolloutThreads, smem, st>>>(h->P, h->dyn, d_u_nom, nullptr, d_cost, h->d_rho);
-    } else {                             // any other chain: constants from the kernel parameter block
-        if (d_noise)
-            rollout_cost_kernel<MODEL, false, false><<<grid, kRolloutThreads, smem, st>>>(h->P, h->dyn, d_u_nom, d_noise, d_cost, h->d_rho);
-        else
-            rollout_cost_kernel<MODEL, true, false><<<grid, kRolloutThreads, smem, st>>>(h->P, h->dyn, d_u_nom, nullptr, d_cost, h->d_rho);
+    const bool baked = HAS_ARM && h->baked_fk;      // FK unrolled from the URDF constants (fk_tables_gen.cuh)
+    const int variant = (d_noise ? 0 : 1) + (baked ? 2 : 0);
+    auto go = [&](auto kernel) -> mppi_status_t {
+        if (h->rollout_smem[variant] == 0) h->rollout_smem[variant] = tuned_rollout_smem(h, kernel, grid, smem);
+        kernel<<<grid, kRolloutThreads, h->rollout_smem[variant], st>>>(h->P, h->dyn, d_u_nom, d_noise, d_cost, h->d_rho);
+        MPPI_CUDA(h, cudaGetLastError());
+        return MPPI_OK;
+    };
+    switch (variant) {
+        case 0: return go(rollout_cost_kernel<MODEL, false, false>);
+        case 1: return go(rollout_cost_kernel<MODEL, true, false>);
+        case 2: return go(rollout_cost_kernel<MODEL, false, HAS_ARM>);
+        default: return go(rollout_cost_kernel<MODEL, true, HAS_ARM>);
     }
-    MPPI_CUDA(h, cudaGetLastError());
-    return MPPI_OK;
 }
 
 template <int MODEL>
@@ -280,21 +313,37 @@ mppi_status_t launch_weight(mppi_ctx *h, const float *d_noise, bool fuse, const 
             h->P, h->dyn, h->d_cost, h->d_rho, chunk, h->d_part, h->d_counter, h->d_wsum, fuse ? 1 : 0, d_u_nom, d_u_new, d_out);
     } else {
         const bool vec4 = ((size_t)K * NU) % 4 == 0 && (reinterpret_cast<uintptr_t>(d_noise) & 15u) == 0;
-        int chunk = 4096;
-        while (chunk > 128 && (long long)((K + chunk - 1) / chunk) * T < 4LL * h->num_sms) chunk >>= 1;
-        int blocks = (K + chunk - 1) / chunk;
-        if (blocks > h->max_parts) { chunk = ((K + h->max_parts - 1) / h->max_parts + 127) / 128 * 128; blocks = (K + chunk - 1) / chunk; }
-        size_t smem_floats = (size_t)chunk;
-        if (smem_floats < (size_t)32 * NU * 4) smem_floats = (size_t)32 * NU * 4;
+        // weights once, then one resident wave of (G x T) streaming blocks
+        int wblocks = (K + 1023) / 1024;
+        if (wblocks > h->num_sms) wblocks = h->num_sms;
+        weights_kernel<<<wblocks, 256, 0, st>>>(h->P, h->d_cost, h->d_rho, h->d_w, h->d_eta_part);
+        MPPI_CUDA(h, cudaGetLastError());
+        const int threads = 32 * NU;
+        size_t smem_floats = (size_t)threads * 4;
         if (smem_floats < fin_floats) smem_floats = fin_floats;
-        if (smem_floats * sizeof(float) > 48 * 1024) return fail(h, MPPI_ERR_UNSUPPORTED, "weighting scratch exceeds 48 KB of shared memory");
-        dim3 grid(blocks, T);
+        if (h->wn_resident == 0) {
+            int per_sm = 0;
+            cudaError_t oe = vec4 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, weighted_noise_kernel<MODEL, 4>, threads, smem_floats * sizeof(float))
+                                  : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, weighted_noise_kernel<MODEL, 1>, threads, smem_floats * sizeof(float));
+            if (oe != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 2; }
+            h->wn_resident = per_sm * h->num_sms;
+        }
+        int G = h->wn_resident / T;
+        if (G < 1) G = 1;
+        if (G > h->max_parts) G = h->max_parts;
+        const int gmax = (K + 127) / 128;
+        if (G > gmax) G = gmax;
+        int chunk = ((K + G - 1) / G + 127) / 128 * 128;
+        G = (K + chunk - 1) / chunk;
+        dim3 grid(G, T);
         if (vec4)
-            weight_injected_kernel<MODEL, 4><<<grid, 32 * NU, smem_floats * sizeof(float), st>>>(
-                h->P, h->dyn, h->d_cost, d_noise, h->d_rho, chunk, h->d_part, h->d_counter, h->d_wsum, fuse ? 1 : 0, d_u_nom, d_u_new, d_out);
+            weighted_noise_kernel<MODEL, 4><<<grid, threads, smem_floats * sizeof(float), st>>>(
+                h->P, h->dyn, h->d_w, d_noise, h->d_rho, chunk, h->d_part, h->d_eta_part, wblocks, h->d_counter, h->d_wsum,
+                fuse ? 1 : 0, d_u_nom, d_u_new, d_out);
         else
-            weight_injected_kernel<MODEL, 1><<<grid, 32 * NU, smem_floats * sizeof(float), st>>>(
-                h->P, h->dyn, h->d_cost, d_noise, h->d_rho, chunk, h->d_part, h->d_counter, h->d_wsum, fuse ? 1 : 0, d_u_nom, d_u_new, d_out);
+            weighted_noise_kernel<MODEL, 1><<<grid, threads, smem_floats * sizeof(float), st>>>(
+                h->P, h->dyn, h->d_w, d_noise, h->d_rho, chunk, h->d_part, h->d_eta_part, wblocks, h->d_counter, h->d_wsum,
+                fuse ? 1 : 0, d_u_nom, d_u_new, d_out);
     }
     MPPI_CUDA(h, cudaGetLastError());
     return MPPI_OK;
@@ -463,6 +512,8 @@ mppi_status_t mppi_create(const mppi_config_t *cfg, mppi_handle_t *out)
     cudaError_t e;
     if ((e = cudaMalloc(&h->d_cost, (size_t)P.K * sizeof(float))) != cudaSuccess) return cleanup(e, "cudaMalloc(cost)");
     if ((e = cudaMalloc(&h->d_rho, 16)) != cudaSuccess) return cleanup(e, "cudaMalloc(rho)");
+    if ((e = cudaMalloc(&h->d_w, (size_t)P.K * sizeof(float))) != cudaSuccess) return cleanup(e, "cudaMalloc(w)");
+    if ((e = cudaMalloc(&h->d_eta_part, (size_t)2 * 1024 * sizeof(float))) != cudaSuccess) return cleanup(e, "cudaMalloc(eta_part)");
     h->d_counter = reinterpret_cast<uint32_t *>(h->d_rho + 1);
     if ((e = cudaMalloc(&h->d_part, (size_t)h->max_parts * row * sizeof(float))) != cudaSuccess) return cleanup(e, "cudaMalloc(partials)");
     if ((e = cudaMalloc(&h->d_wsum, row * sizeof(float))) != cudaSuccess) return cleanup(e, "cudaMalloc(wsum)");
@@ -484,7 +535,7 @@ mppi_status_t mppi_destroy(mppi_handle_t h)
     {
         DeviceGuard guard(h->cfg.device);
         cudaDeviceSynchronize();
-        cudaFree(h->d_cost); cudaFree(h->d_rho); cudaFree(h->d_part); cudaFree(h->d_wsum);
+        cudaFree(h->d_cost); cudaFree(h->d_rho); cudaFree(h->d_w); cudaFree(h->d_eta_part); cudaFree(h->d_part); cudaFree(h->d_wsum);
         cudaFree(h->d_u); cudaFree(h->d_out); cudaFree(h->d_noise);
         if (h->h_pinned) cudaFreeHost(h->h_pinned);
         if (h->own_stream) cudaStreamDestroy(h->own_stream);

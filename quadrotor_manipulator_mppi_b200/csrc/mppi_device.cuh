@@ -187,6 +187,49 @@ __device__ __forceinline__ void sincos_pi(float x, float &s, float &c)
     c = __int_as_float(__float_as_int(cr) ^ flip);
 }
 
+// Branch-free atan2 / asin / approximate reciprocal and square root for the pose cost.  Accuracy
+// (max abs error vs double, measured in tools/fit_math.py): atan2 1.5e-7 + 2-ulp quotient, asin 1.6e-7;
+// rcp / sqrt are the MUFU approximations (<= 2 ulp).  The reference's own float32 atan2/asin carry
+// ~1e-7; these terms enter the cost multiplied by 30 against a float32 ulp of S of 1.2e-4.
+__device__ __forceinline__ float rcp_approx(float x)
+{
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float atan2_poly(float y, float x)
+{
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(fmaxf(ax, ay), 1e-37f), mn = fminf(ax, ay);      // atan2(0, 0) -> 0
+    const float t = mn * rcp_approx(mx);
+    const float z = t * t;
+    float p = fmaf(0.003962172195315361f, z, -0.02036452107131481f);
+    p = fmaf(p, z, 0.049385011196136475f);
+    p = fmaf(p, z, -0.0804230123758316f);
+    p = fmaf(p, z, 0.1087741032242775f);
+    p = fmaf(p, z, -0.14259037375450134f);
+    p = fmaf(p, z, 0.19998809695243835f);
+    p = fmaf(p, z, -0.33333325386047363f);
+    float a = fmaf(p * z, t, t);
+    a = (ay > ax) ? 1.57079632679489662f - a : a;
+    a = (x < 0.0f) ? 3.14159265358979324f - a : a;
+    return copysignf(a, y);
+}
+__device__ __forceinline__ float asin_poly(float x)
+{
+    const float a = fabsf(x);
+    const bool big = a > 0.5f;
+    const float z = big ? fmaf(a, -0.5f, 0.5f) : a * a;
+    const float s = big ? sqrt_approx(z) : a;
+    float p = fmaf(0.038206253200769424f, z, 0.02649438939988613f);
+    p = fmaf(p, z, 0.045010678470134735f);
+    p = fmaf(p, z, 0.07498808950185776f);
+    p = fmaf(p, z, 0.16666673123836517f);
+    float r = fmaf(p * z, s, s);
+    r = big ? fmaf(-2.0f, r, 1.57079632679489662f) : r;
+    return copysignf(r, x);
+}
+
 // ---- FK with compile-time constants (tables from tools/gen_fk_tables.py) -------------------
 // acc (+)= x * k where k is a constant expression: zero terms vanish, +-1 become add / sub.
 #define MPPI_CTERM(acc, have, x, k)                                                                   \
@@ -270,16 +313,16 @@ __device__ __forceinline__ void pose_terms(const float R[9], const float p[3], c
 {
     const float *Tg = D.target_R;
     const float dx = p[0] - D.target_pos[0], dy = p[1] - D.target_pos[1], dz = p[2] - D.target_pos[2];
-    pos = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+    pos = sqrt_approx(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
     const float d00 = fmaf(R[0], Tg[0], fmaf(R[3], Tg[3], R[6] * Tg[6]));
     const float d10 = fmaf(R[1], Tg[0], fmaf(R[4], Tg[3], R[7] * Tg[6]));
     const float d20 = fmaf(R[2], Tg[0], fmaf(R[5], Tg[3], R[8] * Tg[6]));
     const float d21 = fmaf(R[2], Tg[1], fmaf(R[5], Tg[4], R[8] * Tg[7]));
     const float d22 = fmaf(R[2], Tg[2], fmaf(R[5], Tg[5], R[8] * Tg[8]));
-    const float e0 = atan2f(d10, d00);
-    const float e1 = asinf(fminf(fmaxf(-d20, -1.0f), 1.0f));
-    const float e2 = atan2f(d21, d22);
-    ori = sqrtf(fmaf(e0, e0, fmaf(e1, e1, e2 * e2)));
+    const float e0 = atan2_poly(d10, d00);
+    const float e1 = asin_poly(fminf(fmaxf(-d20, -1.0f), 1.0f));
+    const float e2 = atan2_poly(d21, d22);
+    ori = sqrt_approx(fmaf(e0, e0, fmaf(e1, e1, e2 * e2)));
 }
 
 // Quadrotor rigid body, one step (restated from the dead draft S/mppi_solver/drone_mppi.py:57-83;
@@ -298,8 +341,8 @@ __device__ __forceinline__ float wrap_pi(float a)
 __device__ __forceinline__ void quad_advance(QuadState &s, float F, float tx, float ty, float tz,
                                              float dt, const float *qp)
 {
-    const float inv_m = 1.0f / qp[0], kd = qp[4], gz = qp[5];
-    const float inv_cth = 1.0f / s.cth;
+    const float inv_m = rcp_approx(qp[0]), kd = qp[4], gz = qp[5];
+    const float inv_cth = rcp_approx(s.cth);
     const float tth = s.sth * inv_cth;
     const float r02 = s.cpsi * s.sth * s.cphi + s.spsi * s.sphi;
     const float r12 = s.spsi * s.sth * s.cphi - s.cpsi * s.sphi;

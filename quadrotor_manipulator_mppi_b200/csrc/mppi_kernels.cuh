@@ -286,7 +286,8 @@ template <int MODEL>
 __device__ void reduce_partials_and_finalize(const StepParams &P, const DynBlock &D, const float *part,
                                              int n_parts, uint32_t *counter, float *wsum, bool fuse,
                                              const float *u_nom, float *u_new, float *out,
-                                             int32_t *rho_enc, float *scratch)
+                                             int32_t *rho_enc, float *scratch,
+                                             const float *eta_part = nullptr, int n_eta = 0)
 {
     constexpr int NU = ModelNu<MODEL>::value;
     __shared__ bool s_last;
@@ -311,6 +312,10 @@ __device__ void reduce_partials_and_finalize(const StepParams &P, const DynBlock
             acc = ((acc + v0) + v1) + v2 + v3;
         }
         for (; b < n_parts; ++b) acc += __ldcg(part + static_cast<size_t>(b) * row + j);
+        if (eta_part != nullptr && j >= row - 2) {          // eta / sum w^2 come from the weights kernel
+            acc = 0.f;
+            for (int e = 0; e < n_eta; ++e) acc += __ldcg(eta_part + 2 * e + (j - (row - 2)));
+        }
         wsum[j] = acc;
     }
     if (threadIdx.x == 0) *counter = 0u;
@@ -411,38 +416,58 @@ weight_philox_kernel(const __grid_constant__ StepParams P, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------
-// K3 (injected noise [T][K][nu]): HBM-bound re-read.  block = (sample chunk, horizon step t),
-// 32*nu threads; one iteration covers 32*VEC samples = blockDim*VEC contiguous floats, so a
-// thread's VEC components keep the same input index i for the whole loop (coalesced float4).
+// K3a (injected-noise path): w[k] = exp((rho - S[k]) / lambda) once, plus deterministic partial
+// sums of w and w^2.  S/mppi_solver/mppi.py:173-193.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+weights_kernel(const __grid_constant__ StepParams P, const float *__restrict__ S, const int32_t *__restrict__ rho_enc,
+               float *__restrict__ w, float *__restrict__ eta_part)
+{
+    __shared__ float s_e[8], s_e2[8];
+    const float rho = decode_ordered(*rho_enc);
+    float eta = 0.f, eta2 = 0.f;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < P.K; k += gridDim.x * blockDim.x) {
+        const float v = expf(-P.inv_lambda * (S[k] - rho));
+        w[k] = v;
+        eta += v;
+        eta2 = fmaf(v, v, eta2);
+    }
+    eta = warp_sum(eta);
+    eta2 = warp_sum(eta2);
+    if ((threadIdx.x & 31) == 0) { s_e[threadIdx.x >> 5] = eta; s_e2[threadIdx.x >> 5] = eta2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float e = 0.f, e2 = 0.f;
+        for (int i = 0; i < 8; ++i) { e += s_e[i]; e2 += s_e2[i]; }
+        eta_part[2 * blockIdx.x] = e;
+        eta_part[2 * blockIdx.x + 1] = e2;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K3b (injected noise [T][K][nu]): the HBM-bound re-read, a streaming GEMV per horizon step:
+//   out[t][i] = sum_k w[k] * noise[t][k][i].
+// grid = (G, T) sized to ONE resident wave; block (g, t) streams its contiguous K sub-range of row t
+// with 32*nu threads.  One iteration covers 32*VEC samples = blockDim*VEC contiguous floats, so each
+// of a thread's VEC lanes keeps the same input index i for the whole loop (coalesced float4 loads,
+// four in flight per thread); sums stay in registers until one fixed-order block reduction.
 // ------------------------------------------------------------------------------------------
 template <int MODEL, int VEC>
 __global__ void __launch_bounds__(32 * ModelNu<MODEL>::value)
-weight_injected_kernel(const __grid_constant__ StepParams P, const __grid_constant__ DynBlock D,
-                       const float *__restrict__ S, const float *__restrict__ noise, int32_t *rho_enc,
-                       int chunk, float *__restrict__ part, uint32_t *counter, float *wsum, int fuse,
-                       const float *u_nom, float *u_new, float *out)
+weighted_noise_kernel(const __grid_constant__ StepParams P, const __grid_constant__ DynBlock D,
+                      const float *__restrict__ w, const float *__restrict__ noise, int32_t *rho_enc,
+                      int chunk, float *__restrict__ part, const float *__restrict__ eta_part, int n_eta,
+                      uint32_t *counter, float *wsum, int fuse, const float *u_nom, float *u_new, float *out)
 {
     constexpr int NU = ModelNu<MODEL>::value;
     constexpr int NT = 32 * NU;
-    extern __shared__ __align__(16) float s_dyn[];     // weights of the chunk | reduction | finalize scratch
-    float *s_w = s_dyn;
-    __shared__ float s_eta[32], s_eta2[32];
+    constexpr int STEP = 32 * VEC;                     // samples per iteration
+    extern __shared__ __align__(16) float s_dyn[];     // reduction | finalize scratch
 
     const int tid = threadIdx.x;
     const int t = blockIdx.y;
     const int k0 = blockIdx.x * chunk;
-    const int k1 = min(P.K, k0 + chunk);
-    const int nk = k1 - k0;
-    const float rho = decode_ordered(*rho_enc);
-
-    float eta = 0.f, eta2 = 0.f;
-    for (int kk = tid; kk < nk; kk += NT) {
-        const float w = expf(-P.inv_lambda * (S[k0 + kk] - rho));
-        s_w[kk] = w;
-        eta += w;
-        eta2 = fmaf(w, w, eta2);
-    }
-    __syncthreads();
+    const int nk = min(P.K, k0 + chunk) - k0;
 
     int koff[VEC];
 #pragma unroll
@@ -451,31 +476,48 @@ weight_injected_kernel(const __grid_constant__ StepParams P, const __grid_consta
 #pragma unroll
     for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
     const float *row = noise + (static_cast<size_t>(t) * P.K + k0) * NU + tid * VEC;
-    for (int kb = 0; kb < nk; kb += 32 * VEC) {
-        if constexpr (VEC == 4) {
-            if (kb + koff[3] < nk) {       // whole vector in range
+    const float *wk = w + k0;
+    int kb = 0;
+    if constexpr (VEC == 4) {
+        // main loop: 4 iterations in flight
+        for (; kb + 3 * STEP + koff[3] < nk; kb += 4 * STEP) {
+            float4 x[4];
+            float ww[4][4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) x[u] = __ldcs(reinterpret_cast<const float4 *>(row + static_cast<size_t>(kb + u * STEP) * NU));
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) ww[u][v] = __ldg(wk + kb + u * STEP + koff[v]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                acc[0] = fmaf(ww[u][0], x[u].x, acc[0]);
+                acc[1] = fmaf(ww[u][1], x[u].y, acc[1]);
+                acc[2] = fmaf(ww[u][2], x[u].z, acc[2]);
+                acc[3] = fmaf(ww[u][3], x[u].w, acc[3]);
+            }
+        }
+        for (; kb < nk; kb += STEP) {
+            if (kb + koff[3] < nk) {
                 const float4 x = __ldcs(reinterpret_cast<const float4 *>(row + static_cast<size_t>(kb) * NU));
-                acc[0] = fmaf(s_w[kb + koff[0]], x.x, acc[0]);
-                acc[1] = fmaf(s_w[kb + koff[1]], x.y, acc[1]);
-                acc[2] = fmaf(s_w[kb + koff[2]], x.z, acc[2]);
-                acc[3] = fmaf(s_w[kb + koff[3]], x.w, acc[3]);
+                acc[0] = fmaf(__ldg(wk + kb + koff[0]), x.x, acc[0]);
+                acc[1] = fmaf(__ldg(wk + kb + koff[1]), x.y, acc[1]);
+                acc[2] = fmaf(__ldg(wk + kb + koff[2]), x.z, acc[2]);
+                acc[3] = fmaf(__ldg(wk + kb + koff[3]), x.w, acc[3]);
             } else {
 #pragma unroll
                 for (int v = 0; v < 4; ++v)
-                    if (kb + koff[v] < nk) acc[v] = fmaf(s_w[kb + koff[v]], row[static_cast<size_t>(kb) * NU + v], acc[v]);
+                    if (kb + koff[v] < nk) acc[v] = fmaf(__ldg(wk + kb + koff[v]), row[static_cast<size_t>(kb) * NU + v], acc[v]);
             }
-        } else {
-            if (kb + koff[0] < nk) acc[0] = fmaf(s_w[kb + koff[0]], __ldcs(row + static_cast<size_t>(kb) * NU), acc[0]);
         }
+    } else {
+        for (; kb < nk; kb += STEP)
+            if (kb + koff[0] < nk) acc[0] = fmaf(__ldg(wk + kb + koff[0]), __ldcs(row + static_cast<size_t>(kb) * NU), acc[0]);
     }
     // ---- reduce the NT*VEC per-thread sums to nu outputs, fixed order
-    __syncthreads();
-    float *s_red = s_dyn;      // reuse (weights no longer needed)
+    float *s_red = s_dyn;
 #pragma unroll
     for (int v = 0; v < VEC; ++v) s_red[tid * VEC + v] = acc[v];
-    eta = warp_sum(eta);
-    eta2 = warp_sum(eta2);
-    if ((tid & 31) == 0) { s_eta[tid >> 5] = eta; s_eta2[tid >> 5] = eta2; }
     __syncthreads();
     const int rowlen = P.T * NU + 2;
     float *my = part + static_cast<size_t>(blockIdx.x) * rowlen;
@@ -484,14 +526,8 @@ weight_injected_kernel(const __grid_constant__ StepParams P, const __grid_consta
         for (int j = tid; j < NT * VEC; j += NU) v += s_red[j];
         my[t * NU + tid] = v;
     }
-    if (t == 0 && tid == 0) {
-        float e = 0.f, e2 = 0.f;
-        for (int w = 0; w < NT / 32; ++w) { e += s_eta[w]; e2 += s_eta2[w]; }
-        my[rowlen - 2] = e;
-        my[rowlen - 1] = e2;
-    }
     reduce_partials_and_finalize<MODEL>(P, D, part, gridDim.x, counter, wsum, fuse != 0, u_nom, u_new, out,
-                                        rho_enc, s_dyn);
+                                        rho_enc, s_dyn, eta_part, n_eta);
 }
 
 // Materialise the Philox noise of one step (equivalence checks, HBM-bound experiments).
