@@ -270,6 +270,8 @@ def run_native(args):
     st = synthetic_state(args.model)
     solver.set_state(st)
     solver.u_prev = torch.from_numpy(nominal_controls(args.model, T))
+    from quadrotor_manipulator_mppi_b200.sharded import ShardedStepper
+    stepper = ShardedStepper(solver)
     noise = None
     if args.noise == "injected":
         noise = solver.generate_noise(0)        # resident in HBM before the timed region
@@ -282,11 +284,7 @@ def run_native(args):
         if world == 1:
             solver.step_async(noise)
             return 2 if noise is None else 3        # rollout + weighting(+finalize) [+ weights kernel]
-        solver.rollout(noise)
-        dist.all_reduce(solver.rho_enc, op=dist.ReduceOp.MIN)
-        solver.weight(noise)
-        dist.all_reduce(solver.wsum, op=dist.ReduceOp.SUM)
-        solver.finalize()
+        stepper.step_async(noise)
         return 3 if noise is None else 4
 
     def barrier():
@@ -418,11 +416,7 @@ def run_native(args):
         t0 = time.perf_counter()
         for i in range(n_e2e):
             solver.set_state(st)
-            solver.rollout(noise)
-            dist.all_reduce(solver.rho_enc, op=dist.ReduceOp.MIN)
-            solver.weight(noise)
-            dist.all_reduce(solver.wsum, op=dist.ReduceOp.SUM)
-            out = solver.finalize()
+            out = stepper.step_async(noise)
             host.copy_(out, non_blocking=True)
             stream.synchronize()
         e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)

@@ -1,0 +1,79 @@
+"""K-sharded MPPI across the GPUs of one box: one process per GPU (torchrun), NCCL over NVLink.
+
+Samples are independent until the soft-min, so the K dimension is split into contiguous shards
+(rank r owns global samples [k_offset, k_offset + k_local)); Philox counters use the GLOBAL sample
+index, so the result does not depend on the number of ranks.  Every rank holds the same state and
+nominal controls (inputs are ~1 kB and replicated by the caller: no broadcast on the step path).
+Per control step the shards exchange exactly two small messages:
+
+    rollout  ->  allreduce-MIN  (1 x int32: order-preserving encoding of the cost baseline rho)
+    weight   ->  allreduce-SUM  (T*nu + 2 floats: weighted-noise sums, eta, sum w^2)
+    finalize (replicated, deterministic: every rank ends with the same u_new)
+
+Both collectives are latency-bound (<= 2.8 kB); bench.py reports their time separately.
+The reference has no multi-GPU path (it pins CUDA_VISIBLE_DEVICES=0, mppi_solver/mppi.py:30-31).
+"""
+from __future__ import annotations
+
+import struct
+
+import torch
+import torch.distributed as dist
+
+RHO_INIT = 0x7FFFFFFF
+
+
+def shard_range(n_samples: int, world: int, rank: int):
+    """Contiguous split of K over `world` ranks; the first K % world ranks hold one extra sample."""
+    if not (0 <= rank < world) or n_samples < world:
+        raise ValueError(f"cannot shard K={n_samples} over world={world} (rank {rank})")
+    base, extra = divmod(n_samples, world)
+    k_local = base + (1 if rank < extra else 0)
+    k_offset = rank * base + min(rank, extra)
+    return k_offset, k_local
+
+
+def encode_ordered(value: float) -> int:
+    """float32 -> int32 whose signed order equals the float order (the device's atomicMin key)."""
+    i = struct.unpack("<i", struct.pack("<f", float(value)))[0]
+    return i if i >= 0 else i ^ 0x7FFFFFFF
+
+
+def decode_ordered(key: int) -> float:
+    i = int(key)
+    i = i if i >= 0 else i ^ 0x7FFFFFFF
+    return struct.unpack("<f", struct.pack("<i", i))[0]
+
+
+class ShardedStepper:
+    """Drives one shard.  `solver` is a NativeSolver (or anything with rollout / weight / finalize and
+    the `rho_enc` int32[1] / `wsum` float32[T*nu+2] exchange tensors)."""
+
+    def __init__(self, solver, group=None):
+        self.solver = solver
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+
+    def step_async(self, noise=None):
+        s = self.solver
+        s.rollout(noise)
+        if self.world > 1:
+            dist.all_reduce(s.rho_enc, op=dist.ReduceOp.MIN, group=self.group)
+        s.weight(noise)
+        if self.world > 1:
+            dist.all_reduce(s.wsum, op=dist.ReduceOp.SUM, group=self.group)
+        return s.finalize()
+
+    @property
+    def u_prev(self):
+        return self.solver.u_prev
+
+
+def make_sharded_solver(model: int, n_samples_total: int, n_horizon: int, *, device=None, group=None, **kw):
+    """NativeSolver for this rank's shard of a K = n_samples_total problem."""
+    from .core import NativeSolver
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    k_offset, k_local = shard_range(n_samples_total, world, rank)
+    solver = NativeSolver(model, n_samples=k_local, n_horizon=n_horizon, device=device, k_offset=k_offset, **kw)
+    return ShardedStepper(solver, group)
