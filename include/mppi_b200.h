@@ -159,6 +159,13 @@ float *mppi_wsum_ptr(mppi_handle_t h);          /* device, mppi_wsum_count() flo
 int32_t mppi_wsum_count(mppi_handle_t h);
 float *mppi_cost_ptr(mppi_handle_t h);          /* device, S[K] of the last rollout      */
 
+/* compute_control_input as ONE blocking call for a caller that keeps u_prev on the device (the Python
+ * drop-in classes): stages state_host (may be NULL), runs mppi_step on `stream`, copies out[] to host
+ * memory and synchronises the stream.  h2d = the state block (kernel parameter), d2h = out[].      */
+mppi_status_t mppi_step_sync(mppi_handle_t h, const float *state_host, int32_t n_state,
+                             const float *d_u_nom, const float *d_noise, uint64_t step_counter,
+                             float *d_u_new, float *out_host, void *stream);
+
 /* Host-buffer form (what a non-torch caller uses; also the end-to-end timing path):
  * copies state (if given) and u_inout to the device, steps, copies u_new / out / costs back
  * and synchronises.  noise_host may be NULL (Philox).                                   */

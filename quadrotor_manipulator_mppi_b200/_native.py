@@ -24,7 +24,7 @@ EXPORTS = [
     "mppi_abi_version", "mppi_last_error", "mppi_default_config", "mppi_create", "mppi_destroy",
     "mppi_update_config", "mppi_set_chain", "mppi_set_target", "mppi_set_state", "mppi_step", "mppi_rollout", "mppi_weight",
     "mppi_finalize", "mppi_rho_ptr", "mppi_wsum_ptr", "mppi_wsum_count", "mppi_cost_ptr",
-    "mppi_step_host", "mppi_generate_noise", "mppi_measure_fp32_peak",
+    "mppi_step_sync", "mppi_step_host", "mppi_generate_noise", "mppi_measure_fp32_peak",
     "mppi_algorithmic_flops_per_rollout_step",
 ]
 
@@ -82,6 +82,7 @@ def load():
     lib.mppi_wsum_count.argtypes = [vp]
     lib.mppi_cost_ptr.restype = vp
     lib.mppi_cost_ptr.argtypes = [vp]
+    lib.mppi_step_sync.argtypes = [vp, _fp, i32, vp, vp, u64, vp, vp, vp]
     lib.mppi_step_host.argtypes = [vp, _fp, i32, _fp, _fp, u64, _fp, _fp]
     lib.mppi_generate_noise.argtypes = [vp, u64, vp, vp]
     lib.mppi_measure_fp32_peak.argtypes = [i32, _fp]

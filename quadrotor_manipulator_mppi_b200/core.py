@@ -76,7 +76,8 @@ class NativeSolver:
         self._cur = 0
         self._outs = [torch.zeros(_native.MPPI_OUT_FLOATS, device=self.device) for _ in range(4)]
         self._out_i = 0
-        self._out_host = torch.zeros(_native.MPPI_OUT_FLOATS, pin_memory=True)
+        self._out_host = torch.zeros(_native.MPPI_OUT_FLOATS)
+        self._out_host_np = self._out_host.numpy()
         self._state_np = np.zeros(_native.MODEL_STATE[model], np.float32)
         self._state_lock = threading.Lock()
         self.costs = torch.as_tensor(_DevView(self._lib.mppi_cost_ptr(self.handle), self.K, "<f4"), device=self.device)
@@ -167,10 +168,12 @@ class NativeSolver:
 
     def step(self, noise=None, step_counter=None) -> np.ndarray:
         """One control step; returns the `out` vector on the host (pinned copy + stream sync)."""
-        out = self.step_async(noise, step_counter)
-        self._out_host.copy_(out, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
-        return self._out_host.numpy()
+        sc = self.step_counter if step_counter is None else int(step_counter)
+        nxt = self._cur ^ 1
+        ops.step_sync(self.handle, self._u[self._cur], noise, sc, self._u[nxt], self._out_host)
+        self._cur = nxt
+        self.step_counter = sc + 1
+        return self._out_host_np
 
     # ---- the three phases, for K-sharded replicas (see sharded.py)
     def rollout(self, noise=None, step_counter=None):

@@ -636,6 +636,25 @@ mppi_status_t mppi_step(mppi_handle_t h, const float *d_u_nom, const float *d_no
     return weight_dispatch(h, d_noise, true, d_u_nom, d_u_new, d_out ? d_out : h->d_out, st);
 }
 
+mppi_status_t mppi_step_sync(mppi_handle_t h, const float *state_host, int32_t n_state, const float *d_u_nom,
+                             const float *d_noise, uint64_t step_counter, float *d_u_new, float *out_host, void *stream)
+{
+    if (!h || !out_host) return fail(h, MPPI_ERR_INVALID_ARG, "null out buffer");
+    if (state_host) {
+        mppi_status_t rc = mppi_set_state(h, state_host, n_state);
+        if (rc != MPPI_OK) return rc;
+    }
+    mppi_status_t rc = mppi_step(h, d_u_nom, d_noise, step_counter, nullptr, d_u_new, h->d_out, stream);
+    if (rc != MPPI_OK) return rc;
+    DeviceGuard guard(h->cfg.device);
+    cudaStream_t st = (cudaStream_t)stream;
+    float *pin = h->h_pinned + (size_t)h->P.T * h->nu;
+    MPPI_CUDA(h, cudaMemcpyAsync(pin, h->d_out, MPPI_OUT_FLOATS * sizeof(float), cudaMemcpyDeviceToHost, st));
+    MPPI_CUDA(h, cudaStreamSynchronize(st));
+    std::memcpy(out_host, pin, MPPI_OUT_FLOATS * sizeof(float));
+    return MPPI_OK;
+}
+
 mppi_status_t mppi_step_host(mppi_handle_t h, const float *state_host, int32_t n_state, float *u_inout_host,
                              const float *noise_host, uint64_t step_counter, float *cost_out_host, float *out_host)
 {

@@ -46,7 +46,7 @@ class MPPI:
         self.target_pose = Pose()
         self.target_pose.pose = torch.tensor([0.1029, 0.4055, 1.6498])        # mppi.py:71
         self.target_pose.orientation = torch.tensor([-0.5, -0.5, 0.5, -0.5])  # mppi.py:72
-        self._target_sent = None
+        self._target_key = None
         self.ee_pose = Pose()
         self._q64 = np.zeros(7)
         self._qdot64 = np.zeros(7)
@@ -118,10 +118,11 @@ class MPPI:
 
     # ------------------------------------------------------------------ the control step
     def _sync_target(self):
-        tgt = self.target_pose.as_floats()
-        if tgt != self._target_sent:
+        key = self.target_pose.version_key()
+        if key != self._target_key:
+            tgt = self.target_pose.as_floats()
             self._solver.set_target(pos=tgt[:3], quat=tgt[3:])
-            self._target_sent = tgt
+            self._target_key = key
 
     def compute_control_input(self, noise=None, noise_layout: str = "tkn", return_costs: bool = False):
         """mppi.py:122-169.  `noise`: optional injected noise, [T][K][nu] ("tkn") or the

@@ -55,10 +55,12 @@ class MPPI:
         self._solver.set_state(self._state)
 
     def _sync_target(self):
-        tgt = self.target_pose.as_floats() + tuple(float(v) for v in torch.as_tensor(self.drone_target).reshape(-1))
-        if tgt != self._target_sent:
+        dt_ = self.drone_target
+        key = self.target_pose.version_key() + ((id(dt_), dt_._version) if isinstance(dt_, torch.Tensor) else (tuple(dt_),))
+        if key != self._target_sent:
+            tgt = self.target_pose.as_floats() + tuple(float(v) for v in torch.as_tensor(dt_).reshape(-1))
             self._solver.set_target(pos=tgt[:3], quat=tgt[3:7], drone_target=tgt[7:])
-            self._target_sent = tgt
+            self._target_sent = key
 
     def compute_control_input(self, noise=None, noise_layout: str = "tkn"):
         """Returns (qdes[7], vdes[7], next_base_state[12]) as numpy arrays."""

@@ -14,6 +14,8 @@ from . import _native
 _lib_def = torch.library.Library("mppi_b200", "DEF")
 _lib_def.define("step(int handle, Tensor u_nom, Tensor? noise, int step_counter, Tensor(a!) u_new, "
                 "Tensor(b!) out, Tensor(c!)? cost) -> ()")
+_lib_def.define("step_sync(int handle, Tensor u_nom, Tensor? noise, int step_counter, Tensor(a!) u_new, "
+                "Tensor(b!) out_host) -> ()")
 _lib_def.define("rollout(int handle, Tensor u_nom, Tensor? noise, int step_counter, Tensor(a!)? cost) -> ()")
 _lib_def.define("weight(int handle, Tensor? noise, int step_counter) -> ()")
 _lib_def.define("finalize(int handle, Tensor u_nom, int step_counter, Tensor(a!) u_new, Tensor(b!) out) -> ()")
@@ -42,6 +44,16 @@ def _step_cuda(handle, u_nom, noise, step_counter, u_new, out, cost):
                                 _stream(u_nom)), handle)
 
 
+def _step_sync_cuda(handle, u_nom, noise, step_counter, u_new, out_host):
+    """Blocking step: out[] lands in `out_host` (a CPU float32 tensor of MPPI_OUT_FLOATS) when this returns."""
+    lib = _native.load()
+    if out_host.device.type != "cpu" or out_host.dtype != torch.float32 or out_host.numel() != _native.MPPI_OUT_FLOATS:
+        raise ValueError("out_host must be a CPU float32 tensor of MPPI_OUT_FLOATS elements")
+    _native.check(lib.mppi_step_sync(handle, None, 0, _chk(u_nom, "u_nom"), None if noise is None else _chk(noise, "noise"),
+                                     step_counter, _chk(u_new, "u_new", u_nom.numel()), out_host.data_ptr(),
+                                     _stream(u_nom)), handle)
+
+
 def _rollout_cuda(handle, u_nom, noise, step_counter, cost):
     lib = _native.load()
     _native.check(lib.mppi_rollout(handle, _chk(u_nom, "u_nom"), None if noise is None else _chk(noise, "noise"),
@@ -60,6 +72,7 @@ def _generate_noise_cuda(handle, step_counter, noise):
 
 
 _lib_def.impl("step", _step_cuda, "CUDA")
+_lib_def.impl("step_sync", _step_sync_cuda, "CUDA")
 _lib_def.impl("rollout", _rollout_cuda, "CUDA")
 _lib_def.impl("finalize", _finalize_cuda, "CUDA")
 _lib_def.impl("generate_noise", _generate_noise_cuda, "CUDA")
@@ -74,6 +87,7 @@ def weight(handle: int, noise, step_counter: int, device) -> None:
 
 
 step = torch.ops.mppi_b200.step
+step_sync = torch.ops.mppi_b200.step_sync
 rollout = torch.ops.mppi_b200.rollout
 finalize = torch.ops.mppi_b200.finalize
 generate_noise = torch.ops.mppi_b200.generate_noise

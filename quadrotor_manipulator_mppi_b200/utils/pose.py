@@ -95,6 +95,10 @@ class Pose:
         p.orientation = self._orientation.clone()
         return p
 
+    def version_key(self):
+        """Cheap change detector for the solver (tensor identity + in-place version counters)."""
+        return (id(self._pose), self._pose._version, id(self._orientation), self._orientation._version)
+
     def as_floats(self):
         """(x, y, z, qx, qy, qz, qw) as Python floats -- what the solver uploads."""
         return tuple(float(v) for v in self._pose.detach().cpu().reshape(-1)) + \
