@@ -53,6 +53,8 @@ def parse_args():
     ap.add_argument("--horizon", type=int, default=None)
     ap.add_argument("--noise", default="philox", choices=["philox", "injected"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="multi-GPU shard exchange: fused NVLink peer exchange, or NCCL allreduce-MIN + allreduce-SUM")
     ap.add_argument("--no-flush", action="store_true", help="skip the L2 flush between steps (latency experiments)")
     return ap.parse_args()
 
@@ -271,7 +273,7 @@ def run_native(args):
     solver.set_state(st)
     solver.u_prev = torch.from_numpy(nominal_controls(args.model, T))
     from quadrotor_manipulator_mppi_b200.sharded import ShardedStepper
-    stepper = ShardedStepper(solver)
+    stepper = ShardedStepper(solver, exchange=args.exchange)
     noise = None
     if args.noise == "injected":
         noise = solver.generate_noise(0)        # resident in HBM before the timed region
@@ -285,6 +287,8 @@ def run_native(args):
             solver.step_async(noise)
             return 2 if noise is None else 3        # rollout + weighting(+finalize) [+ weights kernel]
         stepper.step_async(noise)
+        if stepper.exchange == "p2p":
+            return 2 if noise is None else 3
         return 3 if noise is None else 4
 
     def barrier():
@@ -435,6 +439,7 @@ def run_native(args):
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"{spec['desc']}, K={K}, T={T}", "noise": args.noise,
                            "K_per_gpu": K_loc, "parallelism": f"k-shard x{world}" if world > 1 else "single GPU",
+                           "exchange": (stepper.exchange if world > 1 else None),
                            "l2": "no flush" if flush is None else "L2 flushed between steps (256 MiB memset) outside the per-step CUDA events",
                            "timing": "CUDA events around every step on the launch stream, summed, max over ranks"},
                 "latency_ms": {"p50": float(np.percentile(step_ms, 50)), "p99": float(np.percentile(step_ms, 99)),

@@ -159,6 +159,21 @@ float *mppi_wsum_ptr(mppi_handle_t h);          /* device, mppi_wsum_count() flo
 int32_t mppi_wsum_count(mppi_handle_t h);
 float *mppi_cost_ptr(mppi_handle_t h);          /* device, S[K] of the last rollout      */
 
+/* K-sharded replicas without NCCL on the step path: every rank exports a small exchange buffer
+ * through CUDA IPC (mppi_p2p_export -> 64-byte handle), the caller all-gathers the handles (any
+ * transport) and binds them (mppi_p2p_bind).  mppi_step_p2p is then mppi_step with the shard
+ * exchange fused into the weighting kernel: each rank weights with its local cost minimum,
+ * publishes (sums, eta, sum w^2, rho) into every peer's inbox over NVLink, and combines the rows
+ * with exp(-(rho_r - rho)/lambda) in rank order -- algebraically the allreduce-MIN + allreduce-SUM.
+ * Every rank must call it once per control step with the same step_counter (new; no reference
+ * counterpart: the reference is single-GPU, mppi_solver/mppi.py:30-31).                         */
+#define MPPI_IPC_HANDLE_BYTES 64
+mppi_status_t mppi_p2p_export(mppi_handle_t h, int32_t world, void *ipc_handle_out);
+mppi_status_t mppi_p2p_bind(mppi_handle_t h, int32_t world, int32_t rank, const void *all_handles);
+mppi_status_t mppi_step_p2p(mppi_handle_t h, const float *d_u_nom, const float *d_noise,
+                            uint64_t step_counter, float *d_cost_out, float *d_u_new, float *d_out,
+                            void *stream);
+
 /* compute_control_input as ONE blocking call for a caller that keeps u_prev on the device (the Python
  * drop-in classes): stages state_host (may be NULL), runs mppi_step on `stream`, copies out[] to host
  * memory and synchronises the stream.  h2d = the state block (kernel parameter), d2h = out[].      */

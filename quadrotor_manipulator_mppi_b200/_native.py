@@ -13,6 +13,7 @@ from . import build as _build
 MPPI_MAX_NU = 12
 MPPI_STATE_FLOATS = 32
 MPPI_OUT_FLOATS = 64
+MPPI_IPC_HANDLE_BYTES = 64
 MPPI_OUT_BASE, MPPI_OUT_U0_NEW, MPPI_OUT_U0_OLD = 16, 28, 40
 MPPI_OUT_REACH, MPPI_OUT_RHO, MPPI_OUT_ETA, MPPI_OUT_ESS, MPPI_OUT_STEP = 52, 53, 54, 55, 56
 MODEL_DRONE3, MODEL_ARM7, MODEL_QUAD4, MODEL_WB11 = 0, 1, 2, 3
@@ -24,7 +25,7 @@ EXPORTS = [
     "mppi_abi_version", "mppi_last_error", "mppi_default_config", "mppi_create", "mppi_destroy",
     "mppi_update_config", "mppi_set_chain", "mppi_set_target", "mppi_set_state", "mppi_step", "mppi_rollout", "mppi_weight",
     "mppi_finalize", "mppi_rho_ptr", "mppi_wsum_ptr", "mppi_wsum_count", "mppi_cost_ptr",
-    "mppi_step_sync", "mppi_step_host", "mppi_generate_noise", "mppi_measure_fp32_peak",
+    "mppi_p2p_export", "mppi_p2p_bind", "mppi_step_p2p", "mppi_step_sync", "mppi_step_host", "mppi_generate_noise", "mppi_measure_fp32_peak",
     "mppi_algorithmic_flops_per_rollout_step",
 ]
 
@@ -82,6 +83,9 @@ def load():
     lib.mppi_wsum_count.argtypes = [vp]
     lib.mppi_cost_ptr.restype = vp
     lib.mppi_cost_ptr.argtypes = [vp]
+    lib.mppi_p2p_export.argtypes = [vp, i32, vp]
+    lib.mppi_p2p_bind.argtypes = [vp, i32, i32, vp]
+    lib.mppi_step_p2p.argtypes = [vp, vp, vp, u64, vp, vp, vp, vp]
     lib.mppi_step_sync.argtypes = [vp, _fp, i32, vp, vp, u64, vp, vp, vp]
     lib.mppi_step_host.argtypes = [vp, _fp, i32, _fp, _fp, u64, _fp, _fp]
     lib.mppi_generate_noise.argtypes = [vp, u64, vp, vp]

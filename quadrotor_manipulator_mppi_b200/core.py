@@ -175,6 +175,17 @@ class NativeSolver:
         self.step_counter = sc + 1
         return self._out_host_np
 
+    def step_p2p_async(self, noise=None, step_counter=None) -> torch.Tensor:
+        """Sharded step with the NVLink peer exchange fused in (after sharded.enable_p2p)."""
+        sc = self.step_counter if step_counter is None else int(step_counter)
+        nxt = self._cur ^ 1
+        out = self._outs[self._out_i]
+        self._out_i = (self._out_i + 1) & 3
+        ops.step_p2p(self.handle, self._u[self._cur], noise, sc, self._u[nxt], out)
+        self._cur = nxt
+        self.step_counter = sc + 1
+        return out
+
     # ---- the three phases, for K-sharded replicas (see sharded.py)
     def rollout(self, noise=None, step_counter=None):
         sc = self.step_counter if step_counter is None else int(step_counter)

@@ -157,6 +157,12 @@ struct mppi_ctx {
     float *h_pinned = nullptr;      // pinned staging for the host-buffer API
     size_t h_pinned_floats = 0;
     int max_parts = 0;
+    // NVLink peer exchange (mppi_p2p_export / mppi_p2p_bind)
+    float *p2p_buf = nullptr;       // this rank's exchange buffer (cudaMalloc, exported through CUDA IPC)
+    size_t p2p_bytes = 0;
+    P2PParams X{};                  // world == 1 until bound
+    P2PParams X_off{};              // world == 1: exchange disabled
+    void *p2p_peer[kMaxRanks] = {};
     bool baked_fk = false;          // runtime chain == compile-time FkKinova tables
     size_t rollout_smem[4] = {0, 0, 0, 0};   // tuned dynamic smem per kernel variant (0 = not yet tuned)
     cudaStream_t own_stream = nullptr;
@@ -289,7 +295,7 @@ mppi_status_t launch_rollout(mppi_ctx *h, const float *d_u_nom, const float *d_n
 
 template <int MODEL>
 mppi_status_t launch_weight(mppi_ctx *h, const float *d_noise, bool fuse, const float *d_u_nom, float *d_u_new,
-                            float *d_out, cudaStream_t st)
+                            float *d_out, cudaStream_t st, const P2PParams &X)
 {
     constexpr int NU = ModelNu<MODEL>::value;
     constexpr int NCH = (NU + 3) / 4;
@@ -310,7 +316,7 @@ mppi_status_t launch_weight(mppi_ctx *h, const float *d_noise, bool fuse, const 
         size_t smem_floats = (size_t)kWeightTile + (size_t)R * TC * 4;
         if (smem_floats < fin_floats) smem_floats = fin_floats;
         weight_philox_kernel<MODEL><<<blocks, threads, smem_floats * sizeof(float), st>>>(
-            h->P, h->dyn, h->d_cost, h->d_rho, chunk, h->d_part, h->d_counter, h->d_wsum, fuse ? 1 : 0, d_u_nom, d_u_new, d_out);
+            h->P, h->dyn, h->d_cost, h->d_rho, chunk, h->d_part, h->d_counter, h->d_wsum, fuse ? 1 : 0, d_u_nom, d_u_new, d_out, X);
     } else {
         const bool vec4 = ((size_t)K * NU) % 4 == 0 && (reinterpret_cast<uintptr_t>(d_noise) & 15u) == 0;
         // weights once, then one resident wave of (G x T) streaming blocks
@@ -339,11 +345,11 @@ mppi_status_t launch_weight(mppi_ctx *h, const float *d_noise, bool fuse, const 
         if (vec4)
             weighted_noise_kernel<MODEL, 4><<<grid, threads, smem_floats * sizeof(float), st>>>(
                 h->P, h->dyn, h->d_w, d_noise, h->d_rho, chunk, h->d_part, h->d_eta_part, wblocks, h->d_counter, h->d_wsum,
-                fuse ? 1 : 0, d_u_nom, d_u_new, d_out);
+                fuse ? 1 : 0, d_u_nom, d_u_new, d_out, X);
         else
             weighted_noise_kernel<MODEL, 1><<<grid, threads, smem_floats * sizeof(float), st>>>(
                 h->P, h->dyn, h->d_w, d_noise, h->d_rho, chunk, h->d_part, h->d_eta_part, wblocks, h->d_counter, h->d_wsum,
-                fuse ? 1 : 0, d_u_nom, d_u_new, d_out);
+                fuse ? 1 : 0, d_u_nom, d_u_new, d_out, X);
     }
     MPPI_CUDA(h, cudaGetLastError());
     return MPPI_OK;
@@ -380,7 +386,7 @@ void snapshot(mppi_ctx *h, uint64_t step_counter)
 }
 
 mppi_status_t rollout_dispatch(mppi_ctx *h, const float *u, const float *n, float *c, cudaStream_t st) { MPPI_DISPATCH(h, launch_rollout, h, u, n, c, st) }
-mppi_status_t weight_dispatch(mppi_ctx *h, const float *n, bool fuse, const float *u, float *un, float *o, cudaStream_t st) { MPPI_DISPATCH(h, launch_weight, h, n, fuse, u, un, o, st) }
+mppi_status_t weight_dispatch(mppi_ctx *h, const float *n, bool fuse, const float *u, float *un, float *o, cudaStream_t st, const P2PParams &X) { MPPI_DISPATCH(h, launch_weight, h, n, fuse, u, un, o, st, X) }
 mppi_status_t finalize_dispatch(mppi_ctx *h, const float *u, float *un, float *o, cudaStream_t st) { MPPI_DISPATCH(h, launch_finalize, h, u, un, o, st) }
 
 struct DeviceGuard {
@@ -477,6 +483,7 @@ mppi_status_t mppi_create(const mppi_config_t *cfg, mppi_handle_t *out)
     if (!h) return fail(nullptr, MPPI_ERR_CUDA, "out of host memory");
     h->cfg = *cfg;
     h->nu = nu;
+    h->X.world = h->X_off.world = 1;
     h->num_sms = prop.multiProcessorCount;
     StepParams &P = h->P;
     P.K = cfg->n_samples; P.T = cfg->n_horizon; P.nu = nu; P.nch = (nu + 3) / 4;
@@ -537,6 +544,8 @@ mppi_status_t mppi_destroy(mppi_handle_t h)
         cudaDeviceSynchronize();
         cudaFree(h->d_cost); cudaFree(h->d_rho); cudaFree(h->d_w); cudaFree(h->d_eta_part); cudaFree(h->d_part); cudaFree(h->d_wsum);
         cudaFree(h->d_u); cudaFree(h->d_out); cudaFree(h->d_noise);
+        for (int r = 0; r < kMaxRanks; ++r) if (h->p2p_peer[r]) cudaIpcCloseMemHandle(h->p2p_peer[r]);
+        cudaFree(h->p2p_buf);
         if (h->h_pinned) cudaFreeHost(h->h_pinned);
         if (h->own_stream) cudaStreamDestroy(h->own_stream);
     }
@@ -611,7 +620,7 @@ mppi_status_t mppi_weight(mppi_handle_t h, const float *d_noise, uint64_t step_c
     if (!h) return MPPI_ERR_INVALID_ARG;
     DeviceGuard guard(h->cfg.device);
     h->dyn.step_lo = (uint32_t)step_counter; h->dyn.step_hi = (uint32_t)(step_counter >> 32);
-    return weight_dispatch(h, d_noise, false, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+    return weight_dispatch(h, d_noise, false, nullptr, nullptr, nullptr, (cudaStream_t)stream, h->X_off);
 }
 
 mppi_status_t mppi_finalize(mppi_handle_t h, const float *d_u_nom, uint64_t step_counter, float *d_u_new, float *d_out, void *stream)
@@ -633,7 +642,67 @@ mppi_status_t mppi_step(mppi_handle_t h, const float *d_u_nom, const float *d_no
     if (rc != MPPI_OK) return rc;
     if (d_cost_out && d_cost_out != h->d_cost)
         MPPI_CUDA(h, cudaMemcpyAsync(d_cost_out, h->d_cost, (size_t)h->P.K * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    return weight_dispatch(h, d_noise, true, d_u_nom, d_u_new, d_out ? d_out : h->d_out, st);
+    return weight_dispatch(h, d_noise, true, d_u_nom, d_u_new, d_out ? d_out : h->d_out, st, h->X_off);
+}
+
+mppi_status_t mppi_p2p_export(mppi_handle_t h, int32_t world, void *ipc_handle_out)
+{
+    if (!h || !ipc_handle_out || world < 2 || world > kMaxRanks)
+        return fail(h, MPPI_ERR_INVALID_ARG, "p2p world must be in [2, 8]");
+    static_assert(sizeof(cudaIpcMemHandle_t) == MPPI_IPC_HANDLE_BYTES, "IPC handle size");
+    DeviceGuard guard(h->cfg.device);
+    const int rowp = (h->P.T * h->nu + 4 + 3) & ~3;
+    const size_t bytes = ((size_t)kMaxRanks * kFlagStrideInts + (size_t)2 * world * rowp) * sizeof(float);
+    if (h->p2p_buf) { cudaFree(h->p2p_buf); h->p2p_buf = nullptr; }
+    MPPI_CUDA(h, cudaMalloc(&h->p2p_buf, bytes));
+    MPPI_CUDA(h, cudaMemset(h->p2p_buf, 0, bytes));
+    MPPI_CUDA(h, cudaDeviceSynchronize());
+    h->p2p_bytes = bytes;
+    cudaIpcMemHandle_t ih;
+    MPPI_CUDA(h, cudaIpcGetMemHandle(&ih, h->p2p_buf));
+    std::memcpy(ipc_handle_out, &ih, sizeof(ih));
+    h->X = P2PParams{};
+    h->X.world = 1;
+    h->X.rowp = rowp;
+    return MPPI_OK;
+}
+
+mppi_status_t mppi_p2p_bind(mppi_handle_t h, int32_t world, int32_t rank, const void *all_handles)
+{
+    if (!h || !all_handles || !h->p2p_buf || world < 2 || world > kMaxRanks || rank < 0 || rank >= world)
+        return fail(h, MPPI_ERR_INVALID_ARG, "mppi_p2p_bind: call mppi_p2p_export first; world in [2, 8]");
+    DeviceGuard guard(h->cfg.device);
+    P2PParams X = h->X;
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) { X.base[r] = h->p2p_buf; continue; }
+        cudaIpcMemHandle_t ih;
+        std::memcpy(&ih, (const char *)all_handles + (size_t)r * MPPI_IPC_HANDLE_BYTES, sizeof(ih));
+        void *p = nullptr;
+        MPPI_CUDA(h, cudaIpcOpenMemHandle(&p, ih, cudaIpcMemLazyEnablePeerAccess));
+        h->p2p_peer[r] = p;
+        X.base[r] = (float *)p;
+    }
+    X.world = world;
+    X.rank = rank;
+    X.epoch = 0;
+    h->X = X;
+    return MPPI_OK;
+}
+
+mppi_status_t mppi_step_p2p(mppi_handle_t h, const float *d_u_nom, const float *d_noise, uint64_t step_counter,
+                            float *d_cost_out, float *d_u_new, float *d_out, void *stream)
+{
+    if (!h || !d_u_nom || !d_u_new) return fail(h, MPPI_ERR_INVALID_ARG, "null u buffers");
+    if (h->X.world < 2) return fail(h, MPPI_ERR_INVALID_ARG, "mppi_step_p2p: peers are not bound (mppi_p2p_bind)");
+    DeviceGuard guard(h->cfg.device);
+    cudaStream_t st = (cudaStream_t)stream;
+    snapshot(h, step_counter);
+    mppi_status_t rc = rollout_dispatch(h, d_u_nom, d_noise, h->d_cost, st);
+    if (rc != MPPI_OK) return rc;
+    if (d_cost_out && d_cost_out != h->d_cost)
+        MPPI_CUDA(h, cudaMemcpyAsync(d_cost_out, h->d_cost, (size_t)h->P.K * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    h->X.epoch += 1;           // every rank steps in lock-step, so the epochs agree
+    return weight_dispatch(h, d_noise, true, d_u_nom, d_u_new, d_out ? d_out : h->d_out, st, h->X);
 }
 
 mppi_status_t mppi_step_sync(mppi_handle_t h, const float *state_host, int32_t n_state, const float *d_u_nom,

@@ -50,6 +50,25 @@ struct DynBlock {
     unsigned step_lo, step_hi;   // Philox counter words 2,3
 };
 
+// Peer-to-peer exchange over NVLink (K-sharded replicas, one process per GPU; buffers are
+// cudaMalloc'ed and mapped into every rank with CUDA IPC).  Rank r's buffer holds
+//   flags [kMaxRanks] (128-byte stride): flags[s] = last epoch published by source rank s
+//   inbox [2 parity][world][rowp] floats: slot (parity, s) = row published by source rank s
+// world == 1 disables the exchange.
+constexpr int kMaxRanks = 8;
+constexpr int kFlagStrideInts = 32;
+struct P2PParams {
+    int world, rank;
+    unsigned epoch;              // starts at 1, +1 per control step, same on every rank
+    int rowp;                    // floats per inbox row (T*nu + 4, padded to a multiple of 4)
+    float *base[kMaxRanks];      // base[r] = rank r's exchange buffer as mapped in THIS process
+};
+__host__ __device__ __forceinline__ int *p2p_flags(float *base) { return reinterpret_cast<int *>(base); }
+__host__ __device__ __forceinline__ float *p2p_inbox(float *base, int world, int rowp, int parity, int src)
+{
+    return base + kMaxRanks * kFlagStrideInts + (static_cast<size_t>(parity) * world + src) * rowp;
+}
+
 template <int MODEL> struct ModelNu;
 template <> struct ModelNu<MPPI_MODEL_DRONE3> { static constexpr int value = 3; };
 template <> struct ModelNu<MPPI_MODEL_ARM7>   { static constexpr int value = 7; };

@@ -280,13 +280,96 @@ finalize_kernel(const __grid_constant__ StepParams P, const __grid_constant__ Dy
     finalize_block<MODEL>(P, D, wsum, u_nom, u_new, out, rho_enc, s_fin);
 }
 
+// One-shot exchange of the shard results over NVLink peer memory, run by ONE block per rank inside
+// the weighting kernel (no NCCL call, no extra launch).  Every rank weights with its LOCAL cost
+// minimum rho_r; rows are combined with c_r = exp(-(rho_r - rho)/lambda), which is algebraically the
+// allreduce-MIN + allreduce-SUM of the two-collective contract (wsum = sum_r c_r wsum_r).  All ranks
+// sum in rank order, so replicas stay bit-identical.
+//   publish: plain stores into every peer's inbox slot (parity = epoch & 1), system fence, then a
+//            release store of the epoch into the peer's flag for this source;
+//   wait   : acquire-spin on the local flags (bounded: a dead peer must not hang the GPU);
+//   two parity buffers are enough because a rank cannot finish epoch e+1 before every peer has
+//   published e+1, i.e. after every peer finished reading e.
+__device__ __forceinline__ void st_release_sys(int *p, int v)
+{
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_sys(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ld_relaxed_sys(const float *p)
+{
+    float v;
+    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <int MODEL>
+__device__ bool p2p_exchange(const StepParams &P, const P2PParams &X, float *wsum, int32_t *rho_enc)
+{
+    constexpr int NU = ModelNu<MODEL>::value;
+    __shared__ float s_scale[kMaxRanks];
+    __shared__ int s_ok;
+    const int row = P.T * NU + 2;
+    const int parity = static_cast<int>(X.epoch & 1u);
+    const int tid = threadIdx.x;
+    if (tid == 0) s_ok = 1;
+    // ---- publish (own slot included, so the combine loop is uniform)
+    for (int dst = 0; dst < X.world; ++dst) {
+        float *slot = p2p_inbox(X.base[dst], X.world, X.rowp, parity, X.rank);
+        for (int j = tid; j < row; j += blockDim.x) slot[j] = wsum[j];
+        if (tid == 0) slot[row] = __int_as_float(*rho_enc);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < X.world) st_release_sys(p2p_flags(X.base[tid]) + X.rank * kFlagStrideInts, static_cast<int>(X.epoch));
+    // ---- wait for every source
+    if (tid < X.world) {
+        const int *flag = p2p_flags(X.base[X.rank]) + tid * kFlagStrideInts;
+        const long long t0 = clock64();
+        while (static_cast<int>(ld_acquire_sys(flag) - static_cast<int>(X.epoch)) < 0) {
+            __nanosleep(64);
+            if (clock64() - t0 > 4000000000LL) { s_ok = 0; break; }     // ~2 s: give up instead of hanging
+        }
+    }
+    __syncthreads();
+    // ---- combine in rank order
+    float *mine = X.base[X.rank];
+    if (tid == 0) {
+        float rho = __int_as_float(0x7f800000);
+        for (int r = 0; r < X.world; ++r)
+            rho = fminf(rho, decode_ordered(__float_as_int(ld_relaxed_sys(p2p_inbox(mine, X.world, X.rowp, parity, r) + row))));
+        for (int r = 0; r < X.world; ++r) {
+            const float rr = decode_ordered(__float_as_int(ld_relaxed_sys(p2p_inbox(mine, X.world, X.rowp, parity, r) + row)));
+            s_scale[r] = expf(-P.inv_lambda * (rr - rho));
+        }
+        *rho_enc = encode_ordered(rho);
+    }
+    __syncthreads();
+    for (int j = tid; j < row; j += blockDim.x) {
+        float acc = 0.f;
+        for (int r = 0; r < X.world; ++r) {
+            const float c = s_scale[r];
+            const float v = ld_relaxed_sys(p2p_inbox(mine, X.world, X.rowp, parity, r) + j);
+            acc = fmaf((j == row - 1) ? c * c : c, v, acc);      // last entry is sum w^2
+        }
+        wsum[j] = acc;
+    }
+    __syncthreads();
+    return s_ok != 0;
+}
+
 // Last-block-done: every block publishes its partial row, the last one to arrive sums the rows
-// in index order (deterministic) into wsum and optionally finalizes.
+// in index order (deterministic) into wsum, exchanges with the peer shards when asked to, and
+// optionally finalizes.
 template <int MODEL>
 __device__ void reduce_partials_and_finalize(const StepParams &P, const DynBlock &D, const float *part,
                                              int n_parts, uint32_t *counter, float *wsum, bool fuse,
                                              const float *u_nom, float *u_new, float *out,
-                                             int32_t *rho_enc, float *scratch,
+                                             int32_t *rho_enc, float *scratch, const P2PParams &X,
                                              const float *eta_part = nullptr, int n_eta = 0)
 {
     constexpr int NU = ModelNu<MODEL>::value;
@@ -320,7 +403,12 @@ __device__ void reduce_partials_and_finalize(const StepParams &P, const DynBlock
     }
     if (threadIdx.x == 0) *counter = 0u;
     __syncthreads();
-    if (fuse) finalize_block<MODEL>(P, D, wsum, u_nom, u_new, out, rho_enc, scratch);
+    bool ok = true;
+    if (X.world > 1) ok = p2p_exchange<MODEL>(P, X, wsum, rho_enc);
+    if (fuse) {
+        finalize_block<MODEL>(P, D, wsum, u_nom, u_new, out, rho_enc, scratch);
+        if (!ok && out != nullptr && threadIdx.x == 0) out[MPPI_OUT_STEP] = -1.0f;      // peer exchange timed out
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -334,7 +422,7 @@ __global__ void __launch_bounds__(1024)
 weight_philox_kernel(const __grid_constant__ StepParams P, const __grid_constant__ DynBlock D,
                      const float *__restrict__ S, int32_t *rho_enc, int chunk,
                      float *__restrict__ part, uint32_t *counter, float *wsum, int fuse,
-                     const float *u_nom, float *u_new, float *out)
+                     const float *u_nom, float *u_new, float *out, const __grid_constant__ P2PParams X)
 {
     constexpr int NU = ModelNu<MODEL>::value;
     constexpr int NCH = (NU + 3) / 4;
@@ -412,7 +500,7 @@ weight_philox_kernel(const __grid_constant__ StepParams P, const __grid_constant
         my[row - 1] = e2;
     }
     reduce_partials_and_finalize<MODEL>(P, D, part, gridDim.x, counter, wsum, fuse != 0, u_nom, u_new, out,
-                                        rho_enc, s_dyn);
+                                        rho_enc, s_dyn, X);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -457,7 +545,8 @@ __global__ void __launch_bounds__(32 * ModelNu<MODEL>::value)
 weighted_noise_kernel(const __grid_constant__ StepParams P, const __grid_constant__ DynBlock D,
                       const float *__restrict__ w, const float *__restrict__ noise, int32_t *rho_enc,
                       int chunk, float *__restrict__ part, const float *__restrict__ eta_part, int n_eta,
-                      uint32_t *counter, float *wsum, int fuse, const float *u_nom, float *u_new, float *out)
+                      uint32_t *counter, float *wsum, int fuse, const float *u_nom, float *u_new, float *out,
+                      const __grid_constant__ P2PParams X)
 {
     constexpr int NU = ModelNu<MODEL>::value;
     constexpr int NT = 32 * NU;
@@ -527,7 +616,7 @@ weighted_noise_kernel(const __grid_constant__ StepParams P, const __grid_constan
         my[t * NU + tid] = v;
     }
     reduce_partials_and_finalize<MODEL>(P, D, part, gridDim.x, counter, wsum, fuse != 0, u_nom, u_new, out,
-                                        rho_enc, s_dyn, eta_part, n_eta);
+                                        rho_enc, s_dyn, X, eta_part, n_eta);
 }
 
 // Materialise the Philox noise of one step (equivalence checks, HBM-bound experiments).

@@ -16,6 +16,8 @@ _lib_def.define("step(int handle, Tensor u_nom, Tensor? noise, int step_counter,
                 "Tensor(b!) out, Tensor(c!)? cost) -> ()")
 _lib_def.define("step_sync(int handle, Tensor u_nom, Tensor? noise, int step_counter, Tensor(a!) u_new, "
                 "Tensor(b!) out_host) -> ()")
+_lib_def.define("step_p2p(int handle, Tensor u_nom, Tensor? noise, int step_counter, Tensor(a!) u_new, "
+                "Tensor(b!) out) -> ()")
 _lib_def.define("rollout(int handle, Tensor u_nom, Tensor? noise, int step_counter, Tensor(a!)? cost) -> ()")
 _lib_def.define("weight(int handle, Tensor? noise, int step_counter) -> ()")
 _lib_def.define("finalize(int handle, Tensor u_nom, int step_counter, Tensor(a!) u_new, Tensor(b!) out) -> ()")
@@ -54,6 +56,14 @@ def _step_sync_cuda(handle, u_nom, noise, step_counter, u_new, out_host):
                                      _stream(u_nom)), handle)
 
 
+def _step_p2p_cuda(handle, u_nom, noise, step_counter, u_new, out):
+    """One control step of a K-shard with the peer exchange fused into the weighting kernel (NVLink, no NCCL)."""
+    lib = _native.load()
+    _native.check(lib.mppi_step_p2p(handle, _chk(u_nom, "u_nom"), None if noise is None else _chk(noise, "noise"),
+                                    step_counter, None, _chk(u_new, "u_new", u_nom.numel()),
+                                    _chk(out, "out", _native.MPPI_OUT_FLOATS), _stream(u_nom)), handle)
+
+
 def _rollout_cuda(handle, u_nom, noise, step_counter, cost):
     lib = _native.load()
     _native.check(lib.mppi_rollout(handle, _chk(u_nom, "u_nom"), None if noise is None else _chk(noise, "noise"),
@@ -73,6 +83,7 @@ def _generate_noise_cuda(handle, step_counter, noise):
 
 _lib_def.impl("step", _step_cuda, "CUDA")
 _lib_def.impl("step_sync", _step_sync_cuda, "CUDA")
+_lib_def.impl("step_p2p", _step_p2p_cuda, "CUDA")
 _lib_def.impl("rollout", _rollout_cuda, "CUDA")
 _lib_def.impl("finalize", _finalize_cuda, "CUDA")
 _lib_def.impl("generate_noise", _generate_noise_cuda, "CUDA")
@@ -88,6 +99,7 @@ def weight(handle: int, noise, step_counter: int, device) -> None:
 
 step = torch.ops.mppi_b200.step
 step_sync = torch.ops.mppi_b200.step_sync
+step_p2p = torch.ops.mppi_b200.step_p2p
 rollout = torch.ops.mppi_b200.rollout
 finalize = torch.ops.mppi_b200.finalize
 generate_noise = torch.ops.mppi_b200.generate_noise

@@ -11,6 +11,11 @@ Per control step the shards exchange exactly two small messages:
     finalize (replicated, deterministic: every rank ends with the same u_new)
 
 Both collectives are latency-bound (<= 2.8 kB); bench.py reports their time separately.
+
+`exchange="p2p"` replaces the two NCCL calls by ONE exchange fused into the weighting kernel over
+NVLink peer memory (CUDA IPC buffers, release/acquire flags): each rank weights with its local
+minimum and the rows are combined with exp(-(rho_r - rho)/lambda) -- algebraically the same MIN + SUM,
+with no collective launch on the step path (csrc/mppi_kernels.cuh: p2p_exchange).
 The reference has no multi-GPU path (it pins CUDA_VISIBLE_DEVICES=0, mppi_solver/mppi.py:30-31).
 """
 from __future__ import annotations
@@ -45,17 +50,41 @@ def decode_ordered(key: int) -> float:
     return struct.unpack("<f", struct.pack("<i", i))[0]
 
 
+def enable_p2p(solver, group=None) -> None:
+    """Exchange CUDA IPC handles of the shards' exchange buffers and bind them (collective call)."""
+    import ctypes as C
+
+    from . import _native
+    lib = _native.load()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    mine = (C.c_ubyte * _native.MPPI_IPC_HANDLE_BYTES)()
+    _native.check(lib.mppi_p2p_export(solver.handle, world, mine), solver.handle)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, bytes(mine), group=group)
+    blob = b"".join(gathered)
+    _native.check(lib.mppi_p2p_bind(solver.handle, world, rank, blob), solver.handle)
+    dist.barrier(group=group)        # nobody steps before every rank has mapped its peers
+
+
 class ShardedStepper:
     """Drives one shard.  `solver` is a NativeSolver (or anything with rollout / weight / finalize and
-    the `rho_enc` int32[1] / `wsum` float32[T*nu+2] exchange tensors)."""
+    the `rho_enc` int32[1] / `wsum` float32[T*nu+2] exchange tensors).  exchange = "nccl" (allreduce-MIN
+    + allreduce-SUM through torch.distributed) or "p2p" (fused NVLink exchange, CUDA only)."""
 
-    def __init__(self, solver, group=None):
+    def __init__(self, solver, group=None, exchange: str = "nccl"):
         self.solver = solver
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if exchange not in ("nccl", "p2p"):
+            raise ValueError("exchange must be 'nccl' or 'p2p'")
+        self.exchange = exchange if self.world > 1 else "nccl"
+        if self.exchange == "p2p":
+            enable_p2p(solver, group)
 
     def step_async(self, noise=None):
         s = self.solver
+        if self.exchange == "p2p":
+            return s.step_p2p_async(noise)
         s.rollout(noise)
         if self.world > 1:
             dist.all_reduce(s.rho_enc, op=dist.ReduceOp.MIN, group=self.group)
@@ -69,11 +98,12 @@ class ShardedStepper:
         return self.solver.u_prev
 
 
-def make_sharded_solver(model: int, n_samples_total: int, n_horizon: int, *, device=None, group=None, **kw):
+def make_sharded_solver(model: int, n_samples_total: int, n_horizon: int, *, device=None, group=None,
+                        exchange: str = "nccl", **kw):
     """NativeSolver for this rank's shard of a K = n_samples_total problem."""
     from .core import NativeSolver
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     k_offset, k_local = shard_range(n_samples_total, world, rank)
     solver = NativeSolver(model, n_samples=k_local, n_horizon=n_horizon, device=device, k_offset=k_offset, **kw)
-    return ShardedStepper(solver, group)
+    return ShardedStepper(solver, group, exchange)

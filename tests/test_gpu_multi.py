@@ -13,7 +13,7 @@ from conftest import ROOT
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, K, T, out_dir):
+def _worker(rank, world, port, K, T, out_dir, exchange):
     import sys
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
@@ -23,7 +23,7 @@ def _worker(rank, world, port, K, T, out_dir):
     try:
         from quadrotor_manipulator_mppi_b200 import _native
         from quadrotor_manipulator_mppi_b200.sharded import make_sharded_solver
-        st = make_sharded_solver(_native.MODEL_WB11, K, T, device=torch.device("cuda", rank), seed=21)
+        st = make_sharded_solver(_native.MODEL_WB11, K, T, device=torch.device("cuda", rank), seed=21, exchange=exchange)
         state = np.zeros(26, np.float32)
         state[2] = 2.1
         state[12:19] = [1.57, 1.7, 0, 4.4, 0, 4.71, 0]
@@ -31,13 +31,15 @@ def _worker(rank, world, port, K, T, out_dir):
         for _ in range(3):
             out = st.step_async()
         torch.cuda.synchronize()
+        assert float(out[_native.MPPI_OUT_STEP]) >= 0.0          # -1 = peer exchange timed out
         np.save(os.path.join(out_dir, f"u_{rank}.npy"), st.u_prev.cpu().numpy())
         np.save(os.path.join(out_dir, f"S_{rank}.npy"), st.solver.costs.cpu().numpy())
     finally:
         dist.destroy_process_group()
 
 
-def test_two_gpu_nccl_matches_single_gpu(tmp_path):
+@pytest.mark.parametrize("exchange", ["nccl", "p2p"])
+def test_two_gpu_matches_single_gpu(tmp_path, exchange):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     from quadrotor_manipulator_mppi_b200 import _native
@@ -46,7 +48,7 @@ def test_two_gpu_nccl_matches_single_gpu(tmp_path):
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
-    mp.spawn(_worker, args=(world, port, K, T, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, K, T, str(tmp_path), exchange), nprocs=world, join=True)
     u = [np.load(tmp_path / f"u_{r}.npy") for r in range(world)]
     assert np.array_equal(u[0], u[1])
     full = NativeSolver(_native.MODEL_WB11, n_samples=K, n_horizon=T, seed=21)
