@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MPPI_ABI_VERSION 1
+#define MPPI_ABI_VERSION 2
 #define MPPI_MAX_NU 12          /* controls per horizon step (whole body = 11)            */
 #define MPPI_MAX_HORIZON 256
 #define MPPI_MAX_JOINTS 8       /* revolute joints in the arm chain                      */
@@ -99,7 +99,28 @@ typedef struct mppi_config {
     float target_quat[4];       /* xyzw, mppi.py:72                                      */
     float drone_target[3];      /* drone_mppi.py:141                                     */
     float reserved[5];
+    /* The cost terms the reference constructs but leaves commented out of the sum
+     * (cost/cost_manager.py:83-87); enabled per bit, ARM7 / WB11 only.  Defaults are the
+     * reference's weights: covar_cost.py:14,20-25, action_cost.py:15-25, joint_space_cost.py:13,18-77. */
+    int32_t cost_flags;         /* MPPI_COST_* bits; 0 = the reference's live cost (pose terms only)        */
+    float gamma;                /* 0.98  discount (cost_manager.py:26)                                       */
+    float covar_weight;         /* 0.1   (cost_manager.py:36)                                                */
+    float alpha;                /* 0.1   (cost_manager.py:25): param_gamma = lambda * (1 - alpha)            */
+    float action_weight;        /* 0.01  (cost_manager.py:39)                                                */
+    float centering_weight;     /* 1.0   (cost_manager.py:42)                                                */
+    float joint_traj_weight;    /* 1.0   (cost_manager.py:43)                                                */
+    float limit_penalty;        /* 1e10  (joint_space_cost.py:70)                                            */
+    float q_center[7];          /* joint_space_cost.py:13                                                    */
+    float q_lower[7];           /* joint_space_cost.py:61                                                    */
+    float q_upper[7];           /* joint_space_cost.py:62                                                    */
+    float reserved2;
 } mppi_config_t;
+
+#define MPPI_COST_COVAR 1        /* covar_weight * lambda(1-alpha) * sum_t u_t^T Sigma^-1 v_t   (Sigma = sigma*I as in the reference) */
+#define MPPI_COST_CENTERING 2    /* centering_weight * sum_t gamma^t |q_t - q_center|^2                       */
+#define MPPI_COST_JOINT_TRAJ 4   /* joint_traj_weight * sum_t gamma^t |q_t - q_traj_t|^2 (q_traj = 0 unless mppi_set_joint_traj) */
+#define MPPI_COST_ACTION 8       /* action_weight * sum_t gamma^t |v_t|^2                                     */
+#define MPPI_COST_JOINT_LIMIT 16 /* sum_t gamma^t * limit_penalty * [any joint outside q_lower..q_upper]      */
 
 typedef struct mppi_ctx *mppi_handle_t;
 
@@ -120,9 +141,14 @@ int32_t mppi_abi_version(void);
 mppi_status_t mppi_set_chain(mppi_handle_t h, int32_t n_chain_joints, const int32_t *types,
                              const float *xyz, const float *rpy, const float *axis);
 
-/* Re-reads the mutable hyper-parameters of cfg (sigma, lambda_, dt, cost_w, quad_params); model,
+/* Re-reads the mutable hyper-parameters of cfg (sigma, lambda_, dt, cost_w, quad_params, cost_flags and
+ * the extra-cost weights); model,
  * sizes, device, seed and k_offset are fixed at creation.                                */
 mppi_status_t mppi_update_config(mppi_handle_t h, const mppi_config_t *cfg);
+
+/* Joint reference trajectory [T][7] for MPPI_COST_JOINT_TRAJ (host floats; the reference passes zeros,
+ * mppi.py:137-138).                                                                       */
+mppi_status_t mppi_set_joint_traj(mppi_handle_t h, const float *traj_host);
 
 /* target_pose / hard-coded drone target (mppi.py:70-72, drone_mppi.py:141).             */
 mppi_status_t mppi_set_target(mppi_handle_t h, const float *target_pos, const float *target_quat_xyzw,

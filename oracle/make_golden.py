@@ -185,6 +185,45 @@ def make_arm(name, K, T, seeds, q, qdot, base, store_noise, f64_state=False, wit
     np.savez_compressed(os.path.join(OUT, name), **rec)
 
 
+def make_arm_extra(name, K, T, seed, q, qdot, base):
+    """Reference arm step with the commented-out cost terms of cost_manager.py:83-87 re-enabled, one at a
+    time and all together, by calling the reference's own (constructed but unused) cost objects."""
+    rec = dict(K=K, T=T, q=np.asarray(q, np.float64), qdot=np.asarray(qdot, np.float64), base=np.asarray(base, np.float64),
+               seeds=np.asarray([seed]), sigma=0.1, lam=0.1, dt=0.01, f64_state=False)
+    noise = golden_noise(seed, K, T, 7, 0.1)
+    rec["noise_0"] = _tkn(noise)
+    g = torch.Generator().manual_seed(seed + 100)
+    u_prev = torch.randn(T, 7, generator=g) * 0.2          # non-zero nominal so the covariance term is non-trivial
+    rec["u_prev_0"] = _np(u_prev)
+    for label, flags in (("covar", 1), ("centering", 2), ("joint_traj", 4), ("action", 8), ("joint_limit", 16), ("all", 31)):
+        m = rh.load_arm(K, T)
+        _seat_arm(m, q, qdot, base)
+        m.u_prev = u_prev.clone()
+        cm = m.cost_manager
+
+        def all_cost(cm=cm, flags=flags):
+            S = torch.zeros((cm.n_sample), device=cm.device)
+            S += cm.pose_cost.compute_stage_cost(cm.eef_trajectories, cm.target)
+            S += cm.pose_cost.compute_terminal_cost(cm.eef_trajectories, cm.target)
+            if flags & 1:
+                S += cm.covar_cost.compute_covar_cost(cm.sigma_matrix, cm.u, cm.v)
+            if flags & 2:
+                S += cm.joint_cost.compute_centering_cost(cm.qSamples)
+            if flags & 4:
+                S += cm.joint_cost.compute_jointTraj_cost(cm.qSamples, cm.joint_trajectories)
+            if flags & 8:
+                S += cm.action_cost.compute_action_cost(cm.uSamples)
+            if flags & 16:
+                S += cm.joint_cost.compute_joint_limit_cost(cm.qSamples)
+            return S
+
+        cm.compute_all_cost = all_cost
+        cap = rh.arm_step(m, noise)
+        rec[f"S_{label}"] = _np(cap["S"])
+        rec[f"u_new_{label}"] = _np(cap["u_new"])
+    np.savez_compressed(os.path.join(OUT, name), **rec)
+
+
 # --------------------------------------------------------------------------- drone
 def make_drone(name, K, T, seeds, x0, v0, store_noise):
     m = rh.load_drone(K, T)
@@ -222,6 +261,7 @@ def main():
              store_noise=True, with_f64=True)
     make_arm("arm_K64_T32_f64state.npz", 64, 32, [1, 2], Q_HOME, qd, base_tilt, store_noise=False, f64_state=True, with_f64=True)
     make_arm("arm_K1024_T30.npz", 1024, 30, [0, 7], Q_HOME, [0.0] * 7, base_hover, store_noise=False, with_f64=True)
+    make_arm_extra("arm_extra_costs.npz", 64, 32, 9, [1.2, 0.8513, -0.4, 4.0, 0.7, 4.2, -1.0], qd, base_tilt)
     make_drone("drone_K64_T32.npz", 64, 32, [1, 2, 3], [0, 0, 2.1], [0, 0, 0], store_noise=True)
     make_drone("drone_K1024_T30.npz", 1024, 30, [0, 7], [0, 0, 2.1], [0.2, -0.1, 0.05], store_noise=False)
     for f in sorted(os.listdir(OUT)):

@@ -373,6 +373,62 @@ void oracle_arm_costs(int K, int T, const float *noise /*[T][K][7]*/, const floa
                                    wts, state_f64);
 }
 
+/* The cost terms the reference constructs but leaves commented out of the sum
+ * (S/cost/cost_manager.py:83-87), evaluated on the same rollout.  flags: 1 covar
+ * (S/cost/covar_cost.py:20-25), 2 centering, 4 joint tracking, 16 joint limit
+ * (S/cost/joint_space_cost.py:18-77), 8 action (S/cost/action_cost.py:15-25).
+ * ext = [gamma, covar_weight, lambda, alpha, action_w, centering_w, joint_traj_w, limit_penalty].
+ * PINNED by tests/golden/arm_extra_costs.npz (reference run with those lines re-enabled). */
+void oracle_arm_extra_costs(int K, int T, const float *noise /*[T][K][7]*/, const float *u_nom /*[T][7]*/,
+                            const float *q0, const float *qd0, float dt, int flags, const float *ext,
+                            const float *sigma /*[7]*/, const float *q_center, const float *q_lower,
+                            const float *q_upper, const float *q_traj /*[T][7] or NULL*/, float *S_out /*[K]*/)
+{
+    const float dt2 = (float)((double)dt * (double)dt);
+    const float gamma = ext[0];
+    const double covar_scale = (double)ext[1] * ((double)ext[2] * (1.0 - (double)ext[3]));   /* python floats */
+#pragma omp parallel for schedule(static)
+    for (int k = 0; k < K; ++k) {
+        double cum_v[7] = {0}, cum_q[7] = {0};
+        float vprev[7];
+        for (int i = 0; i < 7; ++i) vprev[i] = qd0[i];
+        double cov = 0, cen = 0, trk = 0, act = 0, lim = 0;
+        for (int t = 0; t < T; ++t) {
+            const float *eps = noise + ((size_t)t * K + k) * 7;
+            const float g = powf(gamma, (float)t);               /* gamma ** torch.arange(T) */
+            double c1 = 0, a1 = 0, ce = 0, tr = 0;
+            int oob = 0;
+            for (int i = 0; i < 7; ++i) {
+                float a = u_nom[t * 7 + i] + eps[i];
+                float dq = vprev[i] * dt + 0.5f * a * dt2;
+                cum_v[i] += (double)(a * dt);
+                vprev[i] = (float)cum_v[i] + qd0[i];
+                cum_q[i] += (double)dq;
+                float q = (float)cum_q[i] + q0[i];
+                c1 += (double)u_nom[t * 7 + i] * (double)((1.0f / sigma[i]) * a);
+                a1 += (double)(a * a);
+                float dc = q - q_center[i];
+                ce += (double)(dc * dc);
+                float dk = q - (q_traj ? q_traj[t * 7 + i] : 0.0f);
+                tr += (double)(dk * dk);
+                if (q < q_lower[i] || q > q_upper[i]) oob = 1;
+            }
+            cov += (double)(float)c1;
+            act += (double)((ext[4] * (float)a1) * g);
+            cen += (double)((ext[5] * (float)ce) * g);
+            trk += (double)((ext[6] * (float)tr) * g);
+            if (oob) lim += (double)(ext[7] * g);
+        }
+        float S = 0.0f;
+        if (flags & 1) S += (float)(covar_scale * (double)(float)cov);
+        if (flags & 2) S += (float)cen;
+        if (flags & 4) S += (float)trk;
+        if (flags & 8) S += (float)act;
+        if (flags & 16) S += (float)lim;
+        S_out[k] = S;
+    }
+}
+
 /* ------------------------------------------------------------------ drone (nu = 3) */
 /* S/mppi_solver/drone_mppi.py:46-55 (predict_trajectory) and :87-107 (costs):
  *   S = 100 * sum_{t<T-1} |x_t - x*|^2 + 20 * |x_{T-1} - x*|^2                          */

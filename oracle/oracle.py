@@ -153,6 +153,28 @@ def arm_costs(noise_tkn, u_nom, q0, qd0, base, target_pos=ARM_TARGET_POS, target
     return S
 
 
+Q_CENTER = (0.0, 0.0, 0.0, (-3.0718 - 0.0698) / 2, 0.0, (3.7525 - 0.0175) / 2, 0.0)      # cost/joint_space_cost.py:13
+Q_LOWER = (-6.2832, 0.8203, -6.2832, 0.5236, -6.2832, 1.1345, -6.2832)                   # :61
+Q_UPPER = (6.2832, 5.4629, 6.2832, 5.7596, 6.2832, 5.1487, 6.2832)                       # :62
+COST_COVAR, COST_CENTERING, COST_JOINT_TRAJ, COST_ACTION, COST_JOINT_LIMIT = 1, 2, 4, 8, 16
+
+
+def arm_extra_costs(noise_tkn, u_nom, q0, qd0, flags, dt=0.01, lam=0.1, gamma=0.98, covar_weight=0.1, alpha=0.1,
+                    action_weight=0.01, centering_weight=1.0, joint_traj_weight=1.0, limit_penalty=1e10,
+                    sigma=0.1, q_traj=None) -> np.ndarray:
+    """Sum of the reference's optional cost terms selected by `flags` (cost_manager.py:83-87)."""
+    noise, npt = _f(noise_tkn)
+    T, K, nu = noise.shape
+    assert nu == 7
+    S = np.zeros(K, f32)
+    ext = np.array([gamma, covar_weight, lam, alpha, action_weight, centering_weight, joint_traj_weight, limit_penalty], f32)
+    sig = np.broadcast_to(np.asarray(sigma, f32), (7,)).copy()
+    lib().oracle_arm_extra_costs(K, T, npt, _f(u_nom)[1], _f(q0)[1], _f(qd0)[1], C.c_float(dt), int(flags), _f(ext)[1],
+                                 _f(sig)[1], _f(Q_CENTER)[1], _f(Q_LOWER)[1], _f(Q_UPPER)[1],
+                                 None if q_traj is None else _f(q_traj)[1], S.ctypes.data_as(_fp))
+    return S
+
+
 def drone_costs(noise_tkn, u_nom, x0, v0, target=DRONE_TARGET, dt=0.01, weights=DRONE_WEIGHTS) -> np.ndarray:
     noise, npt = _f(noise_tkn)
     T, K, nu = noise.shape

@@ -19,11 +19,12 @@ MPPI_OUT_REACH, MPPI_OUT_RHO, MPPI_OUT_ETA, MPPI_OUT_ESS, MPPI_OUT_STEP = 52, 53
 MODEL_DRONE3, MODEL_ARM7, MODEL_QUAD4, MODEL_WB11 = 0, 1, 2, 3
 MODEL_NU = {MODEL_DRONE3: 3, MODEL_ARM7: 7, MODEL_QUAD4: 4, MODEL_WB11: 11}
 MODEL_STATE = {MODEL_DRONE3: 6, MODEL_ARM7: 21, MODEL_QUAD4: 12, MODEL_WB11: 26}
-ABI_VERSION = 1
+ABI_VERSION = 2
+COST_COVAR, COST_CENTERING, COST_JOINT_TRAJ, COST_ACTION, COST_JOINT_LIMIT = 1, 2, 4, 8, 16
 
 EXPORTS = [
     "mppi_abi_version", "mppi_last_error", "mppi_default_config", "mppi_create", "mppi_destroy",
-    "mppi_update_config", "mppi_set_chain", "mppi_set_target", "mppi_set_state", "mppi_step", "mppi_rollout", "mppi_weight",
+    "mppi_update_config", "mppi_set_joint_traj", "mppi_set_chain", "mppi_set_target", "mppi_set_state", "mppi_step", "mppi_rollout", "mppi_weight",
     "mppi_finalize", "mppi_rho_ptr", "mppi_wsum_ptr", "mppi_wsum_count", "mppi_cost_ptr",
     "mppi_p2p_export", "mppi_p2p_bind", "mppi_step_p2p", "mppi_step_sync", "mppi_step_host", "mppi_generate_noise", "mppi_measure_fp32_peak",
     "mppi_algorithmic_flops_per_rollout_step",
@@ -40,6 +41,10 @@ class MppiConfig(C.Structure):
         ("sigma", C.c_float * MPPI_MAX_NU), ("cost_w", C.c_float * 8), ("quad_params", C.c_float * 6),
         ("target_pos", C.c_float * 3), ("target_quat", C.c_float * 4), ("drone_target", C.c_float * 3),
         ("reserved", C.c_float * 5),
+        ("cost_flags", C.c_int32), ("gamma", C.c_float), ("covar_weight", C.c_float), ("alpha", C.c_float),
+        ("action_weight", C.c_float), ("centering_weight", C.c_float), ("joint_traj_weight", C.c_float),
+        ("limit_penalty", C.c_float), ("q_center", C.c_float * 7), ("q_lower", C.c_float * 7), ("q_upper", C.c_float * 7),
+        ("reserved2", C.c_float),
     ]
 
 
@@ -68,6 +73,7 @@ def load():
     lib.mppi_create.argtypes = [C.POINTER(MppiConfig), C.POINTER(vp)]
     lib.mppi_destroy.argtypes = [vp]
     lib.mppi_update_config.argtypes = [vp, C.POINTER(MppiConfig)]
+    lib.mppi_set_joint_traj.argtypes = [vp, _fp]
     lib.mppi_set_chain.argtypes = [vp, i32, C.POINTER(i32), _fp, _fp, _fp]
     lib.mppi_set_target.argtypes = [vp, _fp, _fp, _fp]
     lib.mppi_set_state.argtypes = [vp, _fp, i32]

@@ -36,7 +36,7 @@ def _require_cuda(device) -> torch.device:
 class NativeSolver:
     def __init__(self, model: int, *, n_samples=None, n_horizon=None, dt=None, lam=None, sigma=None,
                  seed: int = 0, device=None, k_offset: int = 0, savgol_window=None, cost_w=None,
-                 quad_params=None, target_pos=None, target_quat=None, drone_target=None):
+                 quad_params=None, target_pos=None, target_quat=None, drone_target=None, cost_flags: int = 0):
         self.device = _require_cuda(device)
         self._lib = _native.load()
         cfg = _native.default_config(model)
@@ -61,6 +61,7 @@ class NativeSolver:
                 arr = getattr(cfg, name)
                 for i, v in enumerate(val):
                     arr[i] = float(v)
+        cfg.cost_flags = int(cost_flags)
         cfg.seed = int(seed) & (2 ** 64 - 1)
         cfg.k_offset = int(k_offset)
         cfg.device = self.device.index
@@ -127,6 +128,24 @@ class NativeSolver:
         _native.check(self._lib.mppi_set_target(self.handle, None if a is None else _native.fptr(a),
                                                 None if b is None else _native.fptr(b),
                                                 None if c is None else _native.fptr(c)), self.handle)
+
+    def update_config(self, **fields) -> None:
+        """Change mutable hyper-parameters (sigma, lambda_, dt, cost_w, cost_flags, gamma, ...) between steps."""
+        for name, val in fields.items():
+            cur = getattr(self.cfg, name)
+            if hasattr(cur, "__len__"):
+                for i, v in enumerate(val):
+                    cur[i] = float(v)
+            else:
+                setattr(self.cfg, name, val)
+        _native.check(self._lib.mppi_update_config(self.handle, C.byref(self.cfg)), self.handle)
+
+    def set_joint_traj(self, traj) -> None:
+        """Joint reference trajectory [T][7] for the optional tracking cost (zeros by default)."""
+        t = np.ascontiguousarray(traj, np.float32)
+        if t.shape != (self.T, 7):
+            raise ValueError(f"joint trajectory must be [{self.T}][7]")
+        _native.check(self._lib.mppi_set_joint_traj(self.handle, _native.fptr(t)), self.handle)
 
     def set_chain(self, types, xyz, rpy, axis) -> None:
         t = np.ascontiguousarray(types, np.int32)

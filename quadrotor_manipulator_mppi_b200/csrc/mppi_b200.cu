@@ -164,7 +164,8 @@ struct mppi_ctx {
     P2PParams X_off{};              // world == 1: exchange disabled
     void *p2p_peer[kMaxRanks] = {};
     bool baked_fk = false;          // runtime chain == compile-time FkKinova tables
-    size_t rollout_smem[4] = {0, 0, 0, 0};   // tuned dynamic smem per kernel variant (0 = not yet tuned)
+    size_t rollout_smem[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // tuned dynamic smem per kernel variant (0 = not yet tuned)
+    float *d_qtraj = nullptr;       // [T][7] joint reference trajectory (MPPI_COST_JOINT_TRAJ), zeros by default
     cudaStream_t own_stream = nullptr;
     std::string err;
 };
@@ -182,6 +183,29 @@ mppi_status_t fail(mppi_handle_t h, mppi_status_t code, const std::string &msg)
         if (e_ != cudaSuccess)                                                                         \
             return fail(h, MPPI_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));        \
     } while (0)
+
+void load_extra_costs(mppi_ctx *h, const mppi_config_t *cfg)
+{
+    StepParams &P = h->P;
+    P.cost_flags = cfg->cost_flags;
+    P.gamma = cfg->gamma;
+    P.covar_scale = cfg->covar_weight * (cfg->lambda_ * (1.0f - cfg->alpha));     // covar_cost.py:14,23
+    P.action_weight = cfg->action_weight;
+    P.centering_weight = cfg->centering_weight;
+    P.joint_traj_weight = cfg->joint_traj_weight;
+    P.limit_penalty = cfg->limit_penalty;
+    const int arm0 = (cfg->model == MPPI_MODEL_WB11) ? 4 : 0;
+    for (int i = 0; i < 7; ++i) {
+        P.inv_sigma_arm[i] = cfg->sigma[arm0 + i] != 0.f ? 1.0f / cfg->sigma[arm0 + i] : 0.f;
+        P.q_center[i] = cfg->q_center[i]; P.q_lower[i] = cfg->q_lower[i]; P.q_upper[i] = cfg->q_upper[i];
+    }
+    h->cfg.cost_flags = cfg->cost_flags; h->cfg.gamma = cfg->gamma; h->cfg.covar_weight = cfg->covar_weight;
+    h->cfg.alpha = cfg->alpha; h->cfg.action_weight = cfg->action_weight; h->cfg.centering_weight = cfg->centering_weight;
+    h->cfg.joint_traj_weight = cfg->joint_traj_weight; h->cfg.limit_penalty = cfg->limit_penalty;
+    std::memcpy(h->cfg.q_center, cfg->q_center, sizeof(cfg->q_center));
+    std::memcpy(h->cfg.q_lower, cfg->q_lower, sizeof(cfg->q_lower));
+    std::memcpy(h->cfg.q_upper, cfg->q_upper, sizeof(cfg->q_upper));
+}
 
 void set_target_locked(mppi_ctx *h, const float *pos, const float *quat, const float *drone_target)
 {
@@ -278,18 +302,23 @@ mppi_status_t launch_rollout(mppi_ctx *h, const float *d_u_nom, const float *d_n
     const int grid = (h->P.K + kRolloutThreads - 1) / kRolloutThreads;
     const size_t smem = (size_t)h->P.T * NU * sizeof(float);
     const bool baked = HAS_ARM && h->baked_fk;      // FK unrolled from the URDF constants (fk_tables_gen.cuh)
-    const int variant = (d_noise ? 0 : 1) + (baked ? 2 : 0);
+    const bool extra = HAS_ARM && h->P.cost_flags != 0;      // optional cost terms: separate, slower instantiation
+    const int variant = (d_noise ? 0 : 1) + (baked ? 2 : 0) + (extra ? 4 : 0);
     auto go = [&](auto kernel) -> mppi_status_t {
         if (h->rollout_smem[variant] == 0) h->rollout_smem[variant] = tuned_rollout_smem(h, kernel, grid, smem);
-        kernel<<<grid, kRolloutThreads, h->rollout_smem[variant], st>>>(h->P, h->dyn, d_u_nom, d_noise, d_cost, h->d_rho);
+        kernel<<<grid, kRolloutThreads, h->rollout_smem[variant], st>>>(h->P, h->dyn, d_u_nom, d_noise, d_cost, h->d_rho, h->d_qtraj);
         MPPI_CUDA(h, cudaGetLastError());
         return MPPI_OK;
     };
     switch (variant) {
-        case 0: return go(rollout_cost_kernel<MODEL, false, false>);
-        case 1: return go(rollout_cost_kernel<MODEL, true, false>);
-        case 2: return go(rollout_cost_kernel<MODEL, false, HAS_ARM>);
-        default: return go(rollout_cost_kernel<MODEL, true, HAS_ARM>);
+        case 0: return go(rollout_cost_kernel<MODEL, false, false, false>);
+        case 1: return go(rollout_cost_kernel<MODEL, true, false, false>);
+        case 2: return go(rollout_cost_kernel<MODEL, false, HAS_ARM, false>);
+        case 3: return go(rollout_cost_kernel<MODEL, true, HAS_ARM, false>);
+        case 4: return go(rollout_cost_kernel<MODEL, false, false, HAS_ARM>);
+        case 5: return go(rollout_cost_kernel<MODEL, true, false, HAS_ARM>);
+        case 6: return go(rollout_cost_kernel<MODEL, false, HAS_ARM, HAS_ARM>);
+        default: return go(rollout_cost_kernel<MODEL, true, HAS_ARM, HAS_ARM>);
     }
 }
 
@@ -426,6 +455,13 @@ mppi_status_t mppi_default_config(int32_t model, mppi_config_t *cfg)
     // aerial_manipulation/src/controller.cpp:159-161,488-490; k_d is undefined in the draft -> 0
     const float qp[6] = {14.7f, 1.0f / 1.57f, 1.0f / 3.93f, 1.0f / 2.59f, 0.0f, -9.81f};
     std::memcpy(cfg->quad_params, qp, sizeof(qp));
+    cfg->cost_flags = 0;                                  // cost_manager.py:83-87: commented out in the reference
+    cfg->gamma = 0.98f; cfg->covar_weight = 0.1f; cfg->alpha = 0.1f; cfg->action_weight = 0.01f;      // cost_manager.py:25-26,36,39
+    cfg->centering_weight = 1.0f; cfg->joint_traj_weight = 1.0f; cfg->limit_penalty = 1e10f;          // :42-43, joint_space_cost.py:70
+    const float qc[7] = {0.0f, 0.0f, 0.0f, (-3.0718f - 0.0698f) / 2, 0.0f, (3.7525f - 0.0175f) / 2, 0.0f};   // joint_space_cost.py:13
+    const float ql[7] = {-6.2832f, 0.8203f, -6.2832f, 0.5236f, -6.2832f, 1.1345f, -6.2832f};          // :61
+    const float qu[7] = {6.2832f, 5.4629f, 6.2832f, 5.7596f, 6.2832f, 5.1487f, 6.2832f};              // :62
+    std::memcpy(cfg->q_center, qc, sizeof(qc)); std::memcpy(cfg->q_lower, ql, sizeof(ql)); std::memcpy(cfg->q_upper, qu, sizeof(qu));
     switch (model) {
         case MPPI_MODEL_DRONE3:
             cfg->n_samples = 1000; cfg->n_horizon = 32; cfg->savgol_window = 5;       // drone_mppi.py:16-17,160
@@ -501,6 +537,7 @@ mppi_status_t mppi_create(const mppi_config_t *cfg, mppi_handle_t *out)
     std::memcpy(P.cost_w, cfg->cost_w, sizeof(P.cost_w));
     std::memcpy(P.quad, cfg->quad_params, sizeof(P.quad));
     std::memcpy(P.taps, taps, sizeof(taps));
+    load_extra_costs(h, cfg);
     set_target_locked(h, cfg->target_pos, cfg->target_quat, cfg->drone_target);
     if (set_chain_impl(h, 8, kKinovaTypes, &kKinovaXyz[0][0], &kKinovaRpy[0][0], &kKinovaAxis[0][0]) != MPPI_OK) {
         g_create_error = h->err; delete h; return MPPI_ERR_INVALID_ARG;
@@ -526,6 +563,8 @@ mppi_status_t mppi_create(const mppi_config_t *cfg, mppi_handle_t *out)
     if ((e = cudaMalloc(&h->d_wsum, row * sizeof(float))) != cudaSuccess) return cleanup(e, "cudaMalloc(wsum)");
     if ((e = cudaMalloc(&h->d_u, (size_t)P.T * nu * sizeof(float))) != cudaSuccess) return cleanup(e, "cudaMalloc(u)");
     if ((e = cudaMalloc(&h->d_out, MPPI_OUT_FLOATS * sizeof(float))) != cudaSuccess) return cleanup(e, "cudaMalloc(out)");
+    if ((e = cudaMalloc(&h->d_qtraj, (size_t)P.T * 7 * sizeof(float))) != cudaSuccess) return cleanup(e, "cudaMalloc(qtraj)");
+    if ((e = cudaMemset(h->d_qtraj, 0, (size_t)P.T * 7 * sizeof(float))) != cudaSuccess) return cleanup(e, "cudaMemset(qtraj)");
     h->h_pinned_floats = (size_t)P.T * nu + MPPI_OUT_FLOATS;
     if ((e = cudaMallocHost(&h->h_pinned, h->h_pinned_floats * sizeof(float))) != cudaSuccess) return cleanup(e, "cudaMallocHost");
     if ((e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return cleanup(e, "cudaStreamCreate");
@@ -543,7 +582,7 @@ mppi_status_t mppi_destroy(mppi_handle_t h)
         DeviceGuard guard(h->cfg.device);
         cudaDeviceSynchronize();
         cudaFree(h->d_cost); cudaFree(h->d_rho); cudaFree(h->d_w); cudaFree(h->d_eta_part); cudaFree(h->d_part); cudaFree(h->d_wsum);
-        cudaFree(h->d_u); cudaFree(h->d_out); cudaFree(h->d_noise);
+        cudaFree(h->d_u); cudaFree(h->d_out); cudaFree(h->d_noise); cudaFree(h->d_qtraj);
         for (int r = 0; r < kMaxRanks; ++r) if (h->p2p_peer[r]) cudaIpcCloseMemHandle(h->p2p_peer[r]);
         cudaFree(h->p2p_buf);
         if (h->h_pinned) cudaFreeHost(h->h_pinned);
@@ -574,6 +613,15 @@ mppi_status_t mppi_update_config(mppi_handle_t h, const mppi_config_t *cfg)
     std::memcpy(P.sigma, cfg->sigma, sizeof(P.sigma));
     std::memcpy(P.cost_w, cfg->cost_w, sizeof(P.cost_w));
     std::memcpy(P.quad, cfg->quad_params, sizeof(P.quad));
+    load_extra_costs(h, cfg);
+    return MPPI_OK;
+}
+
+mppi_status_t mppi_set_joint_traj(mppi_handle_t h, const float *traj_host)
+{
+    if (!h || !traj_host) return fail(h, MPPI_ERR_INVALID_ARG, "null trajectory");
+    DeviceGuard guard(h->cfg.device);
+    MPPI_CUDA(h, cudaMemcpy(h->d_qtraj, traj_host, (size_t)h->P.T * 7 * sizeof(float), cudaMemcpyHostToDevice));
     return MPPI_OK;
 }
 

@@ -38,6 +38,12 @@ struct StepParams {
     float quad[6];               // mass, 1/Ixx, 1/Iyy, 1/Izz, kd, gz
     float taps[MPPI_MAX_SAVGOL];
     ChainDev chain;
+    // optional cost terms (cost/cost_manager.py:83-87), used by the EXTRA kernel variants only
+    int cost_flags;
+    float gamma, covar_scale /* covar_weight * lambda * (1 - alpha) */, action_weight, centering_weight,
+        joint_traj_weight, limit_penalty;
+    float inv_sigma_arm[7];      // Sigma^-1 of the reference is 1/sigma (Sigma = sigma * I)
+    float q_center[7], q_lower[7], q_upper[7];
 };
 
 // Everything that changes per control step; also passed by value (192 B), so a step needs

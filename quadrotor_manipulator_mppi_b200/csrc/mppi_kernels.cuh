@@ -22,11 +22,12 @@ constexpr int kWeightTile = 2048;       // samples whose weights are staged in s
 // Replaces S/mppi_solver/mppi.py:129-140 (sampling, get_sample_joint, compute_fk_gpu,
 // CostManager.compute_all_cost) and S/mppi_solver/drone_mppi.py:143-151.
 // ------------------------------------------------------------------------------------------
-template <int MODEL, bool PHILOX, bool BAKED>
+template <int MODEL, bool PHILOX, bool BAKED, bool EXTRA = false>
 __global__ void __launch_bounds__(kRolloutThreads)
 rollout_cost_kernel(const __grid_constant__ StepParams P, const __grid_constant__ DynBlock D,
                     const float *__restrict__ u_nom, const float *__restrict__ noise,
-                    float *__restrict__ cost_out, int32_t *__restrict__ rho_enc)
+                    float *__restrict__ cost_out, int32_t *__restrict__ rho_enc,
+                    const float *__restrict__ q_traj = nullptr)
 {
     constexpr int NU = ModelNu<MODEL>::value;
     constexpr int NCH = (NU + 3) / 4;
@@ -86,6 +87,7 @@ rollout_cost_kernel(const __grid_constant__ StepParams P, const __grid_constant_
     if constexpr (HAS_QUAD) quad_load(qs, D.state);
 
     float S = 0.f, comp = 0.f;       // Kahan-compensated running cost
+    float x_cov = 0.f, x_cen = 0.f, x_trk = 0.f, x_act = 0.f, x_lim = 0.f, gpow = 1.0f;   // EXTRA cost terms, gamma^t
     float Sd = 0.f;                  // squared-distance stage cost (drone / quad part)
     float term_d = 0.f;
 
@@ -110,6 +112,17 @@ rollout_cost_kernel(const __grid_constant__ StepParams P, const __grid_constant_
         for (int i = 0; i < NU; ++i) a[i] = __fadd_rn(s_unom[t * NU + i], a[i]);
 
         const bool last = (t == P.T - 1);
+        if constexpr (EXTRA && HAS_ARM) {
+            // covar_cost.py:20-25: u^T Sigma^-1 v per step;  action_cost.py:15-25: gamma^t |v|^2
+            float cov = 0.f, act = 0.f;
+#pragma unroll
+            for (int i = 0; i < 7; ++i) {
+                cov = fmaf(s_unom[t * NU + ARM0 + i] * P.inv_sigma_arm[i], a[ARM0 + i], cov);
+                act = fmaf(a[ARM0 + i], a[ARM0 + i], act);
+            }
+            x_cov += cov;
+            x_act = fmaf(gpow, act, x_act);
+        }
         if constexpr (MODEL == MPPI_MODEL_DRONE3) {
             // double integrator (S/mppi_solver/drone_mppi.py:46-55) + squared distance (:87-107)
             float sq = 0.f;
@@ -142,6 +155,24 @@ rollout_cost_kernel(const __grid_constant__ StepParams P, const __grid_constant_
                 cum_q[i] += dq;
                 sincos_pi(cum_q[i] + D.state[QOFF + i], sq[i], cq[i]);
             }
+            if constexpr (EXTRA) {
+                // joint_space_cost.py:18-77: centering, tracking, joint-limit indicator, all discounted by gamma^t
+                float cen = 0.f, trk = 0.f;
+                bool out_of_bounds = false;
+#pragma unroll
+                for (int i = 0; i < 7; ++i) {
+                    const float q = cum_q[i] + D.state[QOFF + i];
+                    const float dc = q - P.q_center[i];
+                    cen = fmaf(dc, dc, cen);
+                    const float dtk = q - (q_traj ? __ldg(q_traj + t * 7 + i) : 0.0f);
+                    trk = fmaf(dtk, dtk, trk);
+                    out_of_bounds = out_of_bounds || (q < P.q_lower[i]) || (q > P.q_upper[i]);
+                }
+                x_cen = fmaf(gpow, cen, x_cen);
+                x_trk = fmaf(gpow, trk, x_trk);
+                if (out_of_bounds) x_lim = fmaf(gpow, P.limit_penalty, x_lim);
+                gpow *= P.gamma;
+            }
             float R[9], p[3];
             if constexpr (MODEL == MPPI_MODEL_ARM7) {
 #pragma unroll
@@ -173,6 +204,14 @@ rollout_cost_kernel(const __grid_constant__ StepParams P, const __grid_constant_
         S = S + fmaf(Sd, P.cost_w[4], term_d * P.cost_w[5]);
     }
 
+    if constexpr (EXTRA && HAS_ARM) {
+        // same order as the commented-out sum, cost_manager.py:83-87
+        if (P.cost_flags & MPPI_COST_COVAR) S += P.covar_scale * x_cov;
+        if (P.cost_flags & MPPI_COST_CENTERING) S += P.centering_weight * x_cen;
+        if (P.cost_flags & MPPI_COST_JOINT_TRAJ) S += P.joint_traj_weight * x_trk;
+        if (P.cost_flags & MPPI_COST_ACTION) S += P.action_weight * x_act;
+        if (P.cost_flags & MPPI_COST_JOINT_LIMIT) S += x_lim;
+    }
     if (active) cost_out[k] = S;
     // ---- block minimum -> one atomicMin on the order-preserving encoding
     float m = warp_min(active ? S : __int_as_float(0x7f800000));

@@ -25,9 +25,11 @@ from ..utils.pose import Pose
 
 class MPPI:
     MODEL = _native.MODEL_ARM7
+    COST_TERMS = {"covar": _native.COST_COVAR, "centering": _native.COST_CENTERING, "joint_traj": _native.COST_JOINT_TRAJ,
+                  "action": _native.COST_ACTION, "joint_limit": _native.COST_JOINT_LIMIT}
 
     def __init__(self, *, n_samples: int = 100, n_horizon: int = 32, dt: float = 0.01, sigma=0.1, lam: float = 0.1,
-                 seed: int = 0, device=None, verbose: bool = True):
+                 seed: int = 0, device=None, verbose: bool = True, cost_terms=()):
         self.n_action = 7
         self.n_manipulator_dof = 7
         self.n_mobile_dof = 0
@@ -35,8 +37,13 @@ class MPPI:
         self.n_horizon = int(n_horizon)
         self.dt = float(dt)
         self._lambda = float(lam)
+        # cost_terms: any of the terms the reference constructs but comments out of the sum
+        # (cost/cost_manager.py:83-87): "covar", "centering", "joint_traj", "action", "joint_limit"
+        flags = 0
+        for name in cost_terms:
+            flags |= self.COST_TERMS[name]
         self._solver = NativeSolver(self.MODEL, n_samples=n_samples, n_horizon=n_horizon, dt=dt, lam=lam, sigma=sigma,
-                                    seed=seed, device=device)
+                                    seed=seed, device=device, cost_flags=flags)
         self.device = self._solver.device
         if verbose:
             print(f"[MPPI] Using device: {self.device}")                      # mppi.py:33

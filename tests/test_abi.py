@@ -29,7 +29,7 @@ def test_library_builds_and_exports_header_symbols():
 
 def test_config_struct_mirror_and_defaults():
     from quadrotor_manipulator_mppi_b200 import _native
-    assert C.sizeof(_native.MppiConfig) == 224
+    assert C.sizeof(_native.MppiConfig) == 344
     arm = _native.default_config(_native.MODEL_ARM7)
     assert (arm.n_samples, arm.n_horizon, arm.savgol_window) == (100, 32, 9)      # mppi.py:40-41,149
     assert abs(arm.sigma[0] - 0.1) < 1e-7 and abs(arm.lambda_ - 0.1) < 1e-7 and abs(arm.dt - 0.01) < 1e-9

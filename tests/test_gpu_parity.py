@@ -99,6 +99,24 @@ def test_arm_weighting_stage_isolated(name, native):
         assert abs(float(out[native.MPPI_OUT_ESS]) - ess_ref) < 1e-4 * ess_ref
 
 
+@pytest.mark.parametrize("label,terms", [("covar", ("covar",)), ("centering", ("centering",)), ("joint_traj", ("joint_traj",)),
+                                         ("action", ("action",)), ("joint_limit", ("joint_limit",)),
+                                         ("all", ("covar", "centering", "joint_traj", "action", "joint_limit"))])
+def test_arm_optional_cost_terms_against_reference_golden(label, terms, oracle):
+    """the cost terms the reference builds but comments out (cost_manager.py:83-87)."""
+    g = load_golden("arm_extra_costs.npz")
+    m = _arm(int(g["K"]), int(g["T"]), cost_terms=terms)
+    _seat_arm(m, g)
+    m.u_prev = torch.tensor(g["u_prev_0"])
+    _, _, S = m.compute_control_input(noise=g["noise_0"], return_costs=True)
+    S = S.cpu().numpy()
+    assert rel_inf(S, g[f"S_{label}"]) < 2e-6
+    iso = oracle._update(S, g["noise_0"], g["u_prev_0"], 0.1, 9)
+    assert rel_inf(m.u_prev.cpu().numpy(), iso["u_new"]) < 1e-5
+    if label not in ("joint_limit", "all"):     # with the 1e10 indicator a float32 S has no resolution left below it
+        assert rel_inf(m.u_prev.cpu().numpy(), g[f"u_new_{label}"]) < 3e-3
+
+
 # ------------------------------------------------------------------ drone vs golden
 @pytest.mark.parametrize("name", ["drone_K64_T32.npz", "drone_K1024_T30.npz"])
 def test_drone_against_reference_golden(name):

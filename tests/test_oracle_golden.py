@@ -113,6 +113,17 @@ def test_arm_steps(oracle, name):
         assert o["qdes"].dtype == g[f"qdes_{i}"].dtype      # f64 when the state came via update_joint
 
 
+def test_arm_optional_cost_terms(oracle):
+    """The terms cost_manager.py:83-87 leaves commented out, pinned by a reference run with them re-enabled."""
+    g = load_golden("arm_extra_costs.npz")
+    noise, u_prev = g["noise_0"], g["u_prev_0"]
+    base = oracle.arm_costs(noise, u_prev, g["q"], g["qdot"], g["base"])
+    for label, flags in (("covar", 1), ("centering", 2), ("joint_traj", 4), ("action", 8), ("joint_limit", 16), ("all", 31)):
+        S = (base + oracle.arm_extra_costs(noise, u_prev, g["q"], g["qdot"], flags)).astype(np.float32)
+        assert rel_inf(S, g[f"S_{label}"]) < 1e-6, label
+    assert int((g["S_joint_limit"] > 1e9).sum()) == 63          # the fixture does exercise the limit indicator
+
+
 @pytest.mark.parametrize("name", ["drone_K64_T32.npz", "drone_K1024_T30.npz"])
 def test_drone_steps(oracle, name):
     g = load_golden(name)
