@@ -5,6 +5,7 @@
 // either launches on the device or returns an error.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -164,7 +165,8 @@ struct mppi_ctx {
     P2PParams X_off{};              // world == 1: exchange disabled
     void *p2p_peer[kMaxRanks] = {};
     bool baked_fk = false;          // runtime chain == compile-time FkKinova tables
-    size_t rollout_smem[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // tuned dynamic smem per kernel variant (0 = not yet tuned)
+    size_t rollout_smem[16] = {};   // tuned dynamic smem per kernel variant (0 = not yet tuned); +8 = two samples per thread
+    int vec2_min_samples = 0;       // K at or above which the packed two-samples-per-thread rollout is used
     float *d_qtraj = nullptr;       // [T][7] joint reference trajectory (MPPI_COST_JOINT_TRAJ), zeros by default
     cudaStream_t own_stream = nullptr;
     std::string err;
@@ -270,55 +272,73 @@ mppi_status_t set_chain_impl(mppi_ctx *h, int n, const int32_t *types, const flo
 // Pick the residency o <= o_max that minimises ceil(blocks / (SMs * o)) * o -- i.e. avoid a nearly
 // empty last wave -- and enforce it by padding the dynamic shared memory request.
 template <typename KernelT>
-size_t tuned_rollout_smem(mppi_ctx *h, KernelT kernel, int grid, size_t smem_needed)
+size_t tuned_rollout_smem(mppi_ctx *h, KernelT kernel, int threads, int grid, size_t smem_needed)
 {
     int omax = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&omax, kernel, kRolloutThreads, smem_needed) != cudaSuccess || omax < 1) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&omax, kernel, threads, smem_needed) != cudaSuccess || omax < 1) {
         cudaGetLastError();
         return smem_needed;
     }
     auto cost = [&](int o) { return (long long)((grid + (long long)h->num_sms * o - 1) / ((long long)h->num_sms * o)) * o; };
     int best_o = omax;
     long long best = cost(omax);
-    for (int o = omax - 1; o >= 5 && o >= omax - 3; --o)
+    const int omin = omax > 6 ? omax - 3 : (omax + 1) / 2;
+    for (int o = omax - 1; o >= omin && o >= 2; --o)
         if (cost(o) < best) { best = cost(o); best_o = o; }
     if (best_o == omax) return smem_needed;
     size_t pad = (size_t)(228 * 1024) / best_o - 1024 - 256;      // 1 KB per block is reserved by the driver
     pad &= ~(size_t)255;
     if (pad < smem_needed || pad > 48 * 1024) return smem_needed;
     int got = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&got, kernel, kRolloutThreads, pad) != cudaSuccess || got != best_o) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&got, kernel, threads, pad) != cudaSuccess || got != best_o) {
         cudaGetLastError();
         return smem_needed;
     }
     return pad;
 }
 
+template <int MODEL, bool PHILOX, bool BAKED, bool EXTRA>
+mppi_status_t launch_rollout_variant(mppi_ctx *h, int variant, const float *d_u_nom, const float *d_noise, float *d_cost,
+                                     cudaStream_t st)
+{
+    constexpr int NU = ModelNu<MODEL>::value;
+    const size_t smem = (size_t)h->P.T * NU * sizeof(float);
+    // Two samples per thread (packed FP32x2) once there is enough work to fill the machine with
+    // half as many threads; below that, one sample per thread keeps more warps in flight.
+    const bool vec2 = h->P.K >= h->vec2_min_samples;
+    if (vec2) {
+        auto kernel = rollout_cost_kernel<MODEL, PHILOX, BAKED, EXTRA, f2, kRolloutThreads2>;
+        const int grid = (h->P.K + 2 * kRolloutThreads2 - 1) / (2 * kRolloutThreads2);
+        size_t &tuned = h->rollout_smem[variant + 8];
+        if (tuned == 0) tuned = tuned_rollout_smem(h, kernel, kRolloutThreads2, grid, smem);
+        kernel<<<grid, kRolloutThreads2, tuned, st>>>(h->P, h->dyn, d_u_nom, d_noise, d_cost, h->d_rho, h->d_qtraj);
+    } else {
+        auto kernel = rollout_cost_kernel<MODEL, PHILOX, BAKED, EXTRA, float, kRolloutThreads>;
+        const int grid = (h->P.K + kRolloutThreads - 1) / kRolloutThreads;
+        size_t &tuned = h->rollout_smem[variant];
+        if (tuned == 0) tuned = tuned_rollout_smem(h, kernel, kRolloutThreads, grid, smem);
+        kernel<<<grid, kRolloutThreads, tuned, st>>>(h->P, h->dyn, d_u_nom, d_noise, d_cost, h->d_rho, h->d_qtraj);
+    }
+    MPPI_CUDA(h, cudaGetLastError());
+    return MPPI_OK;
+}
+
 template <int MODEL>
 mppi_status_t launch_rollout(mppi_ctx *h, const float *d_u_nom, const float *d_noise, float *d_cost, cudaStream_t st)
 {
-    constexpr int NU = ModelNu<MODEL>::value;
     constexpr bool HAS_ARM = (MODEL == MPPI_MODEL_ARM7 || MODEL == MPPI_MODEL_WB11);
-    const int grid = (h->P.K + kRolloutThreads - 1) / kRolloutThreads;
-    const size_t smem = (size_t)h->P.T * NU * sizeof(float);
     const bool baked = HAS_ARM && h->baked_fk;      // FK unrolled from the URDF constants (fk_tables_gen.cuh)
     const bool extra = HAS_ARM && h->P.cost_flags != 0;      // optional cost terms: separate, slower instantiation
     const int variant = (d_noise ? 0 : 1) + (baked ? 2 : 0) + (extra ? 4 : 0);
-    auto go = [&](auto kernel) -> mppi_status_t {
-        if (h->rollout_smem[variant] == 0) h->rollout_smem[variant] = tuned_rollout_smem(h, kernel, grid, smem);
-        kernel<<<grid, kRolloutThreads, h->rollout_smem[variant], st>>>(h->P, h->dyn, d_u_nom, d_noise, d_cost, h->d_rho, h->d_qtraj);
-        MPPI_CUDA(h, cudaGetLastError());
-        return MPPI_OK;
-    };
     switch (variant) {
-        case 0: return go(rollout_cost_kernel<MODEL, false, false, false>);
-        case 1: return go(rollout_cost_kernel<MODEL, true, false, false>);
-        case 2: return go(rollout_cost_kernel<MODEL, false, HAS_ARM, false>);
-        case 3: return go(rollout_cost_kernel<MODEL, true, HAS_ARM, false>);
-        case 4: return go(rollout_cost_kernel<MODEL, false, false, HAS_ARM>);
-        case 5: return go(rollout_cost_kernel<MODEL, true, false, HAS_ARM>);
-        case 6: return go(rollout_cost_kernel<MODEL, false, HAS_ARM, HAS_ARM>);
-        default: return go(rollout_cost_kernel<MODEL, true, HAS_ARM, HAS_ARM>);
+        case 0: return launch_rollout_variant<MODEL, false, false, false>(h, variant, d_u_nom, d_noise, d_cost, st);
+        case 1: return launch_rollout_variant<MODEL, true, false, false>(h, variant, d_u_nom, d_noise, d_cost, st);
+        case 2: return launch_rollout_variant<MODEL, false, HAS_ARM, false>(h, variant, d_u_nom, d_noise, d_cost, st);
+        case 3: return launch_rollout_variant<MODEL, true, HAS_ARM, false>(h, variant, d_u_nom, d_noise, d_cost, st);
+        case 4: return launch_rollout_variant<MODEL, false, false, HAS_ARM>(h, variant, d_u_nom, d_noise, d_cost, st);
+        case 5: return launch_rollout_variant<MODEL, true, false, HAS_ARM>(h, variant, d_u_nom, d_noise, d_cost, st);
+        case 6: return launch_rollout_variant<MODEL, false, HAS_ARM, HAS_ARM>(h, variant, d_u_nom, d_noise, d_cost, st);
+        default: return launch_rollout_variant<MODEL, true, HAS_ARM, HAS_ARM>(h, variant, d_u_nom, d_noise, d_cost, st);
     }
 }
 
@@ -521,6 +541,11 @@ mppi_status_t mppi_create(const mppi_config_t *cfg, mppi_handle_t *out)
     h->nu = nu;
     h->X.world = h->X_off.world = 1;
     h->num_sms = prop.multiProcessorCount;
+    {
+        // packed path once one sample per thread would already give >= 4 warps per scheduler
+        const char *ev = std::getenv("MPPI_VEC2_MIN_SAMPLES");
+        h->vec2_min_samples = ev ? std::atoi(ev) : h->num_sms * 4 * 4 * 32;
+    }
     StepParams &P = h->P;
     P.K = cfg->n_samples; P.T = cfg->n_horizon; P.nu = nu; P.nch = (nu + 3) / 4;
     P.k_offset = cfg->k_offset;

@@ -10,6 +10,7 @@
 
 #include "mppi_b200.h"
 #include "fk_tables_gen.cuh"
+#include "mppi_vec.cuh"
 
 namespace mppi {
 
@@ -103,12 +104,6 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, const uint32_t *rk)
 
 // u1 = 2 - [1,2) in (0,1];  theta = ([1,2) - 1.5) * 2pi in [-pi,pi);  MUFU lg2 / sqrt / sin / cos.
 // r = sqrt(-2 ln u1) = sqrt(lg2(u1) * (-2 ln 2)); sqrt.approx maps 0 -> 0 (u1 == 1).
-__device__ __forceinline__ float sqrt_approx(float x)
-{
-    float y;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
 __device__ __forceinline__ void box_muller(uint32_t x, uint32_t y, float &n0, float &n1)
 {
     const float u1 = __fsub_rn(2.0f, __uint_as_float(0x3f800000u | (x >> 9)));
@@ -155,17 +150,20 @@ __host__ __device__ __forceinline__ float decode_ordered(int32_t e)
 constexpr int32_t kRhoInit = 0x7fffffff;
 
 // ------------------------------------------------------------------------------------------
-// Small rigid-body helpers (row-major 3x3).
+// Rigid-body helpers (row-major 3x3), generic over the value type V (float: one sample per thread,
+// f2: two samples per thread in packed FP32x2 -- see mppi_vec.cuh).
 // ------------------------------------------------------------------------------------------
 // Rz(yaw) Ry(pitch) Rx(roll)  (S/robot/transformation_matrix.py:4-25, :148-187; S/drone.py:126-154)
-__device__ __forceinline__ void rpy_matrix(float sr, float cr, float sp, float cp, float sy, float cy, float R[9])
+template <class V>
+__device__ __forceinline__ void rpy_matrix(V sr, V cr, V sp, V cp, V sy, V cy, V R[9])
 {
-    R[0] = cy * cp; R[1] = cy * sp * sr - sy * cr; R[2] = cy * sp * cr + sy * sr;
-    R[3] = sy * cp; R[4] = sy * sp * sr + cy * cr; R[5] = sy * sp * cr - cy * sr;
-    R[6] = -sp;     R[7] = cp * sr;                R[8] = cp * cr;
+    const V cysp = vmul(cy, sp), sysp = vmul(sy, sp);
+    R[0] = vmul(cy, cp); R[1] = vfma(cysp, sr, vneg(vmul(sy, cr))); R[2] = vfma(cysp, cr, vmul(sy, sr));
+    R[3] = vmul(sy, cp); R[4] = vfma(sysp, sr, vmul(cy, cr));       R[5] = vfma(sysp, cr, vneg(vmul(cy, sr)));
+    R[6] = vneg(sp);     R[7] = vmul(cp, sr);                       R[8] = vmul(cp, cr);
 }
 
-// xyz + quaternion xyzw, NOT normalised (S/robot/urdf_fk.py:30-55).
+// xyz + quaternion xyzw, NOT normalised (S/robot/urdf_fk.py:30-55).  The base pose is uniform.
 __device__ __forceinline__ void quat_matrix(const float *b, float R[9])
 {
     const float qx = b[3], qy = b[4], qz = b[5], qw = b[6];
@@ -174,140 +172,143 @@ __device__ __forceinline__ void quat_matrix(const float *b, float R[9])
     R[6] = 2.0f * qx * qz - 2.0f * qy * qw; R[7] = 2.0f * qy * qz + 2.0f * qx * qw; R[8] = 1.0f - 2.0f * qx * qx - 2.0f * qy * qy;
 }
 
-// (R,p) <- (R Cr, p + R Ct)
-__device__ __forceinline__ void compose_const(float R[9], float p[3], const float *Cr, const float *Ct)
+// (R,p) <- (R Cr, p + R Ct), constants from the kernel parameter block (any chain)
+template <class V>
+__device__ __forceinline__ void compose_const(V R[9], V p[3], const float *Cr, const float *Ct)
 {
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-        const float a = R[3 * r], b = R[3 * r + 1], c = R[3 * r + 2];
-        p[r] = fmaf(a, Ct[0], fmaf(b, Ct[1], fmaf(c, Ct[2], p[r])));
-        R[3 * r]     = fmaf(a, Cr[0], fmaf(b, Cr[3], c * Cr[6]));
-        R[3 * r + 1] = fmaf(a, Cr[1], fmaf(b, Cr[4], c * Cr[7]));
-        R[3 * r + 2] = fmaf(a, Cr[2], fmaf(b, Cr[5], c * Cr[8]));
+        const V a = R[3 * r], b = R[3 * r + 1], c = R[3 * r + 2];
+        p[r] = vfma(a, V(Ct[0]), vfma(b, V(Ct[1]), vfma(c, V(Ct[2]), p[r])));
+        R[3 * r]     = vfma(a, V(Cr[0]), vfma(b, V(Cr[3]), vmul(c, V(Cr[6]))));
+        R[3 * r + 1] = vfma(a, V(Cr[1]), vfma(b, V(Cr[4]), vmul(c, V(Cr[7]))));
+        R[3 * r + 2] = vfma(a, V(Cr[2]), vfma(b, V(Cr[5]), vmul(c, V(Cr[8]))));
     }
 }
 
 // sin and cos of x to ~1 ulp (max abs error 1.4e-7) without the libm slow path: reduce by pi
 // (2-term Cody-Waite under FMA) to r in [-pi/2, pi/2], near-minimax polynomials in r^2, one sign
 // flip.  Valid for |x| < ~1e4 (joint and Euler angles here stay within a few turns).
-__device__ __forceinline__ void sincos_pi(float x, float &s, float &c)
+template <class V>
+__device__ __forceinline__ void sincos_pi(V x, V &s, V &c)
 {
-    const float kf = fmaf(x, 0.318309886183790672f, 12582912.0f);       // 1.5 * 2^23: rint in the low bits
-    const int n = __float_as_int(kf);
-    const float k = kf - 12582912.0f;
-    float r = fmaf(k, -3.14159274101257324f, x);
-    r = fmaf(k, 8.742278000372485e-8f, r);
-    const float z = r * r;
-    float ps = fmaf(2.634697921166662e-06f, z, -0.00019822725153062493f);
-    ps = fmaf(ps, z, 0.008333242498338223f);
-    ps = fmaf(ps, z, -0.1666666567325592f);
-    float pc = fmaf(-2.62966580066859e-07f, z, 2.4774544726824388e-05f);
-    pc = fmaf(pc, z, -0.0013888651737943292f);
-    pc = fmaf(pc, z, 0.0416666604578495f);
-    pc = fmaf(pc, z, -0.5f);
-    const float sr = fmaf(ps, z * r, r);
-    const float cr = fmaf(pc, z, 1.0f);
-    const int flip = n << 31;                                             // odd multiple of pi: negate both
-    s = __int_as_float(__float_as_int(sr) ^ flip);
-    c = __int_as_float(__float_as_int(cr) ^ flip);
+    const V kf = vfma(x, V(0.318309886183790672f), V(12582912.0f));      // 1.5 * 2^23: rint in the low bits
+    const auto n = vbits(kf);
+    const V k = vadd(kf, V(-12582912.0f));
+    V r = vfma(k, V(-3.14159274101257324f), x);
+    r = vfma(k, V(8.742278000372485e-8f), r);
+    const V z = vmul(r, r);
+    V ps = vfma(V(2.634697921166662e-06f), z, V(-0.00019822725153062493f));
+    ps = vfma(ps, z, V(0.008333242498338223f));
+    ps = vfma(ps, z, V(-0.1666666567325592f));
+    V pc = vfma(V(-2.62966580066859e-07f), z, V(2.4774544726824388e-05f));
+    pc = vfma(pc, z, V(-0.0013888651737943292f));
+    pc = vfma(pc, z, V(0.0416666604578495f));
+    pc = vfma(pc, z, V(-0.5f));
+    const V sr = vfma(ps, vmul(z, r), r);
+    const V cr = vfma(pc, z, V(1.0f));
+    const auto flip = vshl31(n);                                          // odd multiple of pi: negate both
+    s = vxor(sr, flip);
+    c = vxor(cr, flip);
 }
 
-// Branch-free atan2 / asin / approximate reciprocal and square root for the pose cost.  Accuracy
-// (max abs error vs double, measured in tools/fit_math.py): atan2 1.5e-7 + 2-ulp quotient, asin 1.6e-7;
-// rcp / sqrt are the MUFU approximations (<= 2 ulp).  The reference's own float32 atan2/asin carry
-// ~1e-7; these terms enter the cost multiplied by 30 against a float32 ulp of S of 1.2e-4.
-__device__ __forceinline__ float rcp_approx(float x)
+// Branch-free atan2 / asin for the pose cost.  Accuracy (max abs error vs double): atan2 1.5e-7 plus the
+// 2-ulp MUFU quotient, asin 1.6e-7; rcp / sqrt are the MUFU approximations (<= 2 ulp).  The reference's
+// own float32 atan2/asin carry ~1e-7; these terms enter the cost multiplied by 30 against a float32
+// ulp of S of 1.2e-4.
+template <class V>
+__device__ __forceinline__ V atan2_poly(V y, V x)
 {
-    float y;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
+    const V ax = vabs(x), ay = vabs(y);
+    const V mx = vmax(vmax(ax, ay), V(1e-37f)), mn = vmin(ax, ay);         // atan2(0, 0) -> 0
+    const V t = vmul(mn, vrcp(mx));
+    const V z = vmul(t, t);
+    V p = vfma(V(0.003962172195315361f), z, V(-0.02036452107131481f));
+    p = vfma(p, z, V(0.049385011196136475f));
+    p = vfma(p, z, V(-0.0804230123758316f));
+    p = vfma(p, z, V(0.1087741032242775f));
+    p = vfma(p, z, V(-0.14259037375450134f));
+    p = vfma(p, z, V(0.19998809695243835f));
+    p = vfma(p, z, V(-0.33333325386047363f));
+    V a = vfma(vmul(p, z), t, t);
+    a = vsel(vgt(ay, ax), vsub(V(1.57079632679489662f), a), a);
+    a = vsel(vlt(x, V(0.0f)), vsub(V(3.14159265358979324f), a), a);
+    return vcopysign(a, y);
 }
-__device__ __forceinline__ float atan2_poly(float y, float x)
+template <class V>
+__device__ __forceinline__ V asin_poly(V x)
 {
-    const float ax = fabsf(x), ay = fabsf(y);
-    const float mx = fmaxf(fmaxf(ax, ay), 1e-37f), mn = fminf(ax, ay);      // atan2(0, 0) -> 0
-    const float t = mn * rcp_approx(mx);
-    const float z = t * t;
-    float p = fmaf(0.003962172195315361f, z, -0.02036452107131481f);
-    p = fmaf(p, z, 0.049385011196136475f);
-    p = fmaf(p, z, -0.0804230123758316f);
-    p = fmaf(p, z, 0.1087741032242775f);
-    p = fmaf(p, z, -0.14259037375450134f);
-    p = fmaf(p, z, 0.19998809695243835f);
-    p = fmaf(p, z, -0.33333325386047363f);
-    float a = fmaf(p * z, t, t);
-    a = (ay > ax) ? 1.57079632679489662f - a : a;
-    a = (x < 0.0f) ? 3.14159265358979324f - a : a;
-    return copysignf(a, y);
-}
-__device__ __forceinline__ float asin_poly(float x)
-{
-    const float a = fabsf(x);
-    const bool big = a > 0.5f;
-    const float z = big ? fmaf(a, -0.5f, 0.5f) : a * a;
-    const float s = big ? sqrt_approx(z) : a;
-    float p = fmaf(0.038206253200769424f, z, 0.02649438939988613f);
-    p = fmaf(p, z, 0.045010678470134735f);
-    p = fmaf(p, z, 0.07498808950185776f);
-    p = fmaf(p, z, 0.16666673123836517f);
-    float r = fmaf(p * z, s, s);
-    r = big ? fmaf(-2.0f, r, 1.57079632679489662f) : r;
-    return copysignf(r, x);
+    const V a = vabs(x);
+    const auto big = vgt(a, V(0.5f));
+    const V z = vsel(big, vfma(a, V(-0.5f), V(0.5f)), vmul(a, a));
+    const V s = vsel(big, vsqrt(z), a);
+    V p = vfma(V(0.038206253200769424f), z, V(0.02649438939988613f));
+    p = vfma(p, z, V(0.045010678470134735f));
+    p = vfma(p, z, V(0.07498808950185776f));
+    p = vfma(p, z, V(0.16666673123836517f));
+    V r = vfma(vmul(p, z), s, s);
+    r = vsel(big, vfma(V(-2.0f), r, V(1.57079632679489662f)), r);
+    return vcopysign(r, x);
 }
 
 // ---- FK with compile-time constants (tables from tools/gen_fk_tables.py) -------------------
 // acc (+)= x * k where k is a constant expression: zero terms vanish, +-1 become add / sub.
-#define MPPI_CTERM(acc, have, x, k)                                                                   \
-    if constexpr ((k) != 0.0f) {                                                                      \
-        if constexpr (!(have)) acc = ((k) == 1.0f) ? (x) : ((k) == -1.0f) ? -(x) : (x) * (k);         \
-        else acc = ((k) == 1.0f) ? acc + (x) : ((k) == -1.0f) ? acc - (x) : fmaf((x), (k), acc);      \
+#define MPPI_CTERM(acc, have, x, k)                                                                              \
+    if constexpr ((k) != 0.0f) {                                                                                 \
+        if constexpr (!(have)) acc = ((k) == 1.0f) ? (x) : ((k) == -1.0f) ? vneg(x) : vmul((x), V(k));           \
+        else acc = ((k) == 1.0f) ? vadd(acc, (x)) : ((k) == -1.0f) ? vsub(acc, (x)) : vfma((x), V(k), acc);      \
     }
 
-template <class Tab, int J, int COL>
-__device__ __forceinline__ float tab_rot_col(float a, float b, float c)
+template <class Tab, int J, int COL, class V>
+__device__ __forceinline__ V tab_rot_col(V a, V b, V c)
 {
     constexpr float k0 = Tab::R[J][COL], k1 = Tab::R[J][3 + COL], k2 = Tab::R[J][6 + COL];
     constexpr bool h1 = (k0 != 0.0f), h2 = h1 || (k1 != 0.0f);
-    float acc = 0.0f;
+    V acc = V(0.0f);
     MPPI_CTERM(acc, false, a, k0)
     MPPI_CTERM(acc, h1, b, k1)
     MPPI_CTERM(acc, h2, c, k2)
     return acc;
 }
-template <class Tab, int J>
-__device__ __forceinline__ float tab_trans(float a, float b, float c, float p)
+template <class Tab, int J, class V>
+__device__ __forceinline__ V tab_trans(V a, V b, V c, V p)
 {
     constexpr float k0 = Tab::t[J][0], k1 = Tab::t[J][1], k2 = Tab::t[J][2];
-    float acc = p;
+    V acc = p;
     MPPI_CTERM(acc, true, a, k0)
     MPPI_CTERM(acc, true, b, k1)
     MPPI_CTERM(acc, true, c, k2)
     return acc;
 }
 // (R,p) <- (R C_J.R, p + R C_J.t) with C_J from the table
-template <class Tab, int J>
-__device__ __forceinline__ void compose_tab(float R[9], float p[3])
+template <class Tab, int J, class V>
+__device__ __forceinline__ void compose_tab(V R[9], V p[3])
 {
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-        const float a = R[3 * r], b = R[3 * r + 1], c = R[3 * r + 2];
+        const V a = R[3 * r], b = R[3 * r + 1], c = R[3 * r + 2];
         p[r] = tab_trans<Tab, J>(a, b, c, p[r]);
         R[3 * r] = tab_rot_col<Tab, J, 0>(a, b, c);
         R[3 * r + 1] = tab_rot_col<Tab, J, 1>(a, b, c);
         R[3 * r + 2] = tab_rot_col<Tab, J, 2>(a, b, c);
     }
 }
-template <class Tab, int J = 0>
-__device__ __forceinline__ void fk_tab(const float *cq, const float *sq, float R[9], float p[3])
+// R <- R Rz(q): rotate columns 0/1 (S/robot/transformation_matrix.py:58-95 for a z axis)
+template <class V>
+__device__ __forceinline__ void rotate_z(V R[9], V c, V s)
+{
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const V a = R[3 * r], b = R[3 * r + 1];
+        R[3 * r] = vfma(c, a, vmul(s, b));
+        R[3 * r + 1] = vfma(c, b, vneg(vmul(s, a)));
+    }
+}
+template <class Tab, int J = 0, class V>
+__device__ __forceinline__ void fk_tab(const V *cq, const V *sq, V R[9], V p[3])
 {
     if constexpr (J < Tab::kJoints) {
-        const float c = cq[J], s = sq[J];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            const float a = R[3 * r], b = R[3 * r + 1];
-            R[3 * r] = fmaf(c, a, s * b);
-            R[3 * r + 1] = fmaf(c, b, -s * a);
-        }
+        rotate_z(R, cq[J], sq[J]);
         compose_tab<Tab, J + 1>(R, p);
         fk_tab<Tab, J + 1>(cq, sq, R, p);
     }
@@ -316,85 +317,87 @@ __device__ __forceinline__ void fk_tab(const float *cq, const float *sq, float R
 // Forward kinematics of the folded chain; on entry (R,p) = world pose of the chain root
 // already composed with C0.  S/robot/urdfparser.py:133-161 + transformation_matrix.py:58-95
 // collapse to "rotate columns 0/1 by q, then apply the next constant transform".
-template <int NJ>
-__device__ __forceinline__ void fk_chain(const ChainDev &ch, const float *cq, const float *sq, float R[9], float p[3])
+template <int NJ, class V>
+__device__ __forceinline__ void fk_chain(const ChainDev &ch, const V *cq, const V *sq, V R[9], V p[3])
 {
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
-        const float c = cq[j], s = sq[j];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            const float a = R[3 * r], b = R[3 * r + 1];
-            R[3 * r]     = fmaf(c, a, s * b);
-            R[3 * r + 1] = fmaf(c, b, -s * a);
-        }
+        rotate_z(R, cq[j], sq[j]);
         if (j + 1 < NJ || !ch.last_identity) compose_const(R, p, ch.R[j + 1], ch.t[j + 1]);
     }
 }
 
 // ||p - p*||_2 and ||euler_ZYX(R^T R*)||_2  (S/cost/pose_cost.py:24-63,
 // S/utils/rotation_conversions.py:277-319; inv(R) of a rotation is its transpose).
-__device__ __forceinline__ void pose_terms(const float R[9], const float p[3], const DynBlock &D, float &pos, float &ori)
+template <class V>
+__device__ __forceinline__ void pose_terms(const V R[9], const V p[3], const DynBlock &D, V &pos, V &ori)
 {
     const float *Tg = D.target_R;
-    const float dx = p[0] - D.target_pos[0], dy = p[1] - D.target_pos[1], dz = p[2] - D.target_pos[2];
-    pos = sqrt_approx(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
-    const float d00 = fmaf(R[0], Tg[0], fmaf(R[3], Tg[3], R[6] * Tg[6]));
-    const float d10 = fmaf(R[1], Tg[0], fmaf(R[4], Tg[3], R[7] * Tg[6]));
-    const float d20 = fmaf(R[2], Tg[0], fmaf(R[5], Tg[3], R[8] * Tg[6]));
-    const float d21 = fmaf(R[2], Tg[1], fmaf(R[5], Tg[4], R[8] * Tg[7]));
-    const float d22 = fmaf(R[2], Tg[2], fmaf(R[5], Tg[5], R[8] * Tg[8]));
-    const float e0 = atan2_poly(d10, d00);
-    const float e1 = asin_poly(fminf(fmaxf(-d20, -1.0f), 1.0f));
-    const float e2 = atan2_poly(d21, d22);
-    ori = sqrt_approx(fmaf(e0, e0, fmaf(e1, e1, e2 * e2)));
+    const V dx = vsub(p[0], V(D.target_pos[0])), dy = vsub(p[1], V(D.target_pos[1])), dz = vsub(p[2], V(D.target_pos[2]));
+    pos = vsqrt(vfma(dx, dx, vfma(dy, dy, vmul(dz, dz))));
+    const V d00 = vfma(R[0], V(Tg[0]), vfma(R[3], V(Tg[3]), vmul(R[6], V(Tg[6]))));
+    const V d10 = vfma(R[1], V(Tg[0]), vfma(R[4], V(Tg[3]), vmul(R[7], V(Tg[6]))));
+    const V d20 = vfma(R[2], V(Tg[0]), vfma(R[5], V(Tg[3]), vmul(R[8], V(Tg[6]))));
+    const V d21 = vfma(R[2], V(Tg[1]), vfma(R[5], V(Tg[4]), vmul(R[8], V(Tg[7]))));
+    const V d22 = vfma(R[2], V(Tg[2]), vfma(R[5], V(Tg[5]), vmul(R[8], V(Tg[8]))));
+    const V e0 = atan2_poly(d10, d00);
+    const V e1 = asin_poly(vmin(vmax(vneg(d20), V(-1.0f)), V(1.0f)));
+    const V e2 = atan2_poly(d21, d22);
+    ori = vsqrt(vfma(e0, e0, vfma(e1, e1, vmul(e2, e2))));
 }
 
 // Quadrotor rigid body, one step (restated from the dead draft S/mppi_solver/drone_mppi.py:57-83;
 // rules fixed in DESIGN.md).  (s*, c*) are sin/cos of the CURRENT attitude on entry and of the
 // NEW attitude on exit, so the whole-body FK reuses them.
+template <class V>
 struct QuadState {
-    float p[3], rpy[3], v[3], w[3];
-    float sphi, cphi, sth, cth, spsi, cpsi;
+    V p[3], rpy[3], v[3], w[3];
+    V sphi, cphi, sth, cth, spsi, cpsi;
 };
 
-__device__ __forceinline__ float wrap_pi(float a)
+// a - 2 pi rint(a / 2 pi): exact identity for |a| < pi, so it is applied unconditionally
+// (the draft wraps with atan2(sin, cos), drone_mppi.py:77).
+template <class V>
+__device__ __forceinline__ V wrap_pi(V a)
 {
-    return (fabsf(a) > kPi) ? fmaf(-kTwoPi, rintf(a * kInvTwoPi), a) : a;
+    const V k = vadd(vfma(a, V(kInvTwoPi), V(12582912.0f)), V(-12582912.0f));
+    return vfma(V(-kTwoPi), k, a);
 }
 
-__device__ __forceinline__ void quad_advance(QuadState &s, float F, float tx, float ty, float tz,
-                                             float dt, const float *qp)
+template <class V>
+__device__ __forceinline__ void quad_advance(QuadState<V> &s, V F, V tx, V ty, V tz, float dt, const float *qp)
 {
     const float inv_m = rcp_approx(qp[0]), kd = qp[4], gz = qp[5];
-    const float inv_cth = rcp_approx(s.cth);
-    const float tth = s.sth * inv_cth;
-    const float r02 = s.cpsi * s.sth * s.cphi + s.spsi * s.sphi;
-    const float r12 = s.spsi * s.sth * s.cphi - s.cpsi * s.sphi;
-    const float r22 = s.cth * s.cphi;
-    s.w[0] = fmaf(dt, qp[1] * tx, s.w[0]);
-    s.w[1] = fmaf(dt, qp[2] * ty, s.w[1]);
-    s.w[2] = fmaf(dt, qp[3] * tz, s.w[2]);
-    const float dphi = s.w[0] + s.sphi * tth * s.w[1] + s.cphi * tth * s.w[2];
-    const float dth = s.cphi * s.w[1] - s.sphi * s.w[2];
-    const float dpsi = (s.sphi * inv_cth) * s.w[1] + (s.cphi * inv_cth) * s.w[2];
-    const float ax = (r02 * F - kd * s.v[0]) * inv_m;
-    const float ay = (r12 * F - kd * s.v[1]) * inv_m;
-    const float az = gz + (r22 * F - kd * s.v[2]) * inv_m;
-    s.rpy[0] = wrap_pi(fmaf(dt, dphi, s.rpy[0]));
-    s.rpy[1] = wrap_pi(fmaf(dt, dth, s.rpy[1]));
-    s.rpy[2] = wrap_pi(fmaf(dt, dpsi, s.rpy[2]));
-    s.v[0] = fmaf(dt, ax, s.v[0]); s.v[1] = fmaf(dt, ay, s.v[1]); s.v[2] = fmaf(dt, az, s.v[2]);
-    s.p[0] = fmaf(dt, s.v[0], s.p[0]); s.p[1] = fmaf(dt, s.v[1], s.p[1]); s.p[2] = fmaf(dt, s.v[2], s.p[2]);
+    const V inv_cth = vrcp(s.cth);
+    const V tth = vmul(s.sth, inv_cth);
+    const V cs = vmul(s.cpsi, s.sth), ss = vmul(s.spsi, s.sth);
+    const V r02 = vfma(cs, s.cphi, vmul(s.spsi, s.sphi));
+    const V r12 = vfma(ss, s.cphi, vneg(vmul(s.cpsi, s.sphi)));
+    const V r22 = vmul(s.cth, s.cphi);
+    s.w[0] = vfma(V(dt * qp[1]), tx, s.w[0]);
+    s.w[1] = vfma(V(dt * qp[2]), ty, s.w[1]);
+    s.w[2] = vfma(V(dt * qp[3]), tz, s.w[2]);
+    const V dphi = vfma(vmul(s.cphi, tth), s.w[2], vfma(vmul(s.sphi, tth), s.w[1], s.w[0]));
+    const V dth = vfma(s.cphi, s.w[1], vneg(vmul(s.sphi, s.w[2])));
+    const V dpsi = vfma(vmul(s.cphi, inv_cth), s.w[2], vmul(vmul(s.sphi, inv_cth), s.w[1]));
+    const V ax = vmul(vfma(r02, F, vneg(vmul(V(kd), s.v[0]))), V(inv_m));
+    const V ay = vmul(vfma(r12, F, vneg(vmul(V(kd), s.v[1]))), V(inv_m));
+    const V az = vfma(vfma(r22, F, vneg(vmul(V(kd), s.v[2]))), V(inv_m), V(gz));
+    s.rpy[0] = wrap_pi(vfma(V(dt), dphi, s.rpy[0]));
+    s.rpy[1] = wrap_pi(vfma(V(dt), dth, s.rpy[1]));
+    s.rpy[2] = wrap_pi(vfma(V(dt), dpsi, s.rpy[2]));
+    s.v[0] = vfma(V(dt), ax, s.v[0]); s.v[1] = vfma(V(dt), ay, s.v[1]); s.v[2] = vfma(V(dt), az, s.v[2]);
+    s.p[0] = vfma(V(dt), s.v[0], s.p[0]); s.p[1] = vfma(V(dt), s.v[1], s.p[1]); s.p[2] = vfma(V(dt), s.v[2], s.p[2]);
     sincos_pi(s.rpy[0], s.sphi, s.cphi);
     sincos_pi(s.rpy[1], s.sth, s.cth);
     sincos_pi(s.rpy[2], s.spsi, s.cpsi);
 }
 
-__device__ __forceinline__ void quad_load(QuadState &s, const float *st)
+template <class V>
+__device__ __forceinline__ void quad_load(QuadState<V> &s, const float *st)
 {
 #pragma unroll
-    for (int i = 0; i < 3; ++i) { s.p[i] = st[i]; s.rpy[i] = st[3 + i]; s.v[i] = st[6 + i]; s.w[i] = st[9 + i]; }
+    for (int i = 0; i < 3; ++i) { s.p[i] = V(st[i]); s.rpy[i] = V(st[3 + i]); s.v[i] = V(st[6 + i]); s.w[i] = V(st[9 + i]); }
     sincos_pi(s.rpy[0], s.sphi, s.cphi);
     sincos_pi(s.rpy[1], s.sth, s.cth);
     sincos_pi(s.rpy[2], s.spsi, s.cpsi);

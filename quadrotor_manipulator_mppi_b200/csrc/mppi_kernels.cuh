@@ -14,23 +14,30 @@
 
 namespace mppi {
 
-constexpr int kRolloutThreads = 128;
+constexpr int kRolloutThreads = 128;       // one sample per thread
+constexpr int kRolloutThreads2 = 64;       // two samples per thread (packed f32x2): finer blocks for wave balance
 constexpr int kWeightTile = 2048;       // samples whose weights are staged in smem at a time
 
 // ------------------------------------------------------------------------------------------
 // K2: fused noise + rollout + FK + cost.
 // Replaces S/mppi_solver/mppi.py:129-140 (sampling, get_sample_joint, compute_fk_gpu,
 // CostManager.compute_all_cost) and S/mppi_solver/drone_mppi.py:143-151.
+//
+// V = float: one sample per thread (small K: more threads, latency-bound regime).
+// V = f2   : two samples per thread, all FP32 arithmetic in packed FFMA2/FADD2/FMUL2 -- the kernel is
+//            issue-bound and packed ops halve the FP32 issue slots.  Lane 0 = sample k, lane 1 = sample
+//            k + blockDim.x (so global loads / stores of each lane stay coalesced).
 // ------------------------------------------------------------------------------------------
-template <int MODEL, bool PHILOX, bool BAKED, bool EXTRA = false>
-__global__ void __launch_bounds__(kRolloutThreads)
+template <int MODEL, bool PHILOX, bool BAKED, bool EXTRA, class V, int THREADS>
+__global__ void __launch_bounds__(THREADS, (Lanes<V>::n == 2) ? 7 : 1)
 rollout_cost_kernel(const __grid_constant__ StepParams P, const __grid_constant__ DynBlock D,
                     const float *__restrict__ u_nom, const float *__restrict__ noise,
                     float *__restrict__ cost_out, int32_t *__restrict__ rho_enc,
-                    const float *__restrict__ q_traj = nullptr)
+                    const float *__restrict__ q_traj)
 {
     constexpr int NU = ModelNu<MODEL>::value;
     constexpr int NCH = (NU + 3) / 4;
+    constexpr int NL = Lanes<V>::n;
     constexpr bool HAS_ARM = (MODEL == MPPI_MODEL_ARM7 || MODEL == MPPI_MODEL_WB11);
     constexpr bool HAS_QUAD = (MODEL == MPPI_MODEL_QUAD4 || MODEL == MPPI_MODEL_WB11);
     constexpr int ARM0 = (MODEL == MPPI_MODEL_WB11) ? 4 : 0;     // first arm input
@@ -38,7 +45,7 @@ rollout_cost_kernel(const __grid_constant__ StepParams P, const __grid_constant_
 
     extern __shared__ __align__(16) float s_unom[];              // [T][NU]
     __shared__ __align__(8) uint64_t s_bar;
-    __shared__ float s_wmin[kRolloutThreads / 32];
+    __shared__ float s_wmin[THREADS / 32];
 
     // ---- stage the nominal control sequence: one TMA bulk copy + scalar tail
     const int n_u = P.T * NU;
@@ -61,22 +68,29 @@ rollout_cost_kernel(const __grid_constant__ StepParams P, const __grid_constant_
     }
     __syncthreads();
 
-    const int k_raw = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = k_raw < P.K;
-    const int k = active ? k_raw : P.K - 1;
-    const uint32_t kg = static_cast<uint32_t>(P.k_offset + k);
+    // ---- the samples of this thread
+    int ks[NL];
+    bool active[NL];
+    uint32_t kg[NL];
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+        const int k_raw = (blockIdx.x * NL + l) * THREADS + threadIdx.x;
+        active[l] = k_raw < P.K;
+        ks[l] = active[l] ? k_raw : P.K - 1;
+        kg[l] = static_cast<uint32_t>(P.k_offset + ks[l]);
+    }
 
     // ---- per-sample state in registers
-    float cum_v[HAS_ARM ? 7 : 3], cum_q[HAS_ARM ? 7 : 3], vprev[HAS_ARM ? 7 : 3];
-    QuadState qs;
-    float R0[9], p0[3];          // chain root pose composed with C0 (loop-invariant for ARM7)
+    V cum_v[HAS_ARM ? 7 : 3], cum_q[HAS_ARM ? 7 : 3], vprev[HAS_ARM ? 7 : 3];
+    QuadState<V> qs;
+    float R0[9], p0[3];          // chain root pose composed with C0 (uniform and loop-invariant for ARM7)
     if constexpr (MODEL == MPPI_MODEL_DRONE3) {
 #pragma unroll
-        for (int i = 0; i < 3; ++i) { cum_v[i] = 0.f; cum_q[i] = 0.f; vprev[i] = D.state[3 + i]; }
+        for (int i = 0; i < 3; ++i) { cum_v[i] = V(0.f); cum_q[i] = V(0.f); vprev[i] = V(D.state[3 + i]); }
     }
     if constexpr (HAS_ARM) {
 #pragma unroll
-        for (int i = 0; i < 7; ++i) { cum_v[i] = 0.f; cum_q[i] = 0.f; vprev[i] = D.state[QOFF + 7 + i]; }
+        for (int i = 0; i < 7; ++i) { cum_v[i] = V(0.f); cum_q[i] = V(0.f); vprev[i] = V(D.state[QOFF + 7 + i]); }
     }
     if constexpr (MODEL == MPPI_MODEL_ARM7) {
         quat_matrix(&D.state[14], R0);                       // base xyz+quat -> B (S/robot/urdf_fk.py:30-55)
@@ -86,98 +100,103 @@ rollout_cost_kernel(const __grid_constant__ StepParams P, const __grid_constant_
     }
     if constexpr (HAS_QUAD) quad_load(qs, D.state);
 
-    float S = 0.f, comp = 0.f;       // Kahan-compensated running cost
-    float x_cov = 0.f, x_cen = 0.f, x_trk = 0.f, x_act = 0.f, x_lim = 0.f, gpow = 1.0f;   // EXTRA cost terms, gamma^t
-    float Sd = 0.f;                  // squared-distance stage cost (drone / quad part)
-    float term_d = 0.f;
+    V S = V(0.f), comp = V(0.f);       // Kahan-compensated running cost
+    V x_cov = V(0.f), x_cen = V(0.f), x_trk = V(0.f), x_act = V(0.f), x_lim = V(0.f);   // EXTRA cost terms
+    float gpow = 1.0f;                 // gamma^t
+    V Sd = V(0.f);                     // squared-distance stage cost (drone / quad part)
+    V term_d = V(0.f);
 
     for (int t = 0; t < P.T; ++t) {
         // ---- controls of this step: v = u + noise  (S/mppi_solver/mppi.py:130)
-        float a[NU];
-        if constexpr (PHILOX) {
+        V a[NU];
 #pragma unroll
-            for (int c = 0; c < NCH; ++c) {
-                float n4[4];
-                normal4(kg, static_cast<uint32_t>(t * NCH + c), D.step_lo, D.step_hi, P.rkeys, n4);
+        for (int l = 0; l < NL; ++l) {
+            if constexpr (PHILOX) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (4 * c + j < NU) a[4 * c + j] = __fmul_rn(P.sigma[4 * c + j], n4[j]);
+                for (int c = 0; c < NCH; ++c) {
+                    float n4[4];
+                    normal4(kg[l], static_cast<uint32_t>(t * NCH + c), D.step_lo, D.step_hi, P.rkeys, n4);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (4 * c + j < NU) set_lane(a[4 * c + j], l, __fmul_rn(P.sigma[4 * c + j], n4[j]));
+                }
+            } else {
+                const float *row = noise + (static_cast<size_t>(t) * P.K + ks[l]) * NU;
+#pragma unroll
+                for (int i = 0; i < NU; ++i) set_lane(a[i], l, __ldg(row + i));
             }
-        } else {
-            const float *row = noise + (static_cast<size_t>(t) * P.K + k) * NU;
-#pragma unroll
-            for (int i = 0; i < NU; ++i) a[i] = __ldg(row + i);
         }
 #pragma unroll
-        for (int i = 0; i < NU; ++i) a[i] = __fadd_rn(s_unom[t * NU + i], a[i]);
+        for (int i = 0; i < NU; ++i) a[i] = vadd_rn(V(s_unom[t * NU + i]), a[i]);
 
         const bool last = (t == P.T - 1);
         if constexpr (EXTRA && HAS_ARM) {
             // covar_cost.py:20-25: u^T Sigma^-1 v per step;  action_cost.py:15-25: gamma^t |v|^2
-            float cov = 0.f, act = 0.f;
+            V cov = V(0.f), act = V(0.f);
 #pragma unroll
             for (int i = 0; i < 7; ++i) {
-                cov = fmaf(s_unom[t * NU + ARM0 + i] * P.inv_sigma_arm[i], a[ARM0 + i], cov);
-                act = fmaf(a[ARM0 + i], a[ARM0 + i], act);
+                cov = vfma(V(s_unom[t * NU + ARM0 + i] * P.inv_sigma_arm[i]), a[ARM0 + i], cov);
+                act = vfma(a[ARM0 + i], a[ARM0 + i], act);
             }
-            x_cov += cov;
-            x_act = fmaf(gpow, act, x_act);
+            x_cov = vadd(x_cov, cov);
+            x_act = vfma(V(gpow), act, x_act);
         }
         if constexpr (MODEL == MPPI_MODEL_DRONE3) {
             // double integrator (S/mppi_solver/drone_mppi.py:46-55) + squared distance (:87-107)
-            float sq = 0.f;
+            V sq = V(0.f);
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
-                const float dq = fmaf(vprev[i], P.dt, (0.5f * a[i]) * P.dt2);
-                cum_v[i] = fmaf(a[i], P.dt, cum_v[i]);
-                vprev[i] = cum_v[i] + D.state[3 + i];
-                cum_q[i] += dq;
-                const float e = (cum_q[i] + D.state[i]) - D.drone_target[i];
-                sq = fmaf(e, e, sq);
+                const V dq = vfma(vprev[i], V(P.dt), vmul(vmul(V(0.5f), a[i]), V(P.dt2)));
+                cum_v[i] = vfma(a[i], V(P.dt), cum_v[i]);
+                vprev[i] = vadd(cum_v[i], V(D.state[3 + i]));
+                cum_q[i] = vadd(cum_q[i], dq);
+                const V e = vsub(vadd(cum_q[i], V(D.state[i])), V(D.drone_target[i]));
+                sq = vfma(e, e, sq);
             }
-            if (last) term_d = sq; else Sd += sq;
+            if (last) term_d = sq; else Sd = vadd(Sd, sq);
         }
         if constexpr (HAS_QUAD) {
             quad_advance(qs, a[0], a[1], a[2], a[3], P.dt, P.quad);
-            const float ex = qs.p[0] - D.drone_target[0], ey = qs.p[1] - D.drone_target[1], ez = qs.p[2] - D.drone_target[2];
-            const float sq = fmaf(ex, ex, fmaf(ey, ey, ez * ez));
-            if (last) term_d = sq; else Sd += sq;
+            const V ex = vsub(qs.p[0], V(D.drone_target[0])), ey = vsub(qs.p[1], V(D.drone_target[1])),
+                    ez = vsub(qs.p[2], V(D.drone_target[2]));
+            const V sq = vfma(ex, ex, vfma(ey, ey, vmul(ez, ez)));
+            if (last) term_d = sq; else Sd = vadd(Sd, sq);
         }
         if constexpr (HAS_ARM) {
             // S/sampling/standard_normal_noise.py:32-50
-            float cq[7], sq[7];
+            V cq[7], sq[7];
 #pragma unroll
             for (int i = 0; i < 7; ++i) {
-                const float ai = a[ARM0 + i];
-                const float dq = fmaf(vprev[i], P.dt, (0.5f * ai) * P.dt2);
-                cum_v[i] = fmaf(ai, P.dt, cum_v[i]);
-                vprev[i] = cum_v[i] + D.state[QOFF + 7 + i];
-                cum_q[i] += dq;
-                sincos_pi(cum_q[i] + D.state[QOFF + i], sq[i], cq[i]);
+                const V ai = a[ARM0 + i];
+                const V dq = vfma(vprev[i], V(P.dt), vmul(vmul(V(0.5f), ai), V(P.dt2)));
+                cum_v[i] = vfma(ai, V(P.dt), cum_v[i]);
+                vprev[i] = vadd(cum_v[i], V(D.state[QOFF + 7 + i]));
+                cum_q[i] = vadd(cum_q[i], dq);
+                sincos_pi(vadd(cum_q[i], V(D.state[QOFF + i])), sq[i], cq[i]);
             }
             if constexpr (EXTRA) {
                 // joint_space_cost.py:18-77: centering, tracking, joint-limit indicator, all discounted by gamma^t
-                float cen = 0.f, trk = 0.f;
-                bool out_of_bounds = false;
+                V cen = V(0.f), trk = V(0.f);
+                auto out_of_bounds = mask_false(typename Lanes<V>::mask{});
 #pragma unroll
                 for (int i = 0; i < 7; ++i) {
-                    const float q = cum_q[i] + D.state[QOFF + i];
-                    const float dc = q - P.q_center[i];
-                    cen = fmaf(dc, dc, cen);
-                    const float dtk = q - (q_traj ? __ldg(q_traj + t * 7 + i) : 0.0f);
-                    trk = fmaf(dtk, dtk, trk);
-                    out_of_bounds = out_of_bounds || (q < P.q_lower[i]) || (q > P.q_upper[i]);
+                    const V q = vadd(cum_q[i], V(D.state[QOFF + i]));
+                    const V dc = vsub(q, V(P.q_center[i]));
+                    cen = vfma(dc, dc, cen);
+                    const V dtk = vsub(q, V(q_traj ? __ldg(q_traj + t * 7 + i) : 0.0f));
+                    trk = vfma(dtk, dtk, trk);
+                    out_of_bounds = vor(out_of_bounds, vor(vlt(q, V(P.q_lower[i])), vgt(q, V(P.q_upper[i]))));
                 }
-                x_cen = fmaf(gpow, cen, x_cen);
-                x_trk = fmaf(gpow, trk, x_trk);
-                if (out_of_bounds) x_lim = fmaf(gpow, P.limit_penalty, x_lim);
+                x_cen = vfma(V(gpow), cen, x_cen);
+                x_trk = vfma(V(gpow), trk, x_trk);
+                x_lim = vsel(out_of_bounds, vfma(V(gpow), V(P.limit_penalty), x_lim), x_lim);
                 gpow *= P.gamma;
             }
-            float R[9], p[3];
+            V R[9], p[3];
             if constexpr (MODEL == MPPI_MODEL_ARM7) {
 #pragma unroll
-                for (int i = 0; i < 9; ++i) R[i] = R0[i];
-                p[0] = p0[0]; p[1] = p0[1]; p[2] = p0[2];
+                for (int i = 0; i < 9; ++i) R[i] = V(R0[i]);
+                p[0] = V(p0[0]); p[1] = V(p0[1]); p[2] = V(p0[2]);
             } else {
                 // moving base T(p_t, rpy_t) (S/robot/transformation_matrix.py:148-187)
                 rpy_matrix(qs.sphi, qs.cphi, qs.sth, qs.cth, qs.spsi, qs.cpsi, R);
@@ -187,40 +206,47 @@ rollout_cost_kernel(const __grid_constant__ StepParams P, const __grid_constant_
             }
             if constexpr (BAKED) fk_tab<FkKinova>(cq, sq, R, p);
             else fk_chain<7>(P.chain, cq, sq, R, p);
-            float pos, ori;
+            V pos, ori;
             pose_terms(R, p, D, pos, ori);
             // S/cost/cost_manager.py:30-33,78-89
-            const float c = last ? fmaf(P.cost_w[2], pos, P.cost_w[3] * ori)
-                                 : fmaf(P.cost_w[0], pos, P.cost_w[1] * ori);
-            const float y = c - comp;
-            const float tS = S + y;
-            comp = (tS - S) - y;
+            const V c = last ? vfma(V(P.cost_w[2]), pos, vmul(V(P.cost_w[3]), ori))
+                             : vfma(V(P.cost_w[0]), pos, vmul(V(P.cost_w[1]), ori));
+            const V y = vsub(c, comp);
+            const V tS = vadd(S, y);
+            comp = vsub(vsub(tS, S), y);
             S = tS;
         }
     }
     if constexpr (MODEL == MPPI_MODEL_DRONE3 || MODEL == MPPI_MODEL_QUAD4) {
-        S = fmaf(Sd, P.cost_w[4], term_d * P.cost_w[5]);
+        S = vfma(Sd, V(P.cost_w[4]), vmul(term_d, V(P.cost_w[5])));
     } else if constexpr (MODEL == MPPI_MODEL_WB11) {
-        S = S + fmaf(Sd, P.cost_w[4], term_d * P.cost_w[5]);
+        S = vadd(S, vfma(Sd, V(P.cost_w[4]), vmul(term_d, V(P.cost_w[5]))));
     }
-
     if constexpr (EXTRA && HAS_ARM) {
         // same order as the commented-out sum, cost_manager.py:83-87
-        if (P.cost_flags & MPPI_COST_COVAR) S += P.covar_scale * x_cov;
-        if (P.cost_flags & MPPI_COST_CENTERING) S += P.centering_weight * x_cen;
-        if (P.cost_flags & MPPI_COST_JOINT_TRAJ) S += P.joint_traj_weight * x_trk;
-        if (P.cost_flags & MPPI_COST_ACTION) S += P.action_weight * x_act;
-        if (P.cost_flags & MPPI_COST_JOINT_LIMIT) S += x_lim;
+        if (P.cost_flags & MPPI_COST_COVAR) S = vfma(V(P.covar_scale), x_cov, S);
+        if (P.cost_flags & MPPI_COST_CENTERING) S = vfma(V(P.centering_weight), x_cen, S);
+        if (P.cost_flags & MPPI_COST_JOINT_TRAJ) S = vfma(V(P.joint_traj_weight), x_trk, S);
+        if (P.cost_flags & MPPI_COST_ACTION) S = vfma(V(P.action_weight), x_act, S);
+        if (P.cost_flags & MPPI_COST_JOINT_LIMIT) S = vadd(S, x_lim);
     }
-    if (active) cost_out[k] = S;
+
+    float m = __int_as_float(0x7f800000);
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+        if (active[l]) {
+            cost_out[ks[l]] = lane(S, l);
+            m = fminf(m, lane(S, l));
+        }
+    }
     // ---- block minimum -> one atomicMin on the order-preserving encoding
-    float m = warp_min(active ? S : __int_as_float(0x7f800000));
+    m = warp_min(m);
     if ((threadIdx.x & 31) == 0) s_wmin[threadIdx.x >> 5] = m;
     __syncthreads();
     if (threadIdx.x == 0) {
         float bm = s_wmin[0];
 #pragma unroll
-        for (int w = 1; w < kRolloutThreads / 32; ++w) bm = fminf(bm, s_wmin[w]);
+        for (int w = 1; w < THREADS / 32; ++w) bm = fminf(bm, s_wmin[w]);
         atomicMin(rho_enc, encode_ordered(bm));
     }
 }
@@ -270,7 +296,7 @@ __device__ void finalize_block(const StepParams &P, const DynBlock &D, const flo
                 out[7 + i] = D.state[7 + i] + un[i] * dt;                                // mppi.py:157
             }
         } else {
-            QuadState qs;
+            QuadState<float> qs;
             quad_load(qs, D.state);
             quad_advance(qs, un[0], un[1], un[2], un[3], dt, P.quad);
             const int o = (MODEL == MPPI_MODEL_WB11) ? MPPI_OUT_BASE : 0;
@@ -285,13 +311,13 @@ __device__ void finalize_block(const StepParams &P, const DynBlock &D, const flo
         if constexpr (MODEL == MPPI_MODEL_ARM7 || MODEL == MPPI_MODEL_WB11) {
             // check_reach (mppi.py:95-120): L1 position error of FK(base, qdes) to the target
             float cq[7], sq[7], R[9], p[3];
-            for (int i = 0; i < 7; ++i) sincosf(out[i], &sq[i], &cq[i]);
+            for (int i = 0; i < 7; ++i) sincos_pi(out[i], sq[i], cq[i]);
             if constexpr (MODEL == MPPI_MODEL_ARM7) {
                 quat_matrix(&D.state[14], R);
                 p[0] = D.state[14]; p[1] = D.state[15]; p[2] = D.state[16];
             } else {
                 float sr, cr, sp, cp, sy, cy;
-                sincosf(D.state[3], &sr, &cr); sincosf(D.state[4], &sp, &cp); sincosf(D.state[5], &sy, &cy);
+                sincos_pi(D.state[3], sr, cr); sincos_pi(D.state[4], sp, cp); sincos_pi(D.state[5], sy, cy);
                 rpy_matrix(sr, cr, sp, cp, sy, cy, R);
                 p[0] = D.state[0]; p[1] = D.state[1]; p[2] = D.state[2];
             }
