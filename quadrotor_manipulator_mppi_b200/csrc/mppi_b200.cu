@@ -165,8 +165,7 @@ struct mppi_ctx {
     P2PParams X_off{};              // world == 1: exchange disabled
     void *p2p_peer[kMaxRanks] = {};
     bool baked_fk = false;          // runtime chain == compile-time FkKinova tables
-    size_t rollout_smem[16] = {};   // tuned dynamic smem per kernel variant (0 = not yet tuned); +8 = two samples per thread
-    int vec2_min_samples = 0;       // K at or above which the packed two-samples-per-thread rollout is used
+    size_t rollout_smem[8] = {};    // tuned dynamic smem per kernel variant (0 = not yet tuned)
     float *d_qtraj = nullptr;       // [T][7] joint reference trajectory (MPPI_COST_JOINT_TRAJ), zeros by default
     cudaStream_t own_stream = nullptr;
     std::string err;
@@ -303,22 +302,11 @@ mppi_status_t launch_rollout_variant(mppi_ctx *h, int variant, const float *d_u_
 {
     constexpr int NU = ModelNu<MODEL>::value;
     const size_t smem = (size_t)h->P.T * NU * sizeof(float);
-    // Two samples per thread (packed FP32x2) once there is enough work to fill the machine with
-    // half as many threads; below that, one sample per thread keeps more warps in flight.
-    const bool vec2 = h->P.K >= h->vec2_min_samples;
-    if (vec2) {
-        auto kernel = rollout_cost_kernel<MODEL, PHILOX, BAKED, EXTRA, f2, kRolloutThreads2>;
-        const int grid = (h->P.K + 2 * kRolloutThreads2 - 1) / (2 * kRolloutThreads2);
-        size_t &tuned = h->rollout_smem[variant + 8];
-        if (tuned == 0) tuned = tuned_rollout_smem(h, kernel, kRolloutThreads2, grid, smem);
-        kernel<<<grid, kRolloutThreads2, tuned, st>>>(h->P, h->dyn, d_u_nom, d_noise, d_cost, h->d_rho, h->d_qtraj);
-    } else {
-        auto kernel = rollout_cost_kernel<MODEL, PHILOX, BAKED, EXTRA, float, kRolloutThreads>;
-        const int grid = (h->P.K + kRolloutThreads - 1) / kRolloutThreads;
-        size_t &tuned = h->rollout_smem[variant];
-        if (tuned == 0) tuned = tuned_rollout_smem(h, kernel, kRolloutThreads, grid, smem);
-        kernel<<<grid, kRolloutThreads, tuned, st>>>(h->P, h->dyn, d_u_nom, d_noise, d_cost, h->d_rho, h->d_qtraj);
-    }
+    auto kernel = rollout_cost_kernel<MODEL, PHILOX, BAKED, EXTRA>;
+    const int grid = (h->P.K + kRolloutThreads - 1) / kRolloutThreads;
+    size_t &tuned = h->rollout_smem[variant];
+    if (tuned == 0) tuned = tuned_rollout_smem(h, kernel, kRolloutThreads, grid, smem);
+    kernel<<<grid, kRolloutThreads, tuned, st>>>(h->P, h->dyn, d_u_nom, d_noise, d_cost, h->d_rho, h->d_qtraj);
     MPPI_CUDA(h, cudaGetLastError());
     return MPPI_OK;
 }
@@ -541,11 +529,6 @@ mppi_status_t mppi_create(const mppi_config_t *cfg, mppi_handle_t *out)
     h->nu = nu;
     h->X.world = h->X_off.world = 1;
     h->num_sms = prop.multiProcessorCount;
-    {
-        // packed path once one sample per thread would already give >= 4 warps per scheduler
-        const char *ev = std::getenv("MPPI_VEC2_MIN_SAMPLES");
-        h->vec2_min_samples = ev ? std::atoi(ev) : h->num_sms * 4 * 4 * 32;
-    }
     StepParams &P = h->P;
     P.K = cfg->n_samples; P.T = cfg->n_horizon; P.nu = nu; P.nch = (nu + 3) / 4;
     P.k_offset = cfg->k_offset;

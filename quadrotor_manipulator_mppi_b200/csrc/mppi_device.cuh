@@ -102,27 +102,41 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, const uint32_t *rk)
     return c;
 }
 
-// u1 = 2 - [1,2) in (0,1];  theta = ([1,2) - 1.5) * 2pi in [-pi,pi);  MUFU lg2 / sqrt / sin / cos.
+// Box-Muller: u1 = 2 - [1,2) in (0,1];  theta = ([1,2) - 1.5) * 2pi in [-pi,pi);  MUFU lg2 / sqrt / sin / cos.
 // r = sqrt(-2 ln u1) = sqrt(lg2(u1) * (-2 ln 2)); sqrt.approx maps 0 -> 0 (u1 == 1).
-__device__ __forceinline__ void box_muller(uint32_t x, uint32_t y, float &n0, float &n1)
+// Two Box-Muller pairs at once in packed FP32x2: lane 0 from (x, y), lane 1 from (z, w).
+//   rc = (r0 cos th0, r1 cos th1) -> normals 0 and 2;   rs = (r0 sin th0, r1 sin th1) -> normals 1 and 3
+__device__ __forceinline__ void box_muller2(uint4 r4, f2 &rc, f2 &rs)
 {
-    const float u1 = __fsub_rn(2.0f, __uint_as_float(0x3f800000u | (x >> 9)));
-    const float th = __fmul_rn(__fsub_rn(__uint_as_float(0x3f800000u | (y >> 9)), 1.5f), kTwoPi);
-    const float r = sqrt_approx(__fmul_rn(__log2f(u1), -1.3862943611198906f));
-    float s, c;
-    __sincosf(th, &s, &c);
-    n0 = __fmul_rn(r, c);
-    n1 = __fmul_rn(r, s);
+    const f2 fu(__uint_as_float(0x3f800000u | (r4.x >> 9)), __uint_as_float(0x3f800000u | (r4.z >> 9)));
+    const f2 ft(__uint_as_float(0x3f800000u | (r4.y >> 9)), __uint_as_float(0x3f800000u | (r4.w >> 9)));
+    const f2 u1 = vadd(f2(2.0f), vneg(fu));
+    const f2 th = vmul(vadd(ft, f2(-1.5f)), f2(kTwoPi));
+    const f2 l2(__log2f(u1.v.x), __log2f(u1.v.y));
+    const f2 a = vmul(l2, f2(-1.3862943611198906f));
+    const f2 r(sqrt_approx(a.v.x), sqrt_approx(a.v.y));
+    float s0, c0, s1, c1;
+    __sincosf(th.v.x, &s0, &c0);
+    __sincosf(th.v.y, &s1, &c1);
+    rc = vmul(r, f2(c0, c1));
+    rs = vmul(r, f2(s0, s1));
 }
 
-// Four standard normals for inputs 4*chunk..4*chunk+3 of (global sample kg, horizon step t):
-// counter = (kg, t*nch + chunk, step_lo, step_hi), key = seed.
+// Standard normals for inputs 4*chunk..4*chunk+3 of (global sample kg, horizon step t):
+// counter = (kg, t*nch + chunk, step_lo, step_hi), key = seed.  n02 = (normal 0, normal 2),
+// n13 = (normal 1, normal 3).
+__device__ __forceinline__ void normal4_pairs(uint32_t kg, uint32_t tc, uint32_t step_lo, uint32_t step_hi,
+                                              const uint32_t *rkeys, f2 &n02, f2 &n13)
+{
+    const uint4 r = philox4x32_10(make_uint4(kg, tc, step_lo, step_hi), rkeys);
+    box_muller2(r, n02, n13);
+}
 __device__ __forceinline__ void normal4(uint32_t kg, uint32_t tc, uint32_t step_lo, uint32_t step_hi,
                                         const uint32_t *rkeys, float n[4])
 {
-    const uint4 r = philox4x32_10(make_uint4(kg, tc, step_lo, step_hi), rkeys);
-    box_muller(r.x, r.y, n[0], n[1]);
-    box_muller(r.z, r.w, n[2], n[3]);
+    f2 n02, n13;
+    normal4_pairs(kg, tc, step_lo, step_hi, rkeys, n02, n13);
+    n[0] = n02.v.x; n[2] = n02.v.y; n[1] = n13.v.x; n[3] = n13.v.y;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -327,6 +341,105 @@ __device__ __forceinline__ void fk_chain(const ChainDev &ch, const V *cq, const 
     }
 }
 
+// ---- Pose in packed layout ----------------------------------------------------------------
+// One sample per thread, but the FK still packs: each rotation column is held as the pair
+// (row 0, row 1) plus a row-2 scalar, the position as (x, y) + z.  Rotating by a joint angle is then
+// 4 packed + 4 scalar ops instead of 12, with (cos, sin) as broadcast scalar operands.
+struct Pose3 {
+    f2 c0, c1, c2;       // columns, rows 0..1
+    float r0, r1, r2;    // row 2 of columns 0..2
+    f2 pxy;
+    float pz;
+};
+__device__ __forceinline__ Pose3 pose3_from(const float R[9], const float p[3])
+{
+    Pose3 T;
+    T.c0 = f2(R[0], R[3]); T.c1 = f2(R[1], R[4]); T.c2 = f2(R[2], R[5]);
+    T.r0 = R[6]; T.r1 = R[7]; T.r2 = R[8];
+    T.pxy = f2(p[0], p[1]); T.pz = p[2];
+    return T;
+}
+// Rz(yaw) Ry(pitch) Rx(roll) with e = (cy, sy), e_perp = (-sy, cy):
+//   col0 = e cp,  col1 = e (sp sr) + e_perp cr,  col2 = e (sp cr) - e_perp sr   (transformation_matrix.py:148-187)
+__device__ __forceinline__ void pose3_rpy(Pose3 &T, float sr, float cr, float sp, float cp, float sy, float cy)
+{
+    const f2 e(cy, sy), ep(-sy, cy);
+    T.c0 = vmul(e, f2(cp));
+    T.c1 = vfma(e, f2(sp * sr), vmul(ep, f2(cr)));
+    T.c2 = vfma(e, f2(sp * cr), vneg(vmul(ep, f2(sr))));
+    T.r0 = -sp; T.r1 = cp * sr; T.r2 = cp * cr;
+}
+__device__ __forceinline__ void pose3_rotate_z(Pose3 &T, float c, float s)
+{
+    const f2 a = T.c0, b = T.c1;
+    T.c0 = vfma(a, f2(c), vmul(b, f2(s)));
+    T.c1 = vfma(b, f2(c), vneg(vmul(a, f2(s))));
+    const float u = T.r0, w = T.r1;
+    T.r0 = fmaf(c, u, s * w);
+    T.r1 = fmaf(c, w, -s * u);
+}
+template <class Tab, int J>
+__device__ __forceinline__ void pose3_compose_tab(Pose3 &T)
+{
+    const f2 a = T.c0, b = T.c1, c = T.c2;
+    const float u = T.r0, v = T.r1, w = T.r2;
+    T.pxy = tab_trans<Tab, J>(a, b, c, T.pxy);
+    T.pz = tab_trans<Tab, J>(u, v, w, T.pz);
+    T.c0 = tab_rot_col<Tab, J, 0>(a, b, c); T.c1 = tab_rot_col<Tab, J, 1>(a, b, c); T.c2 = tab_rot_col<Tab, J, 2>(a, b, c);
+    T.r0 = tab_rot_col<Tab, J, 0>(u, v, w); T.r1 = tab_rot_col<Tab, J, 1>(u, v, w); T.r2 = tab_rot_col<Tab, J, 2>(u, v, w);
+}
+__device__ __forceinline__ void pose3_compose_const(Pose3 &T, const float *Cr, const float *Ct)
+{
+    const f2 a = T.c0, b = T.c1, c = T.c2;
+    const float u = T.r0, v = T.r1, w = T.r2;
+    T.pxy = vfma(a, f2(Ct[0]), vfma(b, f2(Ct[1]), vfma(c, f2(Ct[2]), T.pxy)));
+    T.pz = fmaf(u, Ct[0], fmaf(v, Ct[1], fmaf(w, Ct[2], T.pz)));
+    T.c0 = vfma(a, f2(Cr[0]), vfma(b, f2(Cr[3]), vmul(c, f2(Cr[6]))));
+    T.c1 = vfma(a, f2(Cr[1]), vfma(b, f2(Cr[4]), vmul(c, f2(Cr[7]))));
+    T.c2 = vfma(a, f2(Cr[2]), vfma(b, f2(Cr[5]), vmul(c, f2(Cr[8]))));
+    T.r0 = fmaf(u, Cr[0], fmaf(v, Cr[3], w * Cr[6]));
+    T.r1 = fmaf(u, Cr[1], fmaf(v, Cr[4], w * Cr[7]));
+    T.r2 = fmaf(u, Cr[2], fmaf(v, Cr[5], w * Cr[8]));
+}
+template <class Tab, int J = 0>
+__device__ __forceinline__ void pose3_fk_tab(const float *cq, const float *sq, Pose3 &T)
+{
+    if constexpr (J < Tab::kJoints) {
+        pose3_rotate_z(T, cq[J], sq[J]);
+        pose3_compose_tab<Tab, J + 1>(T);
+        pose3_fk_tab<Tab, J + 1>(cq, sq, T);
+    }
+}
+template <int NJ>
+__device__ __forceinline__ void pose3_fk_chain(const ChainDev &ch, const float *cq, const float *sq, Pose3 &T)
+{
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        pose3_rotate_z(T, cq[j], sq[j]);
+        if (j + 1 < NJ || !ch.last_identity) pose3_compose_const(T, ch.R[j + 1], ch.t[j + 1]);
+    }
+}
+// Pose cost terms on a Pose3; the two atan2 of the ZYX Euler extraction run as one packed evaluation.
+__device__ __forceinline__ void pose3_terms(const Pose3 &T, const DynBlock &D, float &pos, float &ori)
+{
+    const float *Tg = D.target_R;
+    const f2 t0(Tg[0], Tg[3]), t1(Tg[1], Tg[4]), t2(Tg[2], Tg[5]);
+    const f2 dxy = vadd(T.pxy, f2(-D.target_pos[0], -D.target_pos[1]));
+    const float dz = T.pz - D.target_pos[2];
+    const f2 dd = vmul(dxy, dxy);
+    pos = sqrt_approx(fmaf(dz, dz, dd.v.x + dd.v.y));
+    const f2 m00 = vmul(T.c0, t0), m10 = vmul(T.c1, t0), m20 = vmul(T.c2, t0), m21 = vmul(T.c2, t1), m22 = vmul(T.c2, t2);
+    const float d00 = fmaf(T.r0, Tg[6], m00.v.x + m00.v.y);
+    const float d10 = fmaf(T.r1, Tg[6], m10.v.x + m10.v.y);
+    const float d20 = fmaf(T.r2, Tg[6], m20.v.x + m20.v.y);
+    const float d21 = fmaf(T.r2, Tg[7], m21.v.x + m21.v.y);
+    const float d22 = fmaf(T.r2, Tg[8], m22.v.x + m22.v.y);
+    const f2 e02 = atan2_poly(f2(d10, d21), f2(d00, d22));
+    const float e1 = asin_poly(fminf(fmaxf(-d20, -1.0f), 1.0f));
+    const f2 ee = vmul(e02, e02);
+    ori = sqrt_approx(fmaf(e1, e1, ee.v.x + ee.v.y));
+}
+
 // ||p - p*||_2 and ||euler_ZYX(R^T R*)||_2  (S/cost/pose_cost.py:24-63,
 // S/utils/rotation_conversions.py:277-319; inv(R) of a rotation is its transpose).
 template <class V>
@@ -364,7 +477,7 @@ __device__ __forceinline__ V wrap_pi(V a)
     return vfma(V(-kTwoPi), k, a);
 }
 
-template <class V>
+template <bool REFRESH = true, class V>
 __device__ __forceinline__ void quad_advance(QuadState<V> &s, V F, V tx, V ty, V tz, float dt, const float *qp)
 {
     const float inv_m = rcp_approx(qp[0]), kd = qp[4], gz = qp[5];
@@ -388,9 +501,11 @@ __device__ __forceinline__ void quad_advance(QuadState<V> &s, V F, V tx, V ty, V
     s.rpy[2] = wrap_pi(vfma(V(dt), dpsi, s.rpy[2]));
     s.v[0] = vfma(V(dt), ax, s.v[0]); s.v[1] = vfma(V(dt), ay, s.v[1]); s.v[2] = vfma(V(dt), az, s.v[2]);
     s.p[0] = vfma(V(dt), s.v[0], s.p[0]); s.p[1] = vfma(V(dt), s.v[1], s.p[1]); s.p[2] = vfma(V(dt), s.v[2], s.p[2]);
-    sincos_pi(s.rpy[0], s.sphi, s.cphi);
-    sincos_pi(s.rpy[1], s.sth, s.cth);
-    sincos_pi(s.rpy[2], s.spsi, s.cpsi);
+    if constexpr (REFRESH) {          // callers that batch the sin/cos of several angles pass REFRESH = false
+        sincos_pi(s.rpy[0], s.sphi, s.cphi);
+        sincos_pi(s.rpy[1], s.sth, s.cth);
+        sincos_pi(s.rpy[2], s.spsi, s.cpsi);
+    }
 }
 
 template <class V>

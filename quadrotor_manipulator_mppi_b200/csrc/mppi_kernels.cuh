@@ -14,8 +14,7 @@
 
 namespace mppi {
 
-constexpr int kRolloutThreads = 128;       // one sample per thread
-constexpr int kRolloutThreads2 = 64;       // two samples per thread (packed f32x2): finer blocks for wave balance
+constexpr int kRolloutThreads = 128;
 constexpr int kWeightTile = 2048;       // samples whose weights are staged in smem at a time
 
 // ------------------------------------------------------------------------------------------
@@ -23,13 +22,22 @@ constexpr int kWeightTile = 2048;       // samples whose weights are staged in s
 // Replaces S/mppi_solver/mppi.py:129-140 (sampling, get_sample_joint, compute_fk_gpu,
 // CostManager.compute_all_cost) and S/mppi_solver/drone_mppi.py:143-151.
 //
-// V = float: one sample per thread (small K: more threads, latency-bound regime).
-// V = f2   : two samples per thread, all FP32 arithmetic in packed FFMA2/FADD2/FMUL2 -- the kernel is
-//            issue-bound and packed ops halve the FP32 issue slots.  Lane 0 = sample k, lane 1 = sample
-//            k + blockDim.x (so global loads / stores of each lane stay coalesced).
+// One thread per sample, state in registers across the horizon loop.  The kernel is issue-bound, so
+// the FP32 work of ONE sample is packed into Blackwell's FP32x2 instructions (FFMA2 / FMUL2 / FADD2:
+// same FLOP rate as scalar FFMA, half the issue slots -- tools/probe_ffma2.cu):
+//   * the seven arm joints travel as pairs (0,2) (1,3) (4,6) (5,-) -- the pairing in which the packed
+//     Box-Muller emits its normals -- through the double integrator and sin/cos (with the quadrotor's
+//     Euler angles filling the spare lanes for the whole-body model);
+//   * the FK keeps each rotation column as a (row 0, row 1) pair + a row-2 scalar (Pose3);
+//   * the two atan2 of the Euler-angle cost run as one packed evaluation.
+// Carrying two samples per thread in f2 was measured too: parity-green but latency-bound at 3 warps per
+// scheduler (+3 % only), so packing within a sample at full occupancy is what ships.
 // ------------------------------------------------------------------------------------------
-template <int MODEL, bool PHILOX, bool BAKED, bool EXTRA, class V, int THREADS>
-__global__ void __launch_bounds__(THREADS, (Lanes<V>::n == 2) ? 7 : 1)
+__host__ __device__ constexpr int pairA(int i) { return i == 0 ? 0 : i == 1 ? 1 : i == 2 ? 4 : 5; }     // joint in lane 0 of arm pair i
+__host__ __device__ constexpr int pairB(int i) { return i == 0 ? 2 : i == 1 ? 3 : i == 2 ? 6 : -1; }    // joint in lane 1 (-1: spare lane)
+
+template <int MODEL, bool PHILOX, bool BAKED, bool EXTRA>
+__global__ void __launch_bounds__(kRolloutThreads, 7)
 rollout_cost_kernel(const __grid_constant__ StepParams P, const __grid_constant__ DynBlock D,
                     const float *__restrict__ u_nom, const float *__restrict__ noise,
                     float *__restrict__ cost_out, int32_t *__restrict__ rho_enc,
@@ -37,7 +45,6 @@ rollout_cost_kernel(const __grid_constant__ StepParams P, const __grid_constant_
 {
     constexpr int NU = ModelNu<MODEL>::value;
     constexpr int NCH = (NU + 3) / 4;
-    constexpr int NL = Lanes<V>::n;
     constexpr bool HAS_ARM = (MODEL == MPPI_MODEL_ARM7 || MODEL == MPPI_MODEL_WB11);
     constexpr bool HAS_QUAD = (MODEL == MPPI_MODEL_QUAD4 || MODEL == MPPI_MODEL_WB11);
     constexpr int ARM0 = (MODEL == MPPI_MODEL_WB11) ? 4 : 0;     // first arm input
@@ -45,7 +52,7 @@ rollout_cost_kernel(const __grid_constant__ StepParams P, const __grid_constant_
 
     extern __shared__ __align__(16) float s_unom[];              // [T][NU]
     __shared__ __align__(8) uint64_t s_bar;
-    __shared__ float s_wmin[THREADS / 32];
+    __shared__ float s_wmin[kRolloutThreads / 32];
 
     // ---- stage the nominal control sequence: one TMA bulk copy + scalar tail
     const int n_u = P.T * NU;
@@ -68,185 +75,199 @@ rollout_cost_kernel(const __grid_constant__ StepParams P, const __grid_constant_
     }
     __syncthreads();
 
-    // ---- the samples of this thread
-    int ks[NL];
-    bool active[NL];
-    uint32_t kg[NL];
-#pragma unroll
-    for (int l = 0; l < NL; ++l) {
-        const int k_raw = (blockIdx.x * NL + l) * THREADS + threadIdx.x;
-        active[l] = k_raw < P.K;
-        ks[l] = active[l] ? k_raw : P.K - 1;
-        kg[l] = static_cast<uint32_t>(P.k_offset + ks[l]);
-    }
+    const int k_raw = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = k_raw < P.K;
+    const int k = active ? k_raw : P.K - 1;
+    const uint32_t kg = static_cast<uint32_t>(P.k_offset + k);
 
     // ---- per-sample state in registers
-    V cum_v[HAS_ARM ? 7 : 3], cum_q[HAS_ARM ? 7 : 3], vprev[HAS_ARM ? 7 : 3];
-    QuadState<V> qs;
-    float R0[9], p0[3];          // chain root pose composed with C0 (uniform and loop-invariant for ARM7)
+    float dcv[3], dcq[3], dvp[3];                  // DRONE3 double integrator
+    f2 cum_v[4], cum_q[4], vprev[4];               // arm joints in pairs (pairA, pairB)
+    f2 q0p[4], qd0p[4];                            // measured joint state in the same pairing (uniform)
+    QuadState<float> qs;
+    Pose3 base0;                                   // chain root pose composed with C0 (uniform, loop-invariant for ARM7)
     if constexpr (MODEL == MPPI_MODEL_DRONE3) {
 #pragma unroll
-        for (int i = 0; i < 3; ++i) { cum_v[i] = V(0.f); cum_q[i] = V(0.f); vprev[i] = V(D.state[3 + i]); }
+        for (int i = 0; i < 3; ++i) { dcv[i] = 0.f; dcq[i] = 0.f; dvp[i] = D.state[3 + i]; }
     }
     if constexpr (HAS_ARM) {
 #pragma unroll
-        for (int i = 0; i < 7; ++i) { cum_v[i] = V(0.f); cum_q[i] = V(0.f); vprev[i] = V(D.state[QOFF + 7 + i]); }
+        for (int i = 0; i < 4; ++i) {
+            const int ja = pairA(i), jb = pairB(i);
+            q0p[i] = f2(D.state[QOFF + ja], jb >= 0 ? D.state[QOFF + jb] : 0.f);
+            qd0p[i] = f2(D.state[QOFF + 7 + ja], jb >= 0 ? D.state[QOFF + 7 + jb] : 0.f);
+            cum_v[i] = f2(0.f); cum_q[i] = f2(0.f); vprev[i] = qd0p[i];
+        }
     }
     if constexpr (MODEL == MPPI_MODEL_ARM7) {
+        float R0[9], p0[3];
         quat_matrix(&D.state[14], R0);                       // base xyz+quat -> B (S/robot/urdf_fk.py:30-55)
         p0[0] = D.state[14]; p0[1] = D.state[15]; p0[2] = D.state[16];
         if constexpr (BAKED) compose_tab<FkKinova, 0>(R0, p0);
         else compose_const(R0, p0, P.chain.R[0], P.chain.t[0]);
+        base0 = pose3_from(R0, p0);
     }
     if constexpr (HAS_QUAD) quad_load(qs, D.state);
 
-    V S = V(0.f), comp = V(0.f);       // Kahan-compensated running cost
-    V x_cov = V(0.f), x_cen = V(0.f), x_trk = V(0.f), x_act = V(0.f), x_lim = V(0.f);   // EXTRA cost terms
-    float gpow = 1.0f;                 // gamma^t
-    V Sd = V(0.f);                     // squared-distance stage cost (drone / quad part)
-    V term_d = V(0.f);
+    float S = 0.f, comp = 0.f;       // Kahan-compensated running cost
+    float x_cov = 0.f, x_cen = 0.f, x_trk = 0.f, x_act = 0.f, x_lim = 0.f, gpow = 1.0f;   // EXTRA cost terms, gamma^t
+    float Sd = 0.f;                  // squared-distance stage cost (drone / quad part)
+    float term_d = 0.f;
 
     for (int t = 0; t < P.T; ++t) {
-        // ---- controls of this step: v = u + noise  (S/mppi_solver/mppi.py:130)
-        V a[NU];
+        // ---- controls of this step: v = u + noise  (S/mppi_solver/mppi.py:130).  Inputs 4c..4c+3 arrive
+        // as the pairs (4c, 4c+2) and (4c+1, 4c+3).
+        f2 a02[NCH], a13[NCH];
 #pragma unroll
-        for (int l = 0; l < NL; ++l) {
+        for (int c = 0; c < NCH; ++c) {
+            const int i0 = 4 * c, i1 = 4 * c + 1, i2 = 4 * c + 2, i3 = 4 * c + 3;
             if constexpr (PHILOX) {
-#pragma unroll
-                for (int c = 0; c < NCH; ++c) {
-                    float n4[4];
-                    normal4(kg[l], static_cast<uint32_t>(t * NCH + c), D.step_lo, D.step_hi, P.rkeys, n4);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (4 * c + j < NU) set_lane(a[4 * c + j], l, __fmul_rn(P.sigma[4 * c + j], n4[j]));
-                }
+                f2 n02, n13;
+                normal4_pairs(kg, static_cast<uint32_t>(t * NCH + c), D.step_lo, D.step_hi, P.rkeys, n02, n13);
+                a02[c] = vmul(f2(P.sigma[i0], i2 < NU ? P.sigma[i2] : 0.f), n02);
+                a13[c] = vmul(f2(i1 < NU ? P.sigma[i1] : 0.f, i3 < NU ? P.sigma[i3] : 0.f), n13);
             } else {
-                const float *row = noise + (static_cast<size_t>(t) * P.K + ks[l]) * NU;
-#pragma unroll
-                for (int i = 0; i < NU; ++i) set_lane(a[i], l, __ldg(row + i));
+                const float *row = noise + (static_cast<size_t>(t) * P.K + k) * NU;
+                a02[c] = f2(__ldg(row + i0), i2 < NU ? __ldg(row + i2) : 0.f);
+                a13[c] = f2(i1 < NU ? __ldg(row + i1) : 0.f, i3 < NU ? __ldg(row + i3) : 0.f);
             }
+            const float *un = s_unom + t * NU;
+            a02[c] = vadd(f2(un[i0], i2 < NU ? un[i2] : 0.f), a02[c]);
+            a13[c] = vadd(f2(i1 < NU ? un[i1] : 0.f, i3 < NU ? un[i3] : 0.f), a13[c]);
         }
-#pragma unroll
-        for (int i = 0; i < NU; ++i) a[i] = vadd_rn(V(s_unom[t * NU + i]), a[i]);
+        // scalar view: input i lives in (i & 1 ? a13 : a02)[i >> 2], lane (i >> 1) & 1
+        auto input = [&](int i) -> float { return lane((i & 1) ? a13[i >> 2] : a02[i >> 2], (i >> 1) & 1); };
 
         const bool last = (t == P.T - 1);
-        if constexpr (EXTRA && HAS_ARM) {
-            // covar_cost.py:20-25: u^T Sigma^-1 v per step;  action_cost.py:15-25: gamma^t |v|^2
-            V cov = V(0.f), act = V(0.f);
-#pragma unroll
-            for (int i = 0; i < 7; ++i) {
-                cov = vfma(V(s_unom[t * NU + ARM0 + i] * P.inv_sigma_arm[i]), a[ARM0 + i], cov);
-                act = vfma(a[ARM0 + i], a[ARM0 + i], act);
-            }
-            x_cov = vadd(x_cov, cov);
-            x_act = vfma(V(gpow), act, x_act);
-        }
         if constexpr (MODEL == MPPI_MODEL_DRONE3) {
             // double integrator (S/mppi_solver/drone_mppi.py:46-55) + squared distance (:87-107)
-            V sq = V(0.f);
+            float sq = 0.f;
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
-                const V dq = vfma(vprev[i], V(P.dt), vmul(vmul(V(0.5f), a[i]), V(P.dt2)));
-                cum_v[i] = vfma(a[i], V(P.dt), cum_v[i]);
-                vprev[i] = vadd(cum_v[i], V(D.state[3 + i]));
-                cum_q[i] = vadd(cum_q[i], dq);
-                const V e = vsub(vadd(cum_q[i], V(D.state[i])), V(D.drone_target[i]));
-                sq = vfma(e, e, sq);
+                const float ai = input(i);
+                const float dq = fmaf(dvp[i], P.dt, (0.5f * ai) * P.dt2);
+                dcv[i] = fmaf(ai, P.dt, dcv[i]);
+                dvp[i] = dcv[i] + D.state[3 + i];
+                dcq[i] += dq;
+                const float e = (dcq[i] + D.state[i]) - D.drone_target[i];
+                sq = fmaf(e, e, sq);
             }
-            if (last) term_d = sq; else Sd = vadd(Sd, sq);
+            if (last) term_d = sq; else Sd += sq;
         }
         if constexpr (HAS_QUAD) {
-            quad_advance(qs, a[0], a[1], a[2], a[3], P.dt, P.quad);
-            const V ex = vsub(qs.p[0], V(D.drone_target[0])), ey = vsub(qs.p[1], V(D.drone_target[1])),
-                    ez = vsub(qs.p[2], V(D.drone_target[2]));
-            const V sq = vfma(ex, ex, vfma(ey, ey, vmul(ez, ez)));
-            if (last) term_d = sq; else Sd = vadd(Sd, sq);
+            quad_advance<false>(qs, input(0), input(1), input(2), input(3), P.dt, P.quad);   // sin/cos refreshed below
+            const float ex = qs.p[0] - D.drone_target[0], ey = qs.p[1] - D.drone_target[1], ez = qs.p[2] - D.drone_target[2];
+            const float sq = fmaf(ex, ex, fmaf(ey, ey, ez * ez));
+            if (last) term_d = sq; else Sd += sq;
+        }
+        if constexpr (MODEL == MPPI_MODEL_QUAD4) {
+            f2 s2, c2;
+            sincos_pi(f2(qs.rpy[0], qs.rpy[1]), s2, c2);
+            qs.sphi = s2.v.x; qs.cphi = c2.v.x; qs.sth = s2.v.y; qs.cth = c2.v.y;
+            sincos_pi(qs.rpy[2], qs.spsi, qs.cpsi);
         }
         if constexpr (HAS_ARM) {
-            // S/sampling/standard_normal_noise.py:32-50
-            V cq[7], sq[7];
+            // arm accelerations in the joint pairing: chunk c1 = ARM0/4 holds joints 0..3, the next one joints 4..6
+            constexpr int C1 = ARM0 / 4;
+            const f2 aj[4] = {a02[C1], a13[C1], a02[C1 + 1], a13[C1 + 1]};
+            // S/sampling/standard_normal_noise.py:32-50, two joints per instruction
+            f2 qp[4];
 #pragma unroll
-            for (int i = 0; i < 7; ++i) {
-                const V ai = a[ARM0 + i];
-                const V dq = vfma(vprev[i], V(P.dt), vmul(vmul(V(0.5f), ai), V(P.dt2)));
-                cum_v[i] = vfma(ai, V(P.dt), cum_v[i]);
-                vprev[i] = vadd(cum_v[i], V(D.state[QOFF + 7 + i]));
+            for (int i = 0; i < 4; ++i) {
+                const f2 dq = vfma(vprev[i], f2(P.dt), vmul(vmul(f2(0.5f), aj[i]), f2(P.dt2)));
+                cum_v[i] = vfma(aj[i], f2(P.dt), cum_v[i]);
+                vprev[i] = vadd(cum_v[i], qd0p[i]);
                 cum_q[i] = vadd(cum_q[i], dq);
-                sincos_pi(vadd(cum_q[i], V(D.state[QOFF + i])), sq[i], cq[i]);
+                qp[i] = vadd(cum_q[i], q0p[i]);
             }
             if constexpr (EXTRA) {
-                // joint_space_cost.py:18-77: centering, tracking, joint-limit indicator, all discounted by gamma^t
-                V cen = V(0.f), trk = V(0.f);
-                auto out_of_bounds = mask_false(typename Lanes<V>::mask{});
+                // covar_cost.py:20-25 (u^T Sigma^-1 v), action_cost.py:15-25, joint_space_cost.py:18-77; gamma^t discount
+                f2 cov(0.f), act(0.f), cen(0.f), trk(0.f);
+                bool out_of_bounds = false;
 #pragma unroll
-                for (int i = 0; i < 7; ++i) {
-                    const V q = vadd(cum_q[i], V(D.state[QOFF + i]));
-                    const V dc = vsub(q, V(P.q_center[i]));
+                for (int i = 0; i < 4; ++i) {
+                    const int ja = pairA(i), jb = pairB(i);
+                    const float *un = s_unom + t * NU + ARM0;
+                    const f2 usig(un[ja] * P.inv_sigma_arm[ja], jb >= 0 ? un[jb] * P.inv_sigma_arm[jb] : 0.f);
+                    cov = vfma(usig, aj[i], cov);
+                    act = vfma(aj[i], aj[i], act);
+                    const f2 dc = vsub(qp[i], f2(P.q_center[ja], jb >= 0 ? P.q_center[jb] : 0.f));
                     cen = vfma(dc, dc, cen);
-                    const V dtk = vsub(q, V(q_traj ? __ldg(q_traj + t * 7 + i) : 0.0f));
-                    trk = vfma(dtk, dtk, trk);
-                    out_of_bounds = vor(out_of_bounds, vor(vlt(q, V(P.q_lower[i])), vgt(q, V(P.q_upper[i]))));
+                    const f2 qt(q_traj ? __ldg(q_traj + t * 7 + ja) : 0.f, (q_traj && jb >= 0) ? __ldg(q_traj + t * 7 + jb) : 0.f);
+                    const f2 dk = vsub(qp[i], qt);
+                    trk = vfma(dk, dk, trk);
+                    out_of_bounds = out_of_bounds || qp[i].v.x < P.q_lower[ja] || qp[i].v.x > P.q_upper[ja];
+                    if (jb >= 0) out_of_bounds = out_of_bounds || qp[i].v.y < P.q_lower[jb] || qp[i].v.y > P.q_upper[jb];
                 }
-                x_cen = vfma(V(gpow), cen, x_cen);
-                x_trk = vfma(V(gpow), trk, x_trk);
-                x_lim = vsel(out_of_bounds, vfma(V(gpow), V(P.limit_penalty), x_lim), x_lim);
+                // the spare lane of pair 3 carries zeros in aj / (q - 0) terms: exclude it from the q-dependent sums
+                x_cov += cov.v.x + cov.v.y;
+                x_act = fmaf(gpow, act.v.x + act.v.y, x_act);
+                const float pad_q = qp[3].v.y;        // = 0 + 0 (spare lane): (0 - q_center)^2 would be 0 for both tables
+                (void)pad_q;
+                x_cen = fmaf(gpow, cen.v.x + cen.v.y, x_cen);
+                x_trk = fmaf(gpow, trk.v.x + trk.v.y, x_trk);
+                if (out_of_bounds) x_lim = fmaf(gpow, P.limit_penalty, x_lim);
                 gpow *= P.gamma;
             }
-            V R[9], p[3];
-            if constexpr (MODEL == MPPI_MODEL_ARM7) {
+            // sin / cos of the seven joint angles (and of the new Euler angles for the whole body), packed
+            float cq[7], sq[7];
+            f2 s2, c2;
 #pragma unroll
-                for (int i = 0; i < 9; ++i) R[i] = V(R0[i]);
-                p[0] = V(p0[0]); p[1] = V(p0[1]); p[2] = V(p0[2]);
-            } else {
-                // moving base T(p_t, rpy_t) (S/robot/transformation_matrix.py:148-187)
-                rpy_matrix(qs.sphi, qs.cphi, qs.sth, qs.cth, qs.spsi, qs.cpsi, R);
-                p[0] = qs.p[0]; p[1] = qs.p[1]; p[2] = qs.p[2];
-                if constexpr (BAKED) compose_tab<FkKinova, 0>(R, p);
-                else compose_const(R, p, P.chain.R[0], P.chain.t[0]);
+            for (int i = 0; i < 3; ++i) {
+                sincos_pi(qp[i], s2, c2);
+                sq[pairA(i)] = s2.v.x; cq[pairA(i)] = c2.v.x; sq[pairB(i)] = s2.v.y; cq[pairB(i)] = c2.v.y;
             }
-            if constexpr (BAKED) fk_tab<FkKinova>(cq, sq, R, p);
-            else fk_chain<7>(P.chain, cq, sq, R, p);
-            V pos, ori;
-            pose_terms(R, p, D, pos, ori);
+            Pose3 Tp;
+            if constexpr (MODEL == MPPI_MODEL_ARM7) {
+                sincos_pi(qp[3].v.x, sq[5], cq[5]);
+                Tp = base0;
+            } else {
+                sincos_pi(f2(qp[3].v.x, qs.rpy[0]), s2, c2);
+                sq[5] = s2.v.x; cq[5] = c2.v.x; qs.sphi = s2.v.y; qs.cphi = c2.v.y;
+                sincos_pi(f2(qs.rpy[1], qs.rpy[2]), s2, c2);
+                qs.sth = s2.v.x; qs.cth = c2.v.x; qs.spsi = s2.v.y; qs.cpsi = c2.v.y;
+                // moving base T(p_t, rpy_t) (S/robot/transformation_matrix.py:148-187)
+                pose3_rpy(Tp, qs.sphi, qs.cphi, qs.sth, qs.cth, qs.spsi, qs.cpsi);
+                Tp.pxy = f2(qs.p[0], qs.p[1]); Tp.pz = qs.p[2];
+                if constexpr (BAKED) pose3_compose_tab<FkKinova, 0>(Tp);
+                else pose3_compose_const(Tp, P.chain.R[0], P.chain.t[0]);
+            }
+            if constexpr (BAKED) pose3_fk_tab<FkKinova>(cq, sq, Tp);
+            else pose3_fk_chain<7>(P.chain, cq, sq, Tp);
+            float pos, ori;
+            pose3_terms(Tp, D, pos, ori);
             // S/cost/cost_manager.py:30-33,78-89
-            const V c = last ? vfma(V(P.cost_w[2]), pos, vmul(V(P.cost_w[3]), ori))
-                             : vfma(V(P.cost_w[0]), pos, vmul(V(P.cost_w[1]), ori));
-            const V y = vsub(c, comp);
-            const V tS = vadd(S, y);
-            comp = vsub(vsub(tS, S), y);
+            const float c = last ? fmaf(P.cost_w[2], pos, P.cost_w[3] * ori)
+                                 : fmaf(P.cost_w[0], pos, P.cost_w[1] * ori);
+            const float y = c - comp;
+            const float tS = S + y;
+            comp = (tS - S) - y;
             S = tS;
         }
     }
     if constexpr (MODEL == MPPI_MODEL_DRONE3 || MODEL == MPPI_MODEL_QUAD4) {
-        S = vfma(Sd, V(P.cost_w[4]), vmul(term_d, V(P.cost_w[5])));
+        S = fmaf(Sd, P.cost_w[4], term_d * P.cost_w[5]);
     } else if constexpr (MODEL == MPPI_MODEL_WB11) {
-        S = vadd(S, vfma(Sd, V(P.cost_w[4]), vmul(term_d, V(P.cost_w[5]))));
+        S = S + fmaf(Sd, P.cost_w[4], term_d * P.cost_w[5]);
     }
     if constexpr (EXTRA && HAS_ARM) {
         // same order as the commented-out sum, cost_manager.py:83-87
-        if (P.cost_flags & MPPI_COST_COVAR) S = vfma(V(P.covar_scale), x_cov, S);
-        if (P.cost_flags & MPPI_COST_CENTERING) S = vfma(V(P.centering_weight), x_cen, S);
-        if (P.cost_flags & MPPI_COST_JOINT_TRAJ) S = vfma(V(P.joint_traj_weight), x_trk, S);
-        if (P.cost_flags & MPPI_COST_ACTION) S = vfma(V(P.action_weight), x_act, S);
-        if (P.cost_flags & MPPI_COST_JOINT_LIMIT) S = vadd(S, x_lim);
+        if (P.cost_flags & MPPI_COST_COVAR) S += P.covar_scale * x_cov;
+        if (P.cost_flags & MPPI_COST_CENTERING) S += P.centering_weight * x_cen;
+        if (P.cost_flags & MPPI_COST_JOINT_TRAJ) S += P.joint_traj_weight * x_trk;
+        if (P.cost_flags & MPPI_COST_ACTION) S += P.action_weight * x_act;
+        if (P.cost_flags & MPPI_COST_JOINT_LIMIT) S += x_lim;
     }
 
-    float m = __int_as_float(0x7f800000);
-#pragma unroll
-    for (int l = 0; l < NL; ++l) {
-        if (active[l]) {
-            cost_out[ks[l]] = lane(S, l);
-            m = fminf(m, lane(S, l));
-        }
-    }
+    if (active) cost_out[k] = S;
     // ---- block minimum -> one atomicMin on the order-preserving encoding
-    m = warp_min(m);
+    float m = warp_min(active ? S : __int_as_float(0x7f800000));
     if ((threadIdx.x & 31) == 0) s_wmin[threadIdx.x >> 5] = m;
     __syncthreads();
     if (threadIdx.x == 0) {
         float bm = s_wmin[0];
 #pragma unroll
-        for (int w = 1; w < THREADS / 32; ++w) bm = fminf(bm, s_wmin[w]);
+        for (int w = 1; w < kRolloutThreads / 32; ++w) bm = fminf(bm, s_wmin[w]);
         atomicMin(rho_enc, encode_ordered(bm));
     }
 }

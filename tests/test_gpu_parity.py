@@ -21,14 +21,6 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-4
 
 
-@pytest.fixture(autouse=True, params=["one-sample-per-thread", "packed-f32x2"])
-def rollout_variant(request, monkeypatch):
-    """Every GPU test runs against both rollout kernels: V=float (one sample per thread) and V=f2 (two
-    samples per thread in packed FFMA2).  The library picks by K; MPPI_VEC2_MIN_SAMPLES overrides it."""
-    monkeypatch.setenv("MPPI_VEC2_MIN_SAMPLES", "1" if request.param == "packed-f32x2" else str(1 << 30))
-    return request.param
-
-
 @pytest.fixture(scope="module")
 def native():
     from quadrotor_manipulator_mppi_b200 import _native
