@@ -230,16 +230,22 @@ def make_controller(model, K, T, device, k_offset=0, seed=0):
     return quad_mppi.MPPI(n_samples=K, n_timestep=T, seed=seed, device=device)
 
 
-def feed_state(ctrl, model, st):
+def sensor_message(model, st):
+    """The arguments the ROS node would pass (kinova.py:116 `update_joint(q, v)`, drone.py:164 `set_state(x, v)`)."""
     if model == "wb":
-        ctrl.set_state(st[:3], st[3:6], st[6:9], st[9:12], st[12:19], st[19:26])
-    elif model == "arm":
-        ctrl.update_joint(np.concatenate([st[14:21], st[:7]]).astype(np.float64),
-                          np.concatenate([np.zeros(6), st[7:14]]).astype(np.float64))
-    elif model == "drone":
-        ctrl.set_state(st[:3], st[3:6])
+        return (st[:3], st[3:6], st[6:9], st[9:12], st[12:19], st[19:26])
+    if model == "arm":
+        return (np.concatenate([st[14:21], st[:7]]).astype(np.float64), np.concatenate([np.zeros(6), st[7:14]]).astype(np.float64))
+    if model == "drone":
+        return (st[:3], st[3:6])
+    return (st[:3], st[3:6], st[6:9], st[9:12])
+
+
+def feed_state(ctrl, model, msg):
+    if model == "arm":
+        ctrl.update_joint(*msg)
     else:
-        ctrl.set_state(st[:3], st[3:6], st[6:9], st[9:12])
+        ctrl.set_state(*msg)
 
 
 def run_native(args):
@@ -393,16 +399,19 @@ def run_native(args):
     e2e = None
     if world == 1:
         ctrl = make_controller(args.model, K, T, device)
-        feed_state(ctrl, args.model, st)
+        feed_state(ctrl, args.model, sensor_message(args.model, st))
         n_e2e = max(10, min(args.steps, 100))
         for _ in range(3):
             ctrl.compute_control_input()
+        jits = []
+        for i in range(n_e2e):                              # synthetic sensor messages, prepared outside the timed region
+            jit = st.copy()
+            jit[:3] += rng.uniform(-0.05, 0.05, 3).astype(np.float32)
+            jits.append(sensor_message(args.model, jit))
         torch.cuda.synchronize(device)
         t0 = time.perf_counter()
         for i in range(n_e2e):
-            jit = st.copy()
-            jit[:3] += rng.uniform(-0.05, 0.05, 3).astype(np.float32)
-            feed_state(ctrl, args.model, jit)               # host state -> kernel parameters
+            feed_state(ctrl, args.model, jits[i])           # host state -> kernel parameters
             res = ctrl.compute_control_input()              # host numpy / synchronised outputs
             if args.model in ("drone", "quad"):
                 res[0].cpu()                                # drone.py:240 reads xdes on the host

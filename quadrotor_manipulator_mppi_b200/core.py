@@ -81,6 +81,8 @@ class NativeSolver:
         self._out_host_np = self._out_host.numpy()
         self._state_np = np.zeros(_native.MODEL_STATE[model], np.float32)
         self._state_lock = threading.Lock()
+        self._state_ptr = _native.fptr(self._state_np)
+        self._set_state_c = self._lib.mppi_set_state
         self.costs = torch.as_tensor(_DevView(self._lib.mppi_cost_ptr(self.handle), self.K, "<f4"), device=self.device)
         self.rho_enc = torch.as_tensor(_DevView(self._lib.mppi_rho_ptr(self.handle), 1, "<i4"), device=self.device)
         self.wsum = torch.as_tensor(_DevView(self._lib.mppi_wsum_ptr(self.handle), self._lib.mppi_wsum_count(self.handle),
@@ -112,10 +114,25 @@ class NativeSolver:
 
     def set_state(self, state) -> None:
         """Thread-safe: may be called from a subscriber thread while another thread steps."""
-        st = np.ascontiguousarray(state, dtype=np.float32).reshape(-1)
         with self._state_lock:
-            self._state_np[:] = st      # raises on a length mismatch
-            _native.check(self._lib.mppi_set_state(self.handle, _native.fptr(self._state_np), st.size), self.handle)
+            self._state_np[:] = np.asarray(state, dtype=np.float32).reshape(-1)      # raises on a length mismatch
+            rc = self._set_state_c(self.handle, self._state_ptr, self._state_np.size)
+        if rc:
+            _native.check(rc, self.handle)
+
+    def set_state_parts(self, *parts) -> None:
+        """Same, from consecutive slices (avoids building a temporary concatenation on the caller side)."""
+        with self._state_lock:
+            o = 0
+            for p in parts:
+                n = len(p)
+                self._state_np[o:o + n] = p
+                o += n
+            if o != self._state_np.size:
+                raise ValueError(f"state has {o} entries, expected {self._state_np.size}")
+            rc = self._set_state_c(self.handle, self._state_ptr, o)
+        if rc:
+            _native.check(rc, self.handle)
 
     def set_target(self, pos=None, quat=None, drone_target=None) -> None:
         def p(v, n):

@@ -471,14 +471,14 @@ __device__ void reduce_partials_and_finalize(const StepParams &P, const DynBlock
     if (!s_last) return;
     __threadfence();
     for (int j = threadIdx.x; j < row; j += blockDim.x) {
+        // eight loads in flight per thread; rows are always added in the same order (deterministic)
         float acc = 0.f;
         int b = 0;
-        for (; b + 4 <= n_parts; b += 4) {
-            const float v0 = __ldcg(part + static_cast<size_t>(b) * row + j);
-            const float v1 = __ldcg(part + static_cast<size_t>(b + 1) * row + j);
-            const float v2 = __ldcg(part + static_cast<size_t>(b + 2) * row + j);
-            const float v3 = __ldcg(part + static_cast<size_t>(b + 3) * row + j);
-            acc = ((acc + v0) + v1) + v2 + v3;
+        for (; b + 8 <= n_parts; b += 8) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldcg(part + static_cast<size_t>(b + u) * row + j);
+            acc += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
         }
         for (; b < n_parts; ++b) acc += __ldcg(part + static_cast<size_t>(b) * row + j);
         if (eta_part != nullptr && j >= row - 2) {          // eta / sum w^2 come from the weights kernel

@@ -33,8 +33,6 @@ class MPPI:
         self.sigma = torch.eye(3, device=self.device) * torch.as_tensor(sigma, dtype=torch.float32, device=self.device)
         self.target = torch.tensor([1.0, 2.0, 3.4])                            # drone_mppi.py:141
         self._target_sent = None
-        self.x_prev = torch.zeros(3, device=self.device)
-        self.v_prev = torch.zeros(3, device=self.device)
         self._state = np.zeros(6, np.float32)
         self._solver.set_state(self._state)
         self.last_costs = None
@@ -54,11 +52,18 @@ class MPPI:
 
     def set_state(self, x, v):
         """drone_mppi.py:179-183."""
-        self._state[:3] = np.asarray(x, np.float32)
-        self._state[3:] = np.asarray(v, np.float32)
+        self._state[:3] = x
+        self._state[3:] = v
         self._solver.set_state(self._state)
-        self.x_prev = torch.as_tensor(self._state[:3].copy(), device=self.device)
-        self.v_prev = torch.as_tensor(self._state[3:].copy(), device=self.device)
+
+    # x_prev / v_prev of the reference (drone_mppi.py:24-25) as lazily built device tensors
+    @property
+    def x_prev(self) -> torch.Tensor:
+        return torch.as_tensor(self._state[:3].copy(), device=self.device)
+
+    @property
+    def v_prev(self) -> torch.Tensor:
+        return torch.as_tensor(self._state[3:].copy(), device=self.device)
 
     def compute_control_input(self, noise=None, noise_layout: str = "tkn", return_costs: bool = False):
         """drone_mppi.py:140-176."""

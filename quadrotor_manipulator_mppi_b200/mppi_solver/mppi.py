@@ -111,7 +111,7 @@ class MPPI:
         self._push_state()
 
     def _push_state(self):
-        self._solver.set_state(np.concatenate([self._q64, self._qdot64, self._base64]))
+        self._solver.set_state_parts(self._q64, self._qdot64, self._base64)
 
     def update_joint(self, q_full, v_full):
         """mppi.py:196-200.  Safe to call from the subscriber thread while a step is running."""
@@ -121,7 +121,7 @@ class MPPI:
         self._qdot64 = v_full[6:13].copy()
         self._base64 = q_full[:7].copy()
         self._state_dtype = np.float64
-        self._push_state()
+        self._solver.set_state_parts(self._q64, self._qdot64, self._base64)
 
     # ------------------------------------------------------------------ the control step
     def _sync_target(self):

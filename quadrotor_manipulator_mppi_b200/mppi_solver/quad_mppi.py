@@ -45,8 +45,7 @@ class MPPI:
         self._solver.u_prev = value
 
     def set_state(self, p, rpy, v, w):
-        self._state[:] = np.concatenate([np.asarray(a, np.float32).reshape(3) for a in (p, rpy, v, w)])
-        self._solver.set_state(self._state)
+        self._solver.set_state_parts(p, rpy, v, w)
 
     def compute_control_input(self, noise=None, noise_layout: str = "tkn"):
         """Returns the one-step-ahead state (p, rpy, v, w) as device tensors."""

@@ -50,9 +50,7 @@ class MPPI:
         self._solver.u_prev = value
 
     def set_state(self, p, rpy, v, w, q, qdot):
-        parts = [np.asarray(a, np.float32).reshape(-1) for a in (p, rpy, v, w, q, qdot)]
-        self._state[:] = np.concatenate(parts)
-        self._solver.set_state(self._state)
+        self._solver.set_state_parts(p, rpy, v, w, q, qdot)
 
     def _sync_target(self):
         dt_ = self.drone_target
