@@ -1,0 +1,66 @@
+// Throughput of the FMA-pipe instruction kinds the rollout kernel uses (warp-instructions per cycle per SM sub-partition).
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o probe_pipes tools/probe_pipes.cu && ./probe_pipes
+#include <cstdio>
+#include <cuda_runtime.h>
+
+template <int MODE>
+__global__ void __launch_bounds__(256) probe(float *out, int iters, float a, float b, unsigned m)
+{
+    float2 x[8];
+    unsigned y[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { x[i] = make_float2(threadIdx.x + i, threadIdx.x - i); y[i] = threadIdx.x * 7 + i; }
+    const float2 a2 = make_float2(a, a), b2 = make_float2(b, b);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (MODE == 0) x[i] = __ffma2_rn(x[i], a2, b2);
+                if (MODE == 1) x[i] = __fmul2_rn(x[i], a2);
+                if (MODE == 2) x[i] = __fadd2_rn(x[i], b2);
+                if (MODE == 3) { x[i].x = fmaf(x[i].x, a, b); x[i].y = fmaf(x[i].y, a, b); }
+                if (MODE == 4) { unsigned long long p = (unsigned long long)y[i] * 0xD2511F53u; y[i] = (unsigned)(p >> 32) ^ (unsigned)p ^ m; }
+                if (MODE == 5) { x[i] = __ffma2_rn(x[i], a2, b2); y[i] = (y[i] ^ m) + 0x9e3779b9u; }     // FFMA2 + 1 ALU op
+                if (MODE == 6) { x[i].x = fmaf(x[i].x, a, b); x[i].y = fmaf(x[i].y, a, b); y[i] = (y[i] ^ m) + 0x9e3779b9u; }
+            }
+        }
+    }
+    float s = 0; unsigned t = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s += x[i].x + x[i].y; t ^= y[i]; }
+    if (s == 1234.5f && t == 77u) out[0] = s;
+}
+
+template <int MODE>
+float run(int sms, int iters)
+{
+    float *d; cudaMalloc(&d, 64);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e9f;
+    for (int r = 0; r < 4; ++r) {
+        cudaEventRecord(e0);
+        probe<MODE><<<sms * 8, 256>>>(d, iters, 0.999f, 0.001f, 0x9e3779b9u);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (r > 0 && ms < best) best = ms;
+    }
+    cudaFree(d);
+    return best;
+}
+
+int main()
+{
+    cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
+    const int sms = p.multiProcessorCount, iters = 2048;
+    int khz = 0; cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0);
+    // per iteration each thread executes 64 "slots" of the mode; warps per SMSP = 8*256/32/4 = 16
+    const char *names[] = {"FFMA2", "FMUL2", "FADD2", "2x FFMA", "IMAD.WIDE + 2 LOP", "FFMA2 + ALU", "2x FFMA + ALU"};
+    float t[7] = {run<0>(sms, iters), run<1>(sms, iters), run<2>(sms, iters), run<3>(sms, iters), run<4>(sms, iters), run<5>(sms, iters), run<6>(sms, iters)};
+    for (int i = 0; i < 7; ++i) {
+        const double cyc = t[i] * 1e-3 * 1.965e9;                        // assumes 1965 MHz
+        const double per_slot = cyc / (double)iters / 64.0 / 16.0;      // cycles per warp-slot per scheduler
+        printf("%-20s %.3f ms  %.2f cycles per slot per scheduler\n", names[i], t[i], per_slot);
+    }
+    return 0;
+}
