@@ -389,11 +389,41 @@ def run_native(args):
                 "algorithmic_flop_per_rollout_step": _native.algorithmic_flops(model_id),
                 "kernel_ms": k_ms, "share_of_step": k_ms / (k_ms + w_ms),
                 "weighting_kernel_ms": w_ms}
-    if noise is not None:       # HBM-bound weighting pass: re-read of the [T][K][nu] noise
-        gbs = K_loc * T * nu * 4 / (w_ms * 1e-3) / 1e9
-        roofline["weighting_hbm"] = {"bound": "hbm", "achieved": gbs, "peak": peaks.get("hbm_gbs", 6650.0), "unit": "GB/s",
-                                     "frac": gbs / peaks.get("hbm_gbs", 6650.0),
+    # ---- HBM-bound weighting pass (re-read of a materialised [T][K][nu] noise tensor), timed alone.
+    # In Philox mode the step has no HBM-bound kernel, so the injected-noise weighting pass is measured
+    # here on the side (same K, T) to report the second roofline the north star names.
+    hbm_noise = noise
+    if hbm_noise is None and world == 1 and K_loc * T * nu * 4 <= 4 * 1024 ** 3:
+        hbm_noise = solver.generate_noise(0)
+    if hbm_noise is not None:
+        wt2 = []
+        for i in range(8):
+            if flush is not None:
+                flush.zero_()
+            solver.rollout(hbm_noise)
+            e0.record(stream)
+            solver.weight(hbm_noise)
+            e1.record(stream)
+            torch.cuda.synchronize(device)
+            wt2.append(e0.elapsed_time(e1))
+            solver.finalize()
+        w2_ms = float(np.mean(wt2[2:]))
+        gbs = K_loc * T * nu * 4 / (w2_ms * 1e-3) / 1e9
+        tkey = f"{args.model}_weighting_K{K_loc}_T{T}"
+        wtraffic = None
+        if os.path.exists(tpath):
+            try:
+                wtraffic = json.load(open(tpath)).get(tkey)
+            except Exception:
+                wtraffic = None
+        roofline["weighting_hbm"] = {"kernel": "weights_kernel + weighted_noise_kernel", "bound": "hbm", "achieved": gbs,
+                                     "peak": peaks.get("hbm_gbs", 6650.0), "unit": "GB/s", "frac": gbs / peaks.get("hbm_gbs", 6650.0),
+                                     "traffic": wtraffic, "kernel_ms": w2_ms,
+                                     "algorithmic_bytes_per_rollout_step": nu * 4,
                                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"}
+        if noise is None:
+            del hbm_noise
+            torch.cuda.empty_cache()
 
     # ---- end to end through the public controller class: host state in, host controls out, every step
     e2e = None
