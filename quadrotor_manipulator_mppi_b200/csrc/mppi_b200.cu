@@ -350,7 +350,7 @@ mppi_status_t launch_weight(mppi_ctx *h, const float *d_noise, bool fuse, const 
         if (blocks < 1) blocks = 1;
         const int chunk = (K + blocks - 1) / blocks;
         blocks = (K + chunk - 1) / chunk;
-        size_t smem_floats = (size_t)kWeightTile + (size_t)R * TC * 4;
+        size_t smem_floats = (size_t)2 * kWeightTile + (size_t)R * TC * 4;
         if (smem_floats < fin_floats) smem_floats = fin_floats;
         weight_philox_kernel<MODEL><<<blocks, threads, smem_floats * sizeof(float), st>>>(
             h->P, h->dyn, h->d_cost, h->d_rho, chunk, h->d_part, h->d_counter, h->d_wsum, fuse ? 1 : 0, d_u_nom, d_u_new, d_out, X);

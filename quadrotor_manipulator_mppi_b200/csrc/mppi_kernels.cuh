@@ -512,10 +512,12 @@ weight_philox_kernel(const __grid_constant__ StepParams P, const __grid_constant
 {
     constexpr int NU = ModelNu<MODEL>::value;
     constexpr int NCH = (NU + 3) / 4;
-    extern __shared__ __align__(16) float s_dyn[];      // [kWeightTile] weights | reduction / finalize scratch
+    extern __shared__ __align__(16) float s_dyn[];      // [kWeightTile] weights | [kWeightTile] indices | reduction / finalize scratch
     float *s_w = s_dyn;
-    float *s_red = s_dyn + kWeightTile;
+    int *s_idx = reinterpret_cast<int *>(s_dyn + kWeightTile);
+    float *s_red = s_dyn + 2 * kWeightTile;
     __shared__ float s_eta[32], s_eta2[32];
+    __shared__ int s_cnt[32];
 
     const int TC = P.T * NCH;
     const int R = blockDim.x / TC;
@@ -537,22 +539,44 @@ weight_philox_kernel(const __grid_constant__ StepParams P, const __grid_constant
     for (int base = k0; base < k1; base += kWeightTile) {
         const int nt = min(kWeightTile, k1 - base);
         __syncthreads();
-        for (int kk = tid; kk < nt; kk += blockDim.x) {
-            const float w = expf(-P.inv_lambda * (S[base + kk] - rho));
-            s_w[kk] = w;
-            eta += w;
-            eta2 = fmaf(w, w, eta2);
+        // weights of the tile + an ORDER-PRESERVING compaction of the samples whose weight is not exactly
+        // zero (ballot + per-warp offsets), so the noise loop below only visits samples that contribute.
+        // With lambda << cost spread (the drone) that is a handful of samples.
+        int n_nz = 0;
+        for (int pass = 0; pass < nt; pass += blockDim.x) {
+            const int kk = pass + tid;
+            float w = 0.f;
+            if (kk < nt) {
+                w = expf(-P.inv_lambda * (S[base + kk] - rho));
+                eta += w;
+                eta2 = fmaf(w, w, eta2);
+            }
+            const unsigned ball = __ballot_sync(0xffffffffu, w != 0.f);
+            if ((tid & 31) == 0) s_cnt[tid >> 5] = __popc(ball);
+            __syncthreads();
+            int warp_off = 0, total = 0;
+            const int nw = (blockDim.x + 31) >> 5;
+            for (int wv = 0; wv < nw; ++wv) {
+                const int cw = s_cnt[wv];
+                if (wv < (tid >> 5)) warp_off += cw;
+                total += cw;
+            }
+            if (w != 0.f) {
+                const int slot = n_nz + warp_off + __popc(ball & ((1u << (tid & 31)) - 1u));
+                s_idx[slot] = kk;
+                s_w[slot] = w;
+            }
+            n_nz += total;
+            __syncthreads();
         }
-        __syncthreads();
         if (worker) {
-            for (int kk = r; kk < nt; kk += R) {
-                const float w = s_w[kk];
-                if (w == 0.f) continue;
+            for (int j = r; j < n_nz; j += R) {
+                const float w = s_w[j];
                 float n4[4];
-                normal4(static_cast<uint32_t>(P.k_offset + base + kk), static_cast<uint32_t>(tc),
+                normal4(static_cast<uint32_t>(P.k_offset + base + s_idx[j]), static_cast<uint32_t>(tc),
                         D.step_lo, D.step_hi, P.rkeys, n4);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[j] = fmaf(w, __fmul_rn(sg[j], n4[j]), acc[j]);
+                for (int jj = 0; jj < 4; ++jj) acc[jj] = fmaf(w, __fmul_rn(sg[jj], n4[jj]), acc[jj]);
             }
         }
     }
