@@ -148,6 +148,7 @@ struct mppi_ctx {
     uint32_t *d_counter = nullptr;  // last-block-done counter
     float *d_part = nullptr;        // [max_parts][T*nu+2]
     float *d_wsum = nullptr;        // [T*nu+2]
+    unsigned long long *d_fix = nullptr;   // [T*nu+2] fixed-point accumulators of the Philox weighting pass
     float *d_w = nullptr;           // [K] unnormalised weights (injected-noise path)
     float *d_eta_part = nullptr;    // [<=SMs][2] partial sums of w, w^2
     int wn_resident = 0;            // resident blocks of the streaming weighting kernel (one wave)
@@ -353,7 +354,7 @@ mppi_status_t launch_weight(mppi_ctx *h, const float *d_noise, bool fuse, const 
         size_t smem_floats = (size_t)2 * kWeightTile + (size_t)R * TC * 4;
         if (smem_floats < fin_floats) smem_floats = fin_floats;
         weight_philox_kernel<MODEL><<<blocks, threads, smem_floats * sizeof(float), st>>>(
-            h->P, h->dyn, h->d_cost, h->d_rho, chunk, h->d_part, h->d_counter, h->d_wsum, fuse ? 1 : 0, d_u_nom, d_u_new, d_out, X);
+            h->P, h->dyn, h->d_cost, h->d_rho, chunk, h->d_fix, h->d_counter, h->d_wsum, fuse ? 1 : 0, d_u_nom, d_u_new, d_out, X);
     } else {
         const bool vec4 = ((size_t)K * NU) % 4 == 0 && (reinterpret_cast<uintptr_t>(d_noise) & 15u) == 0;
         // weights once, then one resident wave of (G x T) streaming blocks
@@ -569,6 +570,8 @@ mppi_status_t mppi_create(const mppi_config_t *cfg, mppi_handle_t *out)
     h->d_counter = reinterpret_cast<uint32_t *>(h->d_rho + 1);
     if ((e = cudaMalloc(&h->d_part, (size_t)h->max_parts * row * sizeof(float))) != cudaSuccess) return cleanup(e, "cudaMalloc(partials)");
     if ((e = cudaMalloc(&h->d_wsum, row * sizeof(float))) != cudaSuccess) return cleanup(e, "cudaMalloc(wsum)");
+    if ((e = cudaMalloc(&h->d_fix, row * sizeof(unsigned long long))) != cudaSuccess) return cleanup(e, "cudaMalloc(fix)");
+    if ((e = cudaMemset(h->d_fix, 0, row * sizeof(unsigned long long))) != cudaSuccess) return cleanup(e, "cudaMemset(fix)");
     if ((e = cudaMalloc(&h->d_u, (size_t)P.T * nu * sizeof(float))) != cudaSuccess) return cleanup(e, "cudaMalloc(u)");
     if ((e = cudaMalloc(&h->d_out, MPPI_OUT_FLOATS * sizeof(float))) != cudaSuccess) return cleanup(e, "cudaMalloc(out)");
     if ((e = cudaMalloc(&h->d_qtraj, (size_t)P.T * 7 * sizeof(float))) != cudaSuccess) return cleanup(e, "cudaMalloc(qtraj)");
@@ -589,7 +592,7 @@ mppi_status_t mppi_destroy(mppi_handle_t h)
     {
         DeviceGuard guard(h->cfg.device);
         cudaDeviceSynchronize();
-        cudaFree(h->d_cost); cudaFree(h->d_rho); cudaFree(h->d_w); cudaFree(h->d_eta_part); cudaFree(h->d_part); cudaFree(h->d_wsum);
+        cudaFree(h->d_cost); cudaFree(h->d_rho); cudaFree(h->d_w); cudaFree(h->d_eta_part); cudaFree(h->d_part); cudaFree(h->d_wsum); cudaFree(h->d_fix);
         cudaFree(h->d_u); cudaFree(h->d_out); cudaFree(h->d_noise); cudaFree(h->d_qtraj);
         for (int r = 0; r < kMaxRanks; ++r) if (h->p2p_peer[r]) cudaIpcCloseMemHandle(h->p2p_peer[r]);
         cudaFree(h->p2p_buf);

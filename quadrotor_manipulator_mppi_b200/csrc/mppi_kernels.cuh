@@ -15,7 +15,8 @@
 namespace mppi {
 
 constexpr int kRolloutThreads = 128;
-constexpr int kWeightTile = 2048;       // samples whose weights are staged in smem at a time
+constexpr int kWeightTile = 2048;
+constexpr float kFixScale = 8589934592.0f;   // 2^33: fixed-point scale of the weighting accumulators       // samples whose weights are staged in smem at a time
 
 // ------------------------------------------------------------------------------------------
 // K2: fused noise + rollout + FK + cost.
@@ -456,7 +457,8 @@ __device__ void reduce_partials_and_finalize(const StepParams &P, const DynBlock
                                              int n_parts, uint32_t *counter, float *wsum, bool fuse,
                                              const float *u_nom, float *u_new, float *out,
                                              int32_t *rho_enc, float *scratch, const P2PParams &X,
-                                             const float *eta_part = nullptr, int n_eta = 0)
+                                             const float *eta_part = nullptr, int n_eta = 0,
+                                             unsigned long long *fix = nullptr)
 {
     constexpr int NU = ModelNu<MODEL>::value;
     __shared__ bool s_last;
@@ -470,6 +472,15 @@ __device__ void reduce_partials_and_finalize(const StepParams &P, const DynBlock
     __syncthreads();
     if (!s_last) return;
     __threadfence();
+    if (fix != nullptr) {
+        // fixed-point accumulators -> float sums (sigma applied here), and re-arm them for the next step
+        for (int j = threadIdx.x; j < row; j += blockDim.x) {
+            const long long q = static_cast<long long>(__ldcg(fix + j));
+            fix[j] = 0ull;
+            const float scale = (j < row - 2) ? P.sigma[j % NU] * (1.0f / kFixScale) : (1.0f / kFixScale);
+            wsum[j] = static_cast<float>(q) * scale;
+        }
+    } else
     for (int j = threadIdx.x; j < row; j += blockDim.x) {
         // eight loads in flight per thread; rows are always added in the same order (deterministic)
         float acc = 0.f;
@@ -507,7 +518,7 @@ template <int MODEL>
 __global__ void __launch_bounds__(1024)
 weight_philox_kernel(const __grid_constant__ StepParams P, const __grid_constant__ DynBlock D,
                      const float *__restrict__ S, int32_t *rho_enc, int chunk,
-                     float *__restrict__ part, uint32_t *counter, float *wsum, int fuse,
+                     unsigned long long *__restrict__ fix, uint32_t *counter, float *wsum, int fuse,
                      const float *u_nom, float *u_new, float *out, const __grid_constant__ P2PParams X)
 {
     constexpr int NU = ModelNu<MODEL>::value;
@@ -530,9 +541,6 @@ weight_philox_kernel(const __grid_constant__ StepParams P, const __grid_constant
     const int k0 = blockIdx.x * chunk;
     const int k1 = min(P.K, k0 + chunk);
 
-    float sg[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) sg[j] = (4 * c + j < NU) ? P.sigma[4 * c + j] : 0.f;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     float eta = 0.f, eta2 = 0.f;
 
@@ -576,7 +584,7 @@ weight_philox_kernel(const __grid_constant__ StepParams P, const __grid_constant
                 normal4(static_cast<uint32_t>(P.k_offset + base + s_idx[j]), static_cast<uint32_t>(tc),
                         D.step_lo, D.step_hi, P.rkeys, n4);
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj) acc[jj] = fmaf(w, __fmul_rn(sg[jj], n4[jj]), acc[jj]);
+                for (int jj = 0; jj < 4; ++jj) acc[jj] = fmaf(w, n4[jj], acc[jj]);      // sigma is applied once, after the reduction
             }
         }
     }
@@ -590,15 +598,18 @@ weight_philox_kernel(const __grid_constant__ StepParams P, const __grid_constant
         for (int j = 0; j < 4; ++j) s_red[(r * TC + tc) * 4 + j] = acc[j];
     }
     __syncthreads();
+    // Block sums go into 64-bit FIXED-POINT accumulators with integer atomics: integer addition is
+    // associative, so the result is bit-reproducible whatever the block order, and the last block has
+    // nothing left to reduce (a float row-per-block scheme costs ~15 us of serial L2 round trips here).
+    // |sum w n| <= K * 5.7 < 2^29 for K <= 2^26, scale 2^33 -> below 2^62; resolution 1.2e-10.
     const int row = P.T * NU + 2;
-    float *my = part + static_cast<size_t>(blockIdx.x) * row;
     if (tid < TC) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             if (4 * c + j < NU) {
                 float v = 0.f;
                 for (int rr = 0; rr < R; ++rr) v += s_red[(rr * TC + tc) * 4 + j];
-                my[t * NU + 4 * c + j] = v;
+                if (v != 0.f) atomicAdd(fix + t * NU + 4 * c + j, static_cast<unsigned long long>(__float2ll_rn(v * kFixScale)));
             }
         }
     }
@@ -606,11 +617,11 @@ weight_philox_kernel(const __grid_constant__ StepParams P, const __grid_constant
         float e = 0.f, e2 = 0.f;
         const int nw = (blockDim.x + 31) >> 5;
         for (int w = 0; w < nw; ++w) { e += s_eta[w]; e2 += s_eta2[w]; }
-        my[row - 2] = e;
-        my[row - 1] = e2;
+        if (e != 0.f) atomicAdd(fix + row - 2, static_cast<unsigned long long>(__float2ll_rn(e * kFixScale)));
+        if (e2 != 0.f) atomicAdd(fix + row - 1, static_cast<unsigned long long>(__float2ll_rn(e2 * kFixScale)));
     }
-    reduce_partials_and_finalize<MODEL>(P, D, part, gridDim.x, counter, wsum, fuse != 0, u_nom, u_new, out,
-                                        rho_enc, s_dyn, X);
+    reduce_partials_and_finalize<MODEL>(P, D, nullptr, 0, counter, wsum, fuse != 0, u_nom, u_new, out,
+                                        rho_enc, s_dyn, X, nullptr, 0, fix);
 }
 
 // ------------------------------------------------------------------------------------------
