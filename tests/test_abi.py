@@ -64,3 +64,18 @@ def test_product_package_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src and "libmppi_oracle" not in src, f
+
+
+def test_reference_import_lines_work_through_the_compat_shim():
+    """kinova.py:23 / drone.py:19 import lines, verbatim, resolve to the B200 classes."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); import quadrotor_manipulator_mppi_b200.compat as c; "
+            "sys.path.insert(0, c.PATH)\n"
+            "from mppi_solver.mppi import MPPI as A\nfrom mppi_solver.drone_mppi import MPPI as D\n"
+            "assert A.__module__ == 'quadrotor_manipulator_mppi_b200.mppi_solver.mppi', A.__module__\n"
+            "assert D.__module__ == 'quadrotor_manipulator_mppi_b200.mppi_solver.drone_mppi'\n"
+            "import inspect; assert all(p.kind == p.KEYWORD_ONLY for p in list(inspect.signature(A.__init__).parameters.values())[1:])\n"
+            "print('ok')") % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr
