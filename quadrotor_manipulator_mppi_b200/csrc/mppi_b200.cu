@@ -166,7 +166,7 @@ struct mppi_ctx {
     P2PParams X_off{};              // world == 1: exchange disabled
     void *p2p_peer[kMaxRanks] = {};
     bool baked_fk = false;          // runtime chain == compile-time FkKinova tables
-    size_t rollout_smem[8] = {};    // tuned dynamic smem per kernel variant (0 = not yet tuned)
+    size_t rollout_smem[12] = {};   // tuned dynamic smem per kernel variant (0 = not yet tuned)
     float *d_qtraj = nullptr;       // [T][7] joint reference trajectory (MPPI_COST_JOINT_TRAJ), zeros by default
     cudaStream_t own_stream = nullptr;
     std::string err;
@@ -297,13 +297,14 @@ size_t tuned_rollout_smem(mppi_ctx *h, KernelT kernel, int threads, int grid, si
     return pad;
 }
 
-template <int MODEL, bool PHILOX, bool BAKED, bool EXTRA>
+template <int MODEL, int NOISE, bool BAKED, bool EXTRA>
 mppi_status_t launch_rollout_variant(mppi_ctx *h, int variant, const float *d_u_nom, const float *d_noise, float *d_cost,
                                      cudaStream_t st)
 {
     constexpr int NU = ModelNu<MODEL>::value;
-    const size_t smem = (size_t)h->P.T * NU * sizeof(float);
-    auto kernel = rollout_cost_kernel<MODEL, PHILOX, BAKED, EXTRA>;
+    size_t smem = (size_t)h->P.T * NU * sizeof(float);
+    if (NOISE == 2) smem = ((smem + 15) & ~(size_t)15) + (size_t)kNoiseStages * kRolloutThreads * NU * sizeof(float);
+    auto kernel = rollout_cost_kernel<MODEL, NOISE, BAKED, EXTRA>;
     const int grid = (h->P.K + kRolloutThreads - 1) / kRolloutThreads;
     size_t &tuned = h->rollout_smem[variant];
     if (tuned == 0) tuned = tuned_rollout_smem(h, kernel, kRolloutThreads, grid, smem);
@@ -312,23 +313,30 @@ mppi_status_t launch_rollout_variant(mppi_ctx *h, int variant, const float *d_u_
     return MPPI_OK;
 }
 
-template <int MODEL>
-mppi_status_t launch_rollout(mppi_ctx *h, const float *d_u_nom, const float *d_noise, float *d_cost, cudaStream_t st)
+template <int MODEL, int NOISE>
+mppi_status_t launch_rollout_noise(mppi_ctx *h, const float *d_u_nom, const float *d_noise, float *d_cost, cudaStream_t st)
 {
     constexpr bool HAS_ARM = (MODEL == MPPI_MODEL_ARM7 || MODEL == MPPI_MODEL_WB11);
     const bool baked = HAS_ARM && h->baked_fk;      // FK unrolled from the URDF constants (fk_tables_gen.cuh)
     const bool extra = HAS_ARM && h->P.cost_flags != 0;      // optional cost terms: separate, slower instantiation
-    const int variant = (d_noise ? 0 : 1) + (baked ? 2 : 0) + (extra ? 4 : 0);
-    switch (variant) {
-        case 0: return launch_rollout_variant<MODEL, false, false, false>(h, variant, d_u_nom, d_noise, d_cost, st);
-        case 1: return launch_rollout_variant<MODEL, true, false, false>(h, variant, d_u_nom, d_noise, d_cost, st);
-        case 2: return launch_rollout_variant<MODEL, false, HAS_ARM, false>(h, variant, d_u_nom, d_noise, d_cost, st);
-        case 3: return launch_rollout_variant<MODEL, true, HAS_ARM, false>(h, variant, d_u_nom, d_noise, d_cost, st);
-        case 4: return launch_rollout_variant<MODEL, false, false, HAS_ARM>(h, variant, d_u_nom, d_noise, d_cost, st);
-        case 5: return launch_rollout_variant<MODEL, true, false, HAS_ARM>(h, variant, d_u_nom, d_noise, d_cost, st);
-        case 6: return launch_rollout_variant<MODEL, false, HAS_ARM, HAS_ARM>(h, variant, d_u_nom, d_noise, d_cost, st);
-        default: return launch_rollout_variant<MODEL, true, HAS_ARM, HAS_ARM>(h, variant, d_u_nom, d_noise, d_cost, st);
+    const int variant = NOISE * 4 + (baked ? 1 : 0) + (extra ? 2 : 0);
+    switch ((baked ? 1 : 0) + (extra ? 2 : 0)) {
+        case 0: return launch_rollout_variant<MODEL, NOISE, false, false>(h, variant, d_u_nom, d_noise, d_cost, st);
+        case 1: return launch_rollout_variant<MODEL, NOISE, HAS_ARM, false>(h, variant, d_u_nom, d_noise, d_cost, st);
+        case 2: return launch_rollout_variant<MODEL, NOISE, false, HAS_ARM>(h, variant, d_u_nom, d_noise, d_cost, st);
+        default: return launch_rollout_variant<MODEL, NOISE, HAS_ARM, HAS_ARM>(h, variant, d_u_nom, d_noise, d_cost, st);
     }
+}
+
+template <int MODEL>
+mppi_status_t launch_rollout(mppi_ctx *h, const float *d_u_nom, const float *d_noise, float *d_cost, cudaStream_t st)
+{
+    constexpr int NU = ModelNu<MODEL>::value;
+    if (!d_noise) return launch_rollout_noise<MODEL, 0>(h, d_u_nom, nullptr, d_cost, st);
+    // injected [T][K][nu]: TMA-staged tiles when every 128-sample tile is 16-byte aligned and sized
+    const bool tma_ok = ((size_t)h->P.K * NU) % 4 == 0 && (reinterpret_cast<uintptr_t>(d_noise) & 15u) == 0;
+    if (tma_ok) return launch_rollout_noise<MODEL, 2>(h, d_u_nom, d_noise, d_cost, st);
+    return launch_rollout_noise<MODEL, 1>(h, d_u_nom, d_noise, d_cost, st);
 }
 
 template <int MODEL>

@@ -37,7 +37,12 @@ constexpr float kFixScale = 8589934592.0f;   // 2^33: fixed-point scale of the w
 __host__ __device__ constexpr int pairA(int i) { return i == 0 ? 0 : i == 1 ? 1 : i == 2 ? 4 : 5; }     // joint in lane 0 of arm pair i
 __host__ __device__ constexpr int pairB(int i) { return i == 0 ? 2 : i == 1 ? 3 : i == 2 ? 6 : -1; }    // joint in lane 1 (-1: spare lane)
 
-template <int MODEL, bool PHILOX, bool BAKED, bool EXTRA>
+// NOISE: 0 = in-kernel Philox, 1 = injected [T][K][nu] read directly (any K, any alignment),
+//        2 = injected, staged through shared memory by TMA bulk copies (one 128-sample tile per horizon
+//            step, kNoiseStages deep; needs K*nu % 4 == 0 and a 16-byte aligned tensor).
+constexpr int kNoiseStages = 4;
+
+template <int MODEL, int NOISE, bool BAKED, bool EXTRA>
 __global__ void __launch_bounds__(kRolloutThreads, 7)
 rollout_cost_kernel(const __grid_constant__ StepParams P, const __grid_constant__ DynBlock D,
                     const float *__restrict__ u_nom, const float *__restrict__ noise,
@@ -51,8 +56,10 @@ rollout_cost_kernel(const __grid_constant__ StepParams P, const __grid_constant_
     constexpr int ARM0 = (MODEL == MPPI_MODEL_WB11) ? 4 : 0;     // first arm input
     constexpr int QOFF = (MODEL == MPPI_MODEL_WB11) ? 12 : 0;    // arm q in the state vector
 
-    extern __shared__ __align__(16) float s_unom[];              // [T][NU]
+    constexpr bool PHILOX = (NOISE == 0);
+    extern __shared__ __align__(16) float s_unom[];              // [T][NU] | (NOISE == 2) noise tiles [kNoiseStages][128][NU]
     __shared__ __align__(8) uint64_t s_bar;
+    __shared__ __align__(8) uint64_t s_full[kNoiseStages];
     __shared__ float s_wmin[kRolloutThreads / 32];
 
     // ---- stage the nominal control sequence: one TMA bulk copy + scalar tail
@@ -61,9 +68,27 @@ rollout_cost_kernel(const __grid_constant__ StepParams P, const __grid_constant_
     const bool bulk_ok = bulk_bytes > 0 && ((reinterpret_cast<uintptr_t>(u_nom) & 15u) == 0);
     if (threadIdx.x == 0) {
         mbar_init(&s_bar, 1);
+        if constexpr (NOISE == 2) {
+#pragma unroll
+            for (int st = 0; st < kNoiseStages; ++st) mbar_init(&s_full[st], 1);
+        }
         mbar_fence_init();
     }
     __syncthreads();
+    // ---- injected noise through TMA: the block's samples [k0, k0 + nb) of row t are nb*NU contiguous floats
+    const int k0_blk = blockIdx.x * kRolloutThreads;
+    const int nb = min(kRolloutThreads, P.K - k0_blk);
+    float *s_tiles = s_unom + ((n_u + 3) & ~3);                  // 16-byte aligned behind the nominal sequence
+    const uint32_t tile_bytes = static_cast<uint32_t>(nb) * NU * 4u;
+    if constexpr (NOISE == 2) {
+        if (threadIdx.x == 0) {
+            for (int st = 0; st < kNoiseStages && st < P.T; ++st) {
+                mbar_expect_tx(&s_full[st], tile_bytes);
+                tma_bulk_g2s(s_tiles + st * (kRolloutThreads * NU), noise + (static_cast<size_t>(st) * P.K + k0_blk) * NU,
+                             tile_bytes, &s_full[st]);
+            }
+        }
+    }
     if (bulk_ok) {
         if (threadIdx.x == 0) {
             mbar_expect_tx(&s_bar, bulk_bytes);
@@ -119,6 +144,7 @@ rollout_cost_kernel(const __grid_constant__ StepParams P, const __grid_constant_
         // ---- controls of this step: v = u + noise  (S/mppi_solver/mppi.py:130).  Inputs 4c..4c+3 arrive
         // as the pairs (4c, 4c+2) and (4c+1, 4c+3).
         f2 a02[NCH], a13[NCH];
+        if constexpr (NOISE == 2) mbar_wait(&s_full[t % kNoiseStages], (t / kNoiseStages) & 1);
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
             const int i0 = 4 * c, i1 = 4 * c + 1, i2 = 4 * c + 2, i3 = 4 * c + 3;
@@ -127,14 +153,35 @@ rollout_cost_kernel(const __grid_constant__ StepParams P, const __grid_constant_
                 normal4_pairs(kg, static_cast<uint32_t>(t * NCH + c), D.step_lo, D.step_hi, P.rkeys, n02, n13);
                 a02[c] = vmul(f2(P.sigma[i0], i2 < NU ? P.sigma[i2] : 0.f), n02);
                 a13[c] = vmul(f2(i1 < NU ? P.sigma[i1] : 0.f, i3 < NU ? P.sigma[i3] : 0.f), n13);
-            } else {
+            } else if constexpr (NOISE == 1) {
                 const float *row = noise + (static_cast<size_t>(t) * P.K + k) * NU;
                 a02[c] = f2(__ldg(row + i0), i2 < NU ? __ldg(row + i2) : 0.f);
                 a13[c] = f2(i1 < NU ? __ldg(row + i1) : 0.f, i3 < NU ? __ldg(row + i3) : 0.f);
+            } else {
+                // tile of this horizon step, landed in shared memory through TMA (stride NU words per thread:
+                // conflict-free for odd NU; NU == 4 reads one float4 per thread)
+                const float *row = s_tiles + (t % kNoiseStages) * (kRolloutThreads * NU) + (k - k0_blk) * NU;
+                if constexpr (NU == 4) {
+                    const float4 v4 = *reinterpret_cast<const float4 *>(row);
+                    a02[c] = f2(v4.x, v4.z);
+                    a13[c] = f2(v4.y, v4.w);
+                } else {
+                    a02[c] = f2(row[i0], i2 < NU ? row[i2] : 0.f);
+                    a13[c] = f2(i1 < NU ? row[i1] : 0.f, i3 < NU ? row[i3] : 0.f);
+                }
             }
             const float *un = s_unom + t * NU;
             a02[c] = vadd(f2(un[i0], i2 < NU ? un[i2] : 0.f), a02[c]);
             a13[c] = vadd(f2(i1 < NU ? un[i1] : 0.f, i3 < NU ? un[i3] : 0.f), a13[c]);
+        }
+        if constexpr (NOISE == 2) {
+            __syncthreads();                       // every thread has taken its controls out of the stage
+            if (threadIdx.x == 0 && t + kNoiseStages < P.T) {
+                const int st = t % kNoiseStages;
+                mbar_expect_tx(&s_full[st], tile_bytes);
+                tma_bulk_g2s(s_tiles + st * (kRolloutThreads * NU),
+                             noise + (static_cast<size_t>(t + kNoiseStages) * P.K + k0_blk) * NU, tile_bytes, &s_full[st]);
+            }
         }
         // scalar view: input i lives in (i & 1 ? a13 : a02)[i >> 2], lane (i >> 1) & 1
         auto input = [&](int i) -> float { return lane((i & 1) ? a13[i >> 2] : a02[i >> 2], (i >> 1) & 1); };
