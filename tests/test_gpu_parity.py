@@ -413,3 +413,68 @@ def test_full_size_properties(model_name, K, T, native):
     s2.u_prev = u0
     s2.step(None, step_counter=2)
     assert torch.equal(s2.costs, s.costs) and torch.equal(s2.u_prev, s.u_prev)
+
+
+# ------------------------------------------------------------------ generic chains, runtime re-configuration
+def _chain_variant(oracle, which):
+    """Chains that do NOT match the baked j2s7s300 tables -> the generic constant-bank FK path."""
+    base = oracle.KINOVA_CHAIN
+    jt, qi = list(base.jtype), list(base.qidx)
+    xyz, rpy, axis = base.xyz.copy(), base.rpy.copy(), base.axis.copy()
+    if which == "end_effector":      # j2s7s300_joint_end_effector, aerial_manipulator_gpu.urdf:377-383 (trailing fixed joint)
+        jt.append(0); qi.append(-1)
+        xyz = np.vstack([xyz, [[0, 0, -0.16]]]); rpy = np.vstack([rpy, [[np.pi, 0, np.pi / 2]]]); axis = np.vstack([axis, [[0, 0, 0]]])
+    elif which == "tilted_axes":     # non-z joint axes and non-right-angle origins: exercises the axis alignment fold
+        axis[2] = [0, 1, 0]; axis[4] = [1, 0, 0]; axis[6] = [0.6, 0.0, 0.8]
+        rpy[3] = [0.3, -0.2, 0.5]; xyz[5] = [0.01, 0.2, -0.03]
+    return oracle.Chain(jt, qi, xyz, rpy, axis)
+
+
+@pytest.mark.parametrize("which", ["end_effector", "tilted_axes"])
+def test_generic_chain_against_oracle(which, oracle, native):
+    """other end links / arms work through mppi_set_chain without editing CUDA."""
+    from quadrotor_manipulator_mppi_b200.core import NativeSolver
+    ch = _chain_variant(oracle, which)
+    K, T = 384, 20
+    s = NativeSolver(native.MODEL_ARM7, n_samples=K, n_horizon=T)
+    s.set_chain(ch.jtype, ch.xyz, ch.rpy, ch.axis)
+    q = np.array([1.2, 2.0, -0.4, 4.0, 0.7, 4.2, -1.0], np.float32)
+    qd = np.array([0.05, -0.1, 0.02, 0.3, -0.2, 0.1, -0.05], np.float32)
+    base = np.array([0.3, -0.2, 1.7, 0.0499792, -0.0998334, 0.1494381, 0.9824485], np.float32)
+    s.set_state(np.concatenate([q, qd, base]))
+    noise = _rand_noise(T, K, (0.1,) * 7, 17)
+    s.step(s.prepare_noise(noise))
+    S = s.costs.cpu().numpy()
+    want = oracle.arm_costs(noise, np.zeros((T, 7), np.float32), q, qd, base, chain=ch)
+    assert rel_inf(S, want) < 5e-6
+    # and the baked chain really is a different answer (the test would be vacuous otherwise)
+    assert rel_inf(want, oracle.arm_costs(noise, np.zeros((T, 7), np.float32), q, qd, base)) > 1e-3
+    with pytest.raises(native.MppiError):        # prismatic joints are rejected, not silently mis-handled
+        s.set_chain([0, 2, 1, 1, 1, 1, 1, 1], ch.xyz[:8], ch.rpy[:8], ch.axis[:8])
+
+
+def test_update_config_and_targets_take_effect(oracle, native):
+    from quadrotor_manipulator_mppi_b200.core import NativeSolver
+    K, T = 256, 16
+    s = NativeSolver(native.MODEL_ARM7, n_samples=K, n_horizon=T)
+    state = np.concatenate([oracle.Q_HOME, np.zeros(7), [0, 0, 2.1, 0, 0, 0, 1]]).astype(np.float32)
+    s.set_state(state)
+    noise = _rand_noise(T, K, (0.1,) * 7, 23)
+    s.update_config(lambda_=0.5, cost_w=[10.0, 5.0, 80.0, 2.0, 100.0, 20.0, 0.0, 0.0])
+    tp, tq = [0.3, 0.2, 1.5], [0.1, -0.3, 0.2, 0.9]             # un-normalised quaternion: normalised as the reference does
+    s.set_target(pos=tp, quat=tq)
+    s.step(s.prepare_noise(noise))
+    S = s.costs.cpu().numpy()
+    want = oracle.arm_costs(noise, np.zeros((T, 7), np.float32), oracle.Q_HOME, np.zeros(7), [0, 0, 2.1, 0, 0, 0, 1],
+                            target_pos=tp, target_quat=tq, weights=(10.0, 5.0, 80.0, 2.0))
+    assert rel_inf(S, want) < 5e-6
+    iso = oracle._update(S, noise, np.zeros((T, 7), np.float32), 0.5, 9)
+    assert rel_inf(s.u_prev.cpu().numpy(), iso["u_new"]) < 1e-5
+    # drone target through the drop-in class attribute (drone_mppi.py:141 hard-codes it)
+    d = _drone(128, 12)
+    d.set_state([0, 0, 2.1], [0.1, 0, 0])
+    d.target = torch.tensor([-1.0, 0.5, 2.0])
+    nd = _rand_noise(12, 128, (30.0,) * 3, 29)
+    _, _, Sd = d.compute_control_input(noise=nd, return_costs=True)
+    assert rel_inf(Sd.cpu().numpy(), oracle.drone_costs(nd, np.zeros((12, 3), np.float32), [0, 0, 2.1], [0.1, 0, 0],
+                                                         target=(-1.0, 0.5, 2.0))) < 5e-6
