@@ -479,6 +479,7 @@ def run_native(args):
                 "config": {"workload": f"{spec['desc']}, K={K}, T={T}", "noise": args.noise,
                            "K_per_gpu": K_loc, "parallelism": f"k-shard x{world}" if world > 1 else "single GPU",
                            "exchange": (stepper.exchange if world > 1 else None),
+                           "exchange_fallback": getattr(stepper, "fallback_reason", None),
                            "l2": "no flush" if flush is None else "L2 flushed between steps (256 MiB memset) outside the per-step CUDA events",
                            "timing": "CUDA events around every step on the launch stream, summed, max over ranks"},
                 "latency_ms": {"p50": float(np.percentile(step_ms, 50)), "p99": float(np.percentile(step_ms, 99)),

@@ -51,19 +51,32 @@ def decode_ordered(key: int) -> float:
 
 
 def enable_p2p(solver, group=None) -> None:
-    """Exchange CUDA IPC handles of the shards' exchange buffers and bind them (collective call)."""
+    """Exchange CUDA IPC handles of the shards' exchange buffers and bind them (collective call).
+
+    Either every rank ends up bound or every rank raises: the local outcome is agreed on with a MIN
+    all-reduce, so a rank whose cudaIpcOpenMemHandle fails cannot leave its peers waiting."""
     import ctypes as C
 
     from . import _native
     lib = _native.load()
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     mine = (C.c_ubyte * _native.MPPI_IPC_HANDLE_BYTES)()
-    _native.check(lib.mppi_p2p_export(solver.handle, world, mine), solver.handle)
+    err = None
+    rc = lib.mppi_p2p_export(solver.handle, world, mine)
+    if rc:
+        err = lib.mppi_last_error(solver.handle).decode()
     gathered = [None] * world
-    dist.all_gather_object(gathered, bytes(mine), group=group)
-    blob = b"".join(gathered)
-    _native.check(lib.mppi_p2p_bind(solver.handle, world, rank, blob), solver.handle)
-    dist.barrier(group=group)        # nobody steps before every rank has mapped its peers
+    dist.all_gather_object(gathered, bytes(mine) if err is None else None, group=group)
+    if err is None and all(g is not None for g in gathered):
+        rc = lib.mppi_p2p_bind(solver.handle, world, rank, b"".join(gathered))
+        if rc:
+            err = lib.mppi_last_error(solver.handle).decode()
+    elif err is None:
+        err = "a peer could not export its exchange buffer"
+    ok = torch.tensor([0 if err else 1], dtype=torch.int32, device=solver.device)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)      # also the barrier: nobody steps before all are bound
+    if int(ok.item()) == 0:
+        raise RuntimeError(f"peer-to-peer exchange unavailable on rank {rank}: {err or 'a peer failed'}")
 
 
 class ShardedStepper:
@@ -78,8 +91,12 @@ class ShardedStepper:
         if exchange not in ("nccl", "p2p"):
             raise ValueError("exchange must be 'nccl' or 'p2p'")
         self.exchange = exchange if self.world > 1 else "nccl"
+        self.fallback_reason = None
         if self.exchange == "p2p":
-            enable_p2p(solver, group)
+            try:
+                enable_p2p(solver, group)
+            except RuntimeError as e:       # raised on every rank together: fall back to the NCCL contract path
+                self.exchange, self.fallback_reason = "nccl", str(e)
 
     def step_async(self, noise=None):
         s = self.solver
