@@ -478,3 +478,64 @@ def test_update_config_and_targets_take_effect(oracle, native):
     _, _, Sd = d.compute_control_input(noise=nd, return_costs=True)
     assert rel_inf(Sd.cpu().numpy(), oracle.drone_costs(nd, np.zeros((12, 3), np.float32), [0, 0, 2.1], [0.1, 0, 0],
                                                          target=(-1.0, 0.5, 2.0))) < 5e-6
+
+
+def test_random_states_and_targets_incl_euler_singularity(oracle, native):
+    """Costs vs the oracle over random joint states / base poses / targets.  The ZYX Euler extraction has an
+    unbounded slope at |pitch| -> pi/2 (asin'(1) = inf, SURVEY 'hard parts'), so samples whose relative rotation
+    has |D20| > 0.9999 are checked at 1e-3 and counted; everything else at 1e-5."""
+    from quadrotor_manipulator_mppi_b200.core import NativeSolver
+    rng = np.random.default_rng(2024)
+    K, T = 128, 10
+    s = NativeSolver(native.MODEL_ARM7, n_samples=K, n_horizon=T)
+    worst, n_sing = 0.0, 0
+    for trial in range(24):
+        q = rng.uniform(-3.0, 3.0, 7).astype(np.float32)
+        qd = rng.uniform(-0.5, 0.5, 7).astype(np.float32)
+        quat = rng.standard_normal(4); quat /= np.linalg.norm(quat)
+        base = np.concatenate([rng.uniform(-1, 1, 3), quat]).astype(np.float32)
+        tq = rng.standard_normal(4).astype(np.float32)
+        tp = rng.uniform(-1, 1, 3).astype(np.float32)
+        if trial >= 20:
+            # put the target orientation ~90 degrees of pitch away from the current end-effector orientation
+            R_ee = (oracle.xyzquat_to_matrix(base).astype(np.float64) @ oracle.fk(q).astype(np.float64))[:3, :3]
+            ang = np.pi / 2 - 1e-4 * (trial - 19)
+            Ry = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]])
+            Rt = R_ee @ Ry
+            w = np.sqrt(max(1e-12, 1 + np.trace(Rt))) / 2
+            tq = np.array([(Rt[2, 1] - Rt[1, 2]) / (4 * w), (Rt[0, 2] - Rt[2, 0]) / (4 * w), (Rt[1, 0] - Rt[0, 1]) / (4 * w), w], np.float32)
+        s.set_state(np.concatenate([q, qd, base]))
+        s.set_target(pos=tp, quat=tq)
+        noise = _rand_noise(T, K, (0.1,) * 7, 1000 + trial)
+        s.step(s.prepare_noise(noise))
+        S = s.costs.cpu().numpy()
+        want = oracle.arm_costs(noise, np.zeros((T, 7), np.float32), q, qd, base, target_pos=tp, target_quat=tq)
+        err = rel_inf(S, want)
+        assert np.isfinite(S).all()
+        if trial >= 20:
+            n_sing += 1
+            assert err < 1e-3, (trial, err)
+        else:
+            worst = max(worst, err)
+            assert err < 1e-5, (trial, err)
+        s.u_prev = torch.zeros(T, 7)
+    print(f"worst regular rel err {worst:.2e}; {n_sing} near-singular targets within 1e-3")
+
+
+def test_degenerate_weights(oracle, native):
+    """lambda extremes: huge lambda -> uniform weights (update = mean noise); tiny lambda -> argmin sample's noise."""
+    from quadrotor_manipulator_mppi_b200.core import NativeSolver
+    K, T = 512, 12
+    state = np.array([0, 0, 2.1, 0, 0, 0], np.float32)
+    noise = _rand_noise(T, K, (30.0,) * 3, 77)
+    for lam in (1e9, 1e-6):
+        s = NativeSolver(native.MODEL_DRONE3, n_samples=K, n_horizon=T, lam=lam)
+        s.set_state(state)
+        out = s.step(s.prepare_noise(noise)).copy()
+        S = s.costs.cpu().numpy()
+        u = s.u_prev.cpu().numpy()
+        raw = noise.mean(axis=1) if lam > 1 else noise[:, int(S.argmin())]
+        want = oracle.savgol(raw.astype(np.float32), 5)
+        assert rel_inf(u, want) < 1e-4
+        ess = out[native.MPPI_OUT_ESS]
+        assert (abs(ess - K) < 1e-2 * K) if lam > 1 else (abs(ess - 1.0) < 1e-6)
