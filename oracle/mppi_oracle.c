@@ -686,8 +686,8 @@ int oracle_savgol(int T, int nu, const float *seq /*[T][nu]*/, int window, int p
 /* ------------------------------------------------------------------ counter-based noise */
 /* Philox4x32-10 (Salmon et al., SC'11; Random123 v1.x constants).  New in this build --
  * the reference samples with torch.randn (standard_normal_noise.py:24).  Addressing:
- *   counter = (k_global, t * n_chunks + chunk, step_lo, step_hi), key = (seed_lo, seed_hi)
- * yields the four normals for inputs 4*chunk .. 4*chunk+3 of sample k at horizon step t. */
+ *   counter = (k_global, t * n_calls + call, step_lo, step_hi), key = (seed_lo, seed_hi)
+ * yields the six normals for inputs 6*call .. 6*call+5 of sample k at horizon step t. */
 void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
 {
     uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
@@ -701,17 +701,30 @@ void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-/* Box-Muller on two 32-bit words, same bit recipe as the device code:
- *   u1 = 2 - as_float(0x3f800000 | x>>9)  in (0,1];   r = sqrt(-2 ln u1)
- *   th = (as_float(0x3f800000 | y>>9) - 1.5) * 2pi   in [-pi,pi); (r cos th, r sin th)  */
-static void box_muller(uint32_t x, uint32_t y, float *n0, float *n1)
+/* One call = 128 bits = six 21-bit uniforms (bits [21 i, 21 i + 21) of the little-endian word, placed in the top
+ * of a float mantissa: f in [1,2)) = three Box-Muller pairs, same bit recipe as the device code:
+ *   u1 = 2 - f_radius in (0,1];  r = sqrt(-2 ln u1);  th = (f_angle - 1.5) * 2pi in [-pi,pi);  (r cos th, r sin th) */
+static void uniforms6(const uint32_t r[4], float f[6])
 {
-    union { uint32_t u; float f; } b;
-    b.u = 0x3f800000u | (x >> 9);
-    float u1 = 2.0f - b.f;
+    const uint32_t M = 0x1FFFFFu;
+    uint32_t u[6];
+    u[0] = r[0] & M;
+    u[1] = ((r[0] >> 21) | (r[1] << 11)) & M;
+    u[2] = (r[1] >> 10) & M;
+    u[3] = ((r[1] >> 31) | (r[2] << 1)) & M;
+    u[4] = ((r[2] >> 20) | (r[3] << 12)) & M;
+    u[5] = (r[3] >> 9) & M;
+    for (int i = 0; i < 6; ++i) {
+        union { uint32_t u; float f; } b;
+        b.u = 0x3f800000u | (u[i] << 2);
+        f[i] = b.f;
+    }
+}
+static void box_muller(float f_radius, float f_angle, float *n0, float *n1)
+{
+    float u1 = 2.0f - f_radius;
     float r = sqrtf(-2.0f * logf(u1));
-    b.u = 0x3f800000u | (y >> 9);
-    float th = (b.f - 1.5f) * 6.28318530717958647692f;
+    float th = (f_angle - 1.5f) * 6.28318530717958647692f;
     *n0 = r * cosf(th);
     *n1 = r * sinf(th);
 }
@@ -719,7 +732,7 @@ static void box_muller(uint32_t x, uint32_t y, float *n0, float *n1)
 void oracle_philox_noise(int K, int T, int nu, long long k_offset, uint64_t seed, uint64_t step,
                          const float *sigma /*[nu]*/, float *noise /*[T][K][nu]*/)
 {
-    int nch = (nu + 3) / 4;
+    int nch = ((nu + 1) / 2 + 2) / 3;      /* Philox calls per (sample, step): three pairs per call */
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
 #pragma omp parallel for schedule(static)
     for (int t = 0; t < T; ++t)
@@ -728,12 +741,12 @@ void oracle_philox_noise(int K, int T, int nu, long long k_offset, uint64_t seed
                 uint32_t ctr[4] = {(uint32_t)(k_offset + k), (uint32_t)(t * nch + c),
                                    (uint32_t)step, (uint32_t)(step >> 32)};
                 uint32_t r[4];
-                float n[4];
+                float f[6], n[6];
                 oracle_philox4x32_10(ctr, key, r);
-                box_muller(r[0], r[1], &n[0], &n[1]);
-                box_muller(r[2], r[3], &n[2], &n[3]);
-                for (int j = 0; j < 4; ++j) {
-                    int i = 4 * c + j;
+                uniforms6(r, f);
+                for (int p = 0; p < 3; ++p) box_muller(f[2 * p], f[2 * p + 1], &n[2 * p], &n[2 * p + 1]);
+                for (int j = 0; j < 6; ++j) {
+                    int i = 6 * c + j;
                     if (i < nu) noise[((size_t)t * K + k) * nu + i] = sigma[i] * n[j];
                 }
             }

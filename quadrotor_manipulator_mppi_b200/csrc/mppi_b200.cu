@@ -344,7 +344,7 @@ mppi_status_t launch_weight(mppi_ctx *h, const float *d_noise, bool fuse, const 
                             float *d_out, cudaStream_t st, const P2PParams &X)
 {
     constexpr int NU = ModelNu<MODEL>::value;
-    constexpr int NCH = (NU + 3) / 4;
+    constexpr int NCH = philox_calls(NU);
     const int K = h->P.K, T = h->P.T;
     const size_t fin_floats = (size_t)2 * T * NU + NU;
     if (!d_noise) {
@@ -359,7 +359,7 @@ mppi_status_t launch_weight(mppi_ctx *h, const float *d_noise, bool fuse, const 
         if (blocks < 1) blocks = 1;
         const int chunk = (K + blocks - 1) / blocks;
         blocks = (K + chunk - 1) / chunk;
-        size_t smem_floats = (size_t)2 * kWeightTile + (size_t)R * TC * 4;
+        size_t smem_floats = (size_t)2 * kWeightTile + (size_t)R * TC * 6;
         if (smem_floats < fin_floats) smem_floats = fin_floats;
         weight_philox_kernel<MODEL><<<blocks, threads, smem_floats * sizeof(float), st>>>(
             h->P, h->dyn, h->d_cost, h->d_rho, chunk, h->d_fix, h->d_counter, h->d_wsum, fuse ? 1 : 0, d_u_nom, d_u_new, d_out, X);
@@ -539,7 +539,7 @@ mppi_status_t mppi_create(const mppi_config_t *cfg, mppi_handle_t *out)
     h->X.world = h->X_off.world = 1;
     h->num_sms = prop.multiProcessorCount;
     StepParams &P = h->P;
-    P.K = cfg->n_samples; P.T = cfg->n_horizon; P.nu = nu; P.nch = (nu + 3) / 4;
+    P.K = cfg->n_samples; P.T = cfg->n_horizon; P.nu = nu; P.nch = philox_calls(nu);
     P.k_offset = cfg->k_offset;
     P.seed_lo = (uint32_t)cfg->seed; P.seed_hi = (uint32_t)(cfg->seed >> 32);
     for (int r = 0; r < 10; ++r) {

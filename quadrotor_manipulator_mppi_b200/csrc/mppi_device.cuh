@@ -85,7 +85,7 @@ template <> struct ModelNu<MPPI_MODEL_WB11>   { static constexpr int value = 11;
 // ------------------------------------------------------------------------------------------
 // Counter-based noise: Philox4x32-10 + Box-Muller.  New in this build (the reference calls
 // torch.randn, S/sampling/standard_normal_noise.py:24).  Both the rollout pass and the
-// weighting pass call normal4() with the same (sample, step, chunk) address, so the noise
+// weighting pass derive the normals from the same (sample, step, call) address, so the noise
 // never has to exist in HBM; explicit _rn intrinsics keep the two call sites bit-identical
 // regardless of how the surrounding code is contracted into FMAs.
 // ------------------------------------------------------------------------------------------
@@ -104,12 +104,31 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, const uint32_t *rk)
 
 // Box-Muller: u1 = 2 - [1,2) in (0,1];  theta = ([1,2) - 1.5) * 2pi in [-pi,pi);  MUFU lg2 / sqrt / sin / cos.
 // r = sqrt(-2 ln u1) = sqrt(lg2(u1) * (-2 ln 2)); sqrt.approx maps 0 -> 0 (u1 == 1).
-// Two Box-Muller pairs at once in packed FP32x2: lane 0 from (x, y), lane 1 from (z, w).
-//   rc = (r0 cos th0, r1 cos th1) -> normals 0 and 2;   rs = (r0 sin th0, r1 sin th1) -> normals 1 and 3
-__device__ __forceinline__ void box_muller2(uint4 r4, f2 &rc, f2 &rs)
+// One Philox4x32-10 call yields 128 bits = SIX 21-bit uniforms (126 bits used) = three Box-Muller pairs =
+// six normals, so nu = 11 needs two calls per (sample, step) instead of three.  Uniform i is bits
+// [21 i, 21 i + 21) of the little-endian 128-bit word, placed in the top of a float mantissa: f in [1, 2)
+// with 2^-21 steps (radius up to sqrt(2*21*ln 2) = 5.4 sigma, angle step 3e-6 rad).
+constexpr uint32_t kU21 = 0x1FFFFFu;
+__device__ __forceinline__ void philox_uniforms6(uint4 r, float f[6])
 {
-    const f2 fu(__uint_as_float(0x3f800000u | (r4.x >> 9)), __uint_as_float(0x3f800000u | (r4.z >> 9)));
-    const f2 ft(__uint_as_float(0x3f800000u | (r4.y >> 9)), __uint_as_float(0x3f800000u | (r4.w >> 9)));
+    const uint32_t u0 = r.x & kU21;
+    const uint32_t u1 = __funnelshift_r(r.x, r.y, 21) & kU21;
+    const uint32_t u2 = (r.y >> 10) & kU21;
+    const uint32_t u3 = __funnelshift_r(r.y, r.z, 31) & kU21;
+    const uint32_t u4 = __funnelshift_r(r.z, r.w, 20) & kU21;
+    const uint32_t u5 = (r.w >> 9) & kU21;
+    f[0] = __uint_as_float(0x3f800000u | (u0 << 2)); f[1] = __uint_as_float(0x3f800000u | (u1 << 2));
+    f[2] = __uint_as_float(0x3f800000u | (u2 << 2)); f[3] = __uint_as_float(0x3f800000u | (u3 << 2));
+    f[4] = __uint_as_float(0x3f800000u | (u4 << 2)); f[5] = __uint_as_float(0x3f800000u | (u5 << 2));
+}
+// Number of Philox calls per (sample, step): pairs = ceil(nu / 2), three pairs per call.
+__host__ __device__ constexpr int philox_calls(int nu) { return ((nu + 1) / 2 + 2) / 3; }
+
+// Two Box-Muller pairs at once in packed FP32x2.  fu = radius uniforms, ft = angle uniforms, both in [1, 2):
+//   u1 = 2 - fu in (0, 1],  r = sqrt(-2 ln u1) = sqrt(lg2(u1) * (-2 ln 2))  (sqrt.approx maps 0 -> 0),
+//   theta = (ft - 1.5) * 2 pi in [-pi, pi);  rc = r cos(theta), rs = r sin(theta)       (MUFU lg2 / sqrt / sin / cos)
+__device__ __forceinline__ void box_muller2(f2 fu, f2 ft, f2 &rc, f2 &rs)
+{
     const f2 u1 = vadd(f2(2.0f), vneg(fu));
     const f2 th = vmul(vadd(ft, f2(-1.5f)), f2(kTwoPi));
     const f2 l2(__log2f(u1.v.x), __log2f(u1.v.y));
@@ -122,21 +141,32 @@ __device__ __forceinline__ void box_muller2(uint4 r4, f2 &rc, f2 &rs)
     rs = vmul(r, f2(s0, s1));
 }
 
-// Standard normals for inputs 4*chunk..4*chunk+3 of (global sample kg, horizon step t):
-// counter = (kg, t*nch + chunk, step_lo, step_hi), key = seed.  n02 = (normal 0, normal 2),
-// n13 = (normal 1, normal 3).
-__device__ __forceinline__ void normal4_pairs(uint32_t kg, uint32_t tc, uint32_t step_lo, uint32_t step_hi,
-                                              const uint32_t *rkeys, f2 &n02, f2 &n13)
+// The 12 uniforms of up to two calls for (global sample kg, horizon step t): call j has
+// counter = (kg, t * ncalls + j, step_lo, step_hi), key = seed.  Pair p = uniforms (2p, 2p+1) -> normals (2p, 2p+1).
+template <int NCALLS>
+__device__ __forceinline__ void philox_step_uniforms(uint32_t kg, uint32_t t, uint32_t step_lo, uint32_t step_hi,
+                                                     const uint32_t *rkeys, float f[6 * NCALLS])
 {
-    const uint4 r = philox4x32_10(make_uint4(kg, tc, step_lo, step_hi), rkeys);
-    box_muller2(r, n02, n13);
+#pragma unroll
+    for (int j = 0; j < NCALLS; ++j)
+        philox_uniforms6(philox4x32_10(make_uint4(kg, t * NCALLS + j, step_lo, step_hi), rkeys), f + 6 * j);
 }
-__device__ __forceinline__ void normal4(uint32_t kg, uint32_t tc, uint32_t step_lo, uint32_t step_hi,
-                                        const uint32_t *rkeys, float n[4])
+// Normals for inputs 4e .. 4e+3 (pairs 2e and 2e+1) as rc = (n[4e], n[4e+2]), rs = (n[4e+1], n[4e+3]).
+__device__ __forceinline__ void normals_quad(const float *f, int e, f2 &rc, f2 &rs)
 {
-    f2 n02, n13;
-    normal4_pairs(kg, tc, step_lo, step_hi, rkeys, n02, n13);
-    n[0] = n02.v.x; n[2] = n02.v.y; n[1] = n13.v.x; n[3] = n13.v.y;
+    box_muller2(f2(f[4 * e], f[4 * e + 2]), f2(f[4 * e + 1], f[4 * e + 3]), rc, rs);
+}
+// The six normals of ONE call (weighting pass / noise materialisation): n[2p], n[2p+1] from pair p.
+__device__ __forceinline__ void normal6(uint32_t kg, uint32_t tcall, uint32_t step_lo, uint32_t step_hi,
+                                        const uint32_t *rkeys, float n[6])
+{
+    float f[6];
+    philox_uniforms6(philox4x32_10(make_uint4(kg, tcall, step_lo, step_hi), rkeys), f);
+    f2 rc, rs;
+    box_muller2(f2(f[0], f[2]), f2(f[1], f[3]), rc, rs);
+    n[0] = rc.v.x; n[1] = rs.v.x; n[2] = rc.v.y; n[3] = rs.v.y;
+    box_muller2(f2(f[4], f[4]), f2(f[5], f[5]), rc, rs);
+    n[4] = rc.v.x; n[5] = rs.v.x;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -145,12 +145,15 @@ rollout_cost_kernel(const __grid_constant__ StepParams P, const __grid_constant_
         // as the pairs (4c, 4c+2) and (4c+1, 4c+3).
         f2 a02[NCH], a13[NCH];
         if constexpr (NOISE == 2) mbar_wait(&s_full[t % kNoiseStages], (t / kNoiseStages) & 1);
+        float unif[6 * philox_calls(NU)];
+        if constexpr (PHILOX)
+            philox_step_uniforms<philox_calls(NU)>(kg, static_cast<uint32_t>(t), D.step_lo, D.step_hi, P.rkeys, unif);
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
             const int i0 = 4 * c, i1 = 4 * c + 1, i2 = 4 * c + 2, i3 = 4 * c + 3;
             if constexpr (PHILOX) {
                 f2 n02, n13;
-                normal4_pairs(kg, static_cast<uint32_t>(t * NCH + c), D.step_lo, D.step_hi, P.rkeys, n02, n13);
+                normals_quad(unif, c, n02, n13);
                 a02[c] = vmul(f2(P.sigma[i0], i2 < NU ? P.sigma[i2] : 0.f), n02);
                 a13[c] = vmul(f2(i1 < NU ? P.sigma[i1] : 0.f, i3 < NU ? P.sigma[i3] : 0.f), n13);
             } else if constexpr (NOISE == 1) {
@@ -569,7 +572,7 @@ weight_philox_kernel(const __grid_constant__ StepParams P, const __grid_constant
                      const float *u_nom, float *u_new, float *out, const __grid_constant__ P2PParams X)
 {
     constexpr int NU = ModelNu<MODEL>::value;
-    constexpr int NCH = (NU + 3) / 4;
+    constexpr int NCH = philox_calls(NU);             // one thread per (horizon step, Philox call): six normals each
     extern __shared__ __align__(16) float s_dyn[];      // [kWeightTile] weights | [kWeightTile] indices | reduction / finalize scratch
     float *s_w = s_dyn;
     int *s_idx = reinterpret_cast<int *>(s_dyn + kWeightTile);
@@ -588,7 +591,7 @@ weight_philox_kernel(const __grid_constant__ StepParams P, const __grid_constant
     const int k0 = blockIdx.x * chunk;
     const int k1 = min(P.K, k0 + chunk);
 
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float eta = 0.f, eta2 = 0.f;
 
     for (int base = k0; base < k1; base += kWeightTile) {
@@ -627,11 +630,11 @@ weight_philox_kernel(const __grid_constant__ StepParams P, const __grid_constant
         if (worker) {
             for (int j = r; j < n_nz; j += R) {
                 const float w = s_w[j];
-                float n4[4];
-                normal4(static_cast<uint32_t>(P.k_offset + base + s_idx[j]), static_cast<uint32_t>(tc),
-                        D.step_lo, D.step_hi, P.rkeys, n4);
+                float n6[6];
+                normal6(static_cast<uint32_t>(P.k_offset + base + s_idx[j]), static_cast<uint32_t>(tc),
+                        D.step_lo, D.step_hi, P.rkeys, n6);
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj) acc[jj] = fmaf(w, n4[jj], acc[jj]);      // sigma is applied once, after the reduction
+                for (int jj = 0; jj < 6; ++jj) acc[jj] = fmaf(w, n6[jj], acc[jj]);      // sigma is applied once, after the reduction
             }
         }
     }
@@ -642,7 +645,7 @@ weight_philox_kernel(const __grid_constant__ StepParams P, const __grid_constant
     __syncthreads();
     if (worker) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) s_red[(r * TC + tc) * 4 + j] = acc[j];
+        for (int j = 0; j < 6; ++j) s_red[(r * TC + tc) * 6 + j] = acc[j];
     }
     __syncthreads();
     // Block sums go into 64-bit FIXED-POINT accumulators with integer atomics: integer addition is
@@ -652,11 +655,11 @@ weight_philox_kernel(const __grid_constant__ StepParams P, const __grid_constant
     const int row = P.T * NU + 2;
     if (tid < TC) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (4 * c + j < NU) {
+        for (int j = 0; j < 6; ++j) {
+            if (6 * c + j < NU) {
                 float v = 0.f;
-                for (int rr = 0; rr < R; ++rr) v += s_red[(rr * TC + tc) * 4 + j];
-                if (v != 0.f) atomicAdd(fix + t * NU + 4 * c + j, static_cast<unsigned long long>(__float2ll_rn(v * kFixScale)));
+                for (int rr = 0; rr < R; ++rr) v += s_red[(rr * TC + tc) * 6 + j];
+                if (v != 0.f) atomicAdd(fix + t * NU + 6 * c + j, static_cast<unsigned long long>(__float2ll_rn(v * kFixScale)));
             }
         }
     }
@@ -793,7 +796,7 @@ __global__ void __launch_bounds__(256)
 generate_noise_kernel(const __grid_constant__ StepParams P, uint32_t step_lo, uint32_t step_hi,
                       float *__restrict__ noise)
 {
-    constexpr int NCH = (NU + 3) / 4;
+    constexpr int NCH = philox_calls(NU);
     const long long n = static_cast<long long>(P.T) * P.K * NCH;
     for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < n;
          idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -801,12 +804,11 @@ generate_noise_kernel(const __grid_constant__ StepParams P, uint32_t step_lo, ui
         const long long tk = idx / NCH;
         const int k = static_cast<int>(tk % P.K);
         const int t = static_cast<int>(tk / P.K);
-        float n4[4];
-        normal4(static_cast<uint32_t>(P.k_offset + k), static_cast<uint32_t>(t * NCH + c), step_lo, step_hi,
-                P.rkeys, n4);
+        float n6[6];
+        normal6(static_cast<uint32_t>(P.k_offset + k), static_cast<uint32_t>(t * NCH + c), step_lo, step_hi, P.rkeys, n6);
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (4 * c + j < NU) noise[(static_cast<size_t>(t) * P.K + k) * NU + 4 * c + j] = __fmul_rn(P.sigma[4 * c + j], n4[j]);
+        for (int j = 0; j < 6; ++j)
+            if (6 * c + j < NU) noise[(static_cast<size_t>(t) * P.K + k) * NU + 6 * c + j] = __fmul_rn(P.sigma[6 * c + j], n6[j]);
     }
 }
 
