@@ -108,7 +108,7 @@ def cpu_baseline(model: str, K: int, T: int, budget_s: float, n_steps: int = 1) 
     """Time the oracle port on a bounded sample sized to ~budget_s of CPU work in total."""
     probe_K = min(K, 1024)
     step, orc = oracle_step_fn(model, probe_K, T)
-    threads = orc.set_threads(0)
+    threads = orc.set_threads(len(os.sched_getaffinity(0)))     # all usable host cores, whatever OMP_NUM_THREADS says
     step()
     t0 = time.perf_counter()
     step()
@@ -137,7 +137,8 @@ def run_reference(args):
     total = args.steps + args.warmup
     probe_K = min(K, 1024)
     step, orc = oracle_step_fn(args.model, probe_K, T)
-    threads = orc.set_threads(0)
+    # torchrun exports OMP_NUM_THREADS=1: the CPU arm must still use every usable host core
+    threads = orc.set_threads(len(os.sched_getaffinity(0)))
     step()
     t0 = time.perf_counter()
     step()
