@@ -127,6 +127,49 @@ def cpu_baseline(model: str, K: int, T: int, budget_s: float, n_steps: int = 1) 
             "ms_per_step_sample": med * 1e3}
 
 
+def cpu_baseline_torch(model: str, K: int, T: int, budget_s: float = 6.0) -> dict:
+    """Time oracle/torch_port.py -- the eager-PyTorch restatement that replays the reference's aten op sequence
+    (the reference's own CPU PyTorch path, BASELINE.json north_star) -- on a bounded sample, all host cores."""
+    import torch
+    from oracle import torch_port as tp
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    nu = MODELS[model]["nu"]
+    st = torch.from_numpy(synthetic_state(model))
+    sig = torch.tensor({"wb": [30 * 20.2, 1, 1, 1] + [0.1] * 7, "arm": [0.1] * 7, "drone": [30.0] * 3, "quad": [30 * 14.7, 1, 1, 1]}[model])
+
+    def make(Ks):
+        u = torch.from_numpy(nominal_controls(model, T))
+
+        def step():
+            noise = torch.randn(Ks, T, nu) * sig              # standard_normal_noise.py:24
+            if model == "wb":
+                return tp.wb_step(noise, u, st[:12], st[12:19], st[19:26])
+            if model == "arm":
+                return tp.arm_step(noise, u, st[:7], st[7:14], st[14:21])
+            if model == "drone":
+                return tp.drone_step(noise, u, st[:3], st[3:6])
+            return tp.quad_step(noise, u, st)
+        return step
+    probe = min(K, 512)
+    step = make(probe)
+    step()
+    t0 = time.perf_counter()
+    step()
+    per_sample = (time.perf_counter() - t0) / probe
+    Ks = int(min(K, max(probe, budget_s / 2 / max(per_sample, 1e-9))))
+    step = make(Ks)
+    times = []
+    for _ in range(2):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    med = float(np.median(times))
+    return {"value": Ks * T / med, "unit": "rollout-steps/s", "cores": cores, "kind": "port",
+            "sample": f"{Ks} of {K} samples x T={T}, 2 steps, oracle/torch_port.py (eager PyTorch CPU, replays the reference's "
+                      f"aten op sequence, torch.randn noise), torch threads = {cores}", "ms_per_step_sample": med * 1e3}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -469,9 +512,10 @@ def run_native(args):
         e2e = {"value": K * T * n_e2e / e2e_s, "unit": "rollout-steps/s", "h2d_bytes_per_step": int(st.size * 4),
                "d2h_bytes_per_step": int(_native.MPPI_OUT_FLOATS * 4), "ms_per_step": e2e_s / n_e2e * 1e3, "steps": n_e2e}
 
-    cpu = None
+    cpu = cpu_torch = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(args.model, K, T, budget_s=12.0, n_steps=2)
+        cpu_torch = cpu_baseline_torch(args.model, K, T)
 
     if rank == 0:
         line = {"metric": "rollout_steps_per_s", "value": value, "unit": "rollout-steps/s", "n_gpus": n_gpus,
@@ -486,7 +530,7 @@ def run_native(args):
                 "latency_ms": {"p50": float(np.percentile(step_ms, 50)), "p99": float(np.percentile(step_ms, 99)),
                                "max": float(step_ms.max()), "host_wall_ms_per_step_incl_flush": wall / args.steps * 1e3},
                 "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
-                "cpu_baseline": cpu}
+                "cpu_baseline": cpu, "cpu_baseline_torch": cpu_torch}
         if coll:
             line["collectives"] = coll
         print(json.dumps(line))
