@@ -282,8 +282,9 @@ size_t tuned_rollout_smem(mppi_ctx *h, KernelT kernel, int threads, int grid, si
     auto cost = [&](int o) { return (long long)((grid + (long long)h->num_sms * o - 1) / ((long long)h->num_sms * o)) * o; };
     int best_o = omax;
     long long best = cost(omax);
-    const int omin = omax > 6 ? omax - 3 : (omax + 1) / 2;
-    for (int o = omax - 1; o >= omin && o >= 2; --o)
+    // only one step below the register-limited residency, and never below 4 blocks (16 warps) per SM:
+    // under that the kernel turns latency-bound and the wave model no longer holds
+    for (int o = omax - 1; o >= omax - 1 && o >= 4; --o)
         if (cost(o) < best) { best = cost(o); best_o = o; }
     if (best_o == omax) return smem_needed;
     size_t pad = (size_t)(228 * 1024) / best_o - 1024 - 256;      // 1 KB per block is reserved by the driver

@@ -42,8 +42,10 @@ __host__ __device__ constexpr int pairB(int i) { return i == 0 ? 2 : i == 1 ? 3 
 //            step, kNoiseStages deep; needs K*nu % 4 == 0 and a 16-byte aligned tensor).
 constexpr int kNoiseStages = 4;
 
+// 4 blocks/SM (<= 128 registers): measured best -- with a 72-register cap (7 blocks/SM) ptxas cannot interleave the
+// Philox multiplies with the FK arithmetic and the FMA pipe stalls more (0.421 -> 0.393 ms on the bench case).
 template <int MODEL, int NOISE, bool BAKED, bool EXTRA>
-__global__ void __launch_bounds__(kRolloutThreads, 7)
+__global__ void __launch_bounds__(kRolloutThreads, 4)
 rollout_cost_kernel(const __grid_constant__ StepParams P, const __grid_constant__ DynBlock D,
                     const float *__restrict__ u_nom, const float *__restrict__ noise,
                     float *__restrict__ cost_out, int32_t *__restrict__ rho_enc,
