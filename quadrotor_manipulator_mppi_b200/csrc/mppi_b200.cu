@@ -263,6 +263,7 @@ mppi_status_t set_chain_impl(mppi_ctx *h, int n, const int32_t *types, const flo
         for (int i = 0; i < 3; ++i) baked = baked && std::fabs(ch.t[j][i] - FkKinova::t[j][i]) < 1e-6f;
     }
     h->baked_fk = baked;
+    ch.baked = baked ? 1 : 0;
     if (nrev != 7) return fail(h, MPPI_ERR_UNSUPPORTED, "the arm kernels are built for 7 revolute joints");
     h->P.chain = ch;
     return MPPI_OK;

@@ -24,6 +24,7 @@ struct ChainDev {
     float t[MPPI_MAX_JOINTS + 1][3];
     int n;               // revolute joints
     int last_identity;   // Cn == I (true for the j2s7s300_link_7 end link)
+    int baked;           // equals the compile-time FkKinova tables (fk_tables_gen.cuh)
 };
 
 // Everything that is fixed for a handle; passed by value as a kernel parameter (constant bank).

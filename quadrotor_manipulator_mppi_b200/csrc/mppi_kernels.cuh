@@ -357,8 +357,10 @@ __device__ void finalize_block(const StepParams &P, const DynBlock &D, const flo
         u_new[j] = v;
     }
     __syncthreads();
+    // The epilogue is split over three warps so that its serial pieces overlap (this block is the tail of the step):
+    //   warp 0 lane 0: controller outputs;  warp 1 lane 0: check_reach FK;  warp 2: u0 / statistics.
+    const float dt = P.dt;
     if (out != nullptr && threadIdx.x == 0) {
-        const float dt = P.dt;
         if constexpr (MODEL == MPPI_MODEL_DRONE3) {
             for (int i = 0; i < 3; ++i) {
                 out[i] = D.state[i] + D.state[3 + i] * dt + 0.5f * un[i] * P.dt2;      // drone_mppi.py:170
@@ -372,7 +374,7 @@ __device__ void finalize_block(const StepParams &P, const DynBlock &D, const flo
         } else {
             QuadState<float> qs;
             quad_load(qs, D.state);
-            quad_advance(qs, un[0], un[1], un[2], un[3], dt, P.quad);
+            quad_advance<false>(qs, un[0], un[1], un[2], un[3], dt, P.quad);
             const int o = (MODEL == MPPI_MODEL_WB11) ? MPPI_OUT_BASE : 0;
             for (int i = 0; i < 3; ++i) { out[o + i] = qs.p[i]; out[o + 3 + i] = qs.rpy[i]; out[o + 6 + i] = qs.v[i]; out[o + 9 + i] = qs.w[i]; }
             if constexpr (MODEL == MPPI_MODEL_WB11) {
@@ -382,10 +384,14 @@ __device__ void finalize_block(const StepParams &P, const DynBlock &D, const flo
                 }
             }
         }
-        if constexpr (MODEL == MPPI_MODEL_ARM7 || MODEL == MPPI_MODEL_WB11) {
+    }
+    if constexpr (MODEL == MPPI_MODEL_ARM7 || MODEL == MPPI_MODEL_WB11) {
+        if (out != nullptr && threadIdx.x == 32) {
             // check_reach (mppi.py:95-120): L1 position error of FK(base, qdes) to the target
+            constexpr int A0 = (MODEL == MPPI_MODEL_WB11) ? 4 : 0, Q0 = (MODEL == MPPI_MODEL_WB11) ? 12 : 0;
             float cq[7], sq[7], R[9], p[3];
-            for (int i = 0; i < 7; ++i) sincos_pi(out[i], sq[i], cq[i]);
+            for (int i = 0; i < 7; ++i)
+                sincos_pi(D.state[Q0 + i] + u0_old[A0 + i] * dt + 0.5f * un[A0 + i] * dt * dt, sq[i], cq[i]);
             if constexpr (MODEL == MPPI_MODEL_ARM7) {
                 quat_matrix(&D.state[14], R);
                 p[0] = D.state[14]; p[1] = D.state[15]; p[2] = D.state[16];
@@ -395,15 +401,24 @@ __device__ void finalize_block(const StepParams &P, const DynBlock &D, const flo
                 rpy_matrix(sr, cr, sp, cp, sy, cy, R);
                 p[0] = D.state[0]; p[1] = D.state[1]; p[2] = D.state[2];
             }
-            compose_const(R, p, P.chain.R[0], P.chain.t[0]);
-            fk_chain<7>(P.chain, cq, sq, R, p);
-            out[MPPI_OUT_REACH] = fabsf(p[0] - D.target_pos[0]) + fabsf(p[1] - D.target_pos[1]) + fabsf(p[2] - D.target_pos[2]);
+            Pose3 Tp = pose3_from(R, p);
+            if (P.chain.baked) {
+                pose3_compose_tab<FkKinova, 0>(Tp);
+                pose3_fk_tab<FkKinova>(cq, sq, Tp);
+            } else {
+                pose3_compose_const(Tp, P.chain.R[0], P.chain.t[0]);
+                pose3_fk_chain<7>(P.chain, cq, sq, Tp);
+            }
+            out[MPPI_OUT_REACH] = fabsf(Tp.pxy.v.x - D.target_pos[0]) + fabsf(Tp.pxy.v.y - D.target_pos[1]) + fabsf(Tp.pz - D.target_pos[2]);
         }
-        for (int i = 0; i < NU; ++i) { out[MPPI_OUT_U0_NEW + i] = un[i]; out[MPPI_OUT_U0_OLD + i] = u0_old[i]; }
-        out[MPPI_OUT_RHO] = decode_ordered(*rho_enc);
-        out[MPPI_OUT_ETA] = eta;
-        out[MPPI_OUT_ESS] = eta * eta / eta2;
-        out[MPPI_OUT_STEP] = static_cast<float>(D.step_lo & 0xffffffu);
+    }
+    if (out != nullptr && threadIdx.x >= 64 && threadIdx.x < 96) {
+        const int l = threadIdx.x - 64;
+        if (l < NU) { out[MPPI_OUT_U0_NEW + l] = un[l]; out[MPPI_OUT_U0_OLD + l] = u0_old[l]; }
+        if (l == 16) out[MPPI_OUT_RHO] = decode_ordered(*rho_enc);
+        if (l == 17) out[MPPI_OUT_ETA] = eta;
+        if (l == 18) out[MPPI_OUT_ESS] = eta * eta / eta2;
+        if (l == 19) out[MPPI_OUT_STEP] = static_cast<float>(D.step_lo & 0xffffffu);
     }
     __syncthreads();
     if (threadIdx.x == 0) *rho_enc = kRhoInit;          // re-arm the minimum for the next step
