@@ -135,8 +135,10 @@ const char *mppi_last_error(mppi_handle_t h);   /* h may be NULL: last create() 
 int32_t mppi_abi_version(void);
 
 /* URDFparser chain (robot/urdfparser.py:110-163) as constants: for each joint of the chain
- * from the absolute root to the end link, in order: type (0 fixed, 1 revolute/continuous),
- * origin xyz[3], origin rpy[3], axis[3].  The library folds it to  C0 Rz(q1) C1 ... Rz(qn) Cn.
+ * from the absolute root to the end link, in order: type (0 fixed, 1 revolute/continuous,
+ * 2 prismatic -- robot/transformation_matrix.py:38-55), origin xyz[3], origin rpy[3], axis[3].
+ * The library folds it to  C0 J1(q1) C1 ... Jn(qn) Cn  with Ji = Rz(qi) or Trans(0,0,qi); the
+ * chain must have exactly 7 actuated joints (the arm models' inputs).
  * mppi_create() pre-loads the j2s7s300 chain of aerial_manipulator_gpu.urdf.            */
 mppi_status_t mppi_set_chain(mppi_handle_t h, int32_t n_chain_joints, const int32_t *types,
                              const float *xyz, const float *rpy, const float *axis);

@@ -12,9 +12,10 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
-LIB = os.path.join(PKG, "libmppi_b200.so")
+LIB = os.environ.get("MPPI_B200_LIB") or os.path.join(PKG, "libmppi_b200.so")     # override: a prebuilt library
 SOURCES = [os.path.join(CSRC, "mppi_b200.cu")]
 HEADERS = [os.path.join(CSRC, "mppi_device.cuh"), os.path.join(CSRC, "mppi_kernels.cuh"),
+           os.path.join(CSRC, "mppi_vec.cuh"), os.path.join(CSRC, "fk_tables_gen.cuh"),
            os.path.join(ROOT, "include", "mppi_b200.h")]
 
 

@@ -233,8 +233,9 @@ mppi_status_t set_chain_impl(mppi_ctx *h, int n, const int32_t *types, const flo
     for (int j = 0; j < n; ++j) {
         C = mat4_mul(C, origin_transform(xyz + 3 * j, rpy + 3 * j));
         if (types[j] == 0) continue;
-        if (types[j] != 1) return fail(h, MPPI_ERR_UNSUPPORTED, "only fixed and revolute/continuous joints are supported");
-        if (nrev >= MPPI_MAX_JOINTS) return fail(h, MPPI_ERR_INVALID_ARG, "too many revolute joints");
+        if (types[j] != 1 && types[j] != 2) return fail(h, MPPI_ERR_INVALID_ARG, "joint type must be 0 (fixed), 1 (revolute/continuous) or 2 (prismatic)");
+        if (nrev >= MPPI_MAX_JOINTS) return fail(h, MPPI_ERR_INVALID_ARG, "too many actuated joints");
+        if (types[j] == 2) ch.prismatic |= 1 << nrev;      // Trans(axis q) = A Trans(0,0,q) A^T: same fold as a rotation about the axis
         double ax[3] = {axis[3 * j], axis[3 * j + 1], axis[3 * j + 2]};
         double nrm = std::sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);
         if (nrm < 1e-12) { ax[0] = 1; ax[1] = 0; ax[2] = 0; nrm = 1; }    // transformation_matrix.py:63-66
@@ -257,14 +258,14 @@ mppi_status_t set_chain_impl(mppi_ctx *h, int n, const int32_t *types, const flo
     for (int i = 0; i < 16; ++i) dev = std::fmax(dev, std::fabs(C.m[i] - I.m[i]));
     ch.n = nrev;
     ch.last_identity = dev < 1e-12;
-    bool baked = (nrev == FkKinova::kJoints);
+    bool baked = (nrev == FkKinova::kJoints) && ch.prismatic == 0;
     for (int j = 0; baked && j <= nrev; ++j) {
         for (int i = 0; i < 9; ++i) baked = baked && std::fabs(ch.R[j][i] - FkKinova::R[j][i]) < 1e-6f;
         for (int i = 0; i < 3; ++i) baked = baked && std::fabs(ch.t[j][i] - FkKinova::t[j][i]) < 1e-6f;
     }
     h->baked_fk = baked;
     ch.baked = baked ? 1 : 0;
-    if (nrev != 7) return fail(h, MPPI_ERR_UNSUPPORTED, "the arm kernels are built for 7 revolute joints");
+    if (nrev != 7) return fail(h, MPPI_ERR_UNSUPPORTED, "the arm kernels are built for 7 actuated joints");
     h->P.chain = ch;
     return MPPI_OK;
 }
@@ -309,7 +310,11 @@ mppi_status_t launch_rollout_variant(mppi_ctx *h, int variant, const float *d_u_
     auto kernel = rollout_cost_kernel<MODEL, NOISE, BAKED, EXTRA>;
     const int grid = (h->P.K + kRolloutThreads - 1) / kRolloutThreads;
     size_t &tuned = h->rollout_smem[variant];
-    if (tuned == 0) tuned = tuned_rollout_smem(h, kernel, kRolloutThreads, grid, smem);
+    if (tuned == 0) {
+        if (smem > 48 * 1024)       // long horizons / wide noise tiles: opt in to the large dynamic shared memory carve-out
+            MPPI_CUDA(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tuned = tuned_rollout_smem(h, kernel, kRolloutThreads, grid, smem);
+    }
     kernel<<<grid, kRolloutThreads, tuned, st>>>(h->P, h->dyn, d_u_nom, d_noise, d_cost, h->d_rho, h->d_qtraj);
     MPPI_CUDA(h, cudaGetLastError());
     return MPPI_OK;

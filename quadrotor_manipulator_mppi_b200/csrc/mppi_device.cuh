@@ -25,6 +25,7 @@ struct ChainDev {
     int n;               // revolute joints
     int last_identity;   // Cn == I (true for the j2s7s300_link_7 end link)
     int baked;           // equals the compile-time FkKinova tables (fk_tables_gen.cuh)
+    int prismatic;       // bit j: joint j slides along its (folded) z axis instead of rotating about it
 };
 
 // Everything that is fixed for a handle; passed by value as a kernel parameter (constant bank).
@@ -442,11 +443,16 @@ __device__ __forceinline__ void pose3_fk_tab(const float *cq, const float *sq, P
     }
 }
 template <int NJ>
-__device__ __forceinline__ void pose3_fk_chain(const ChainDev &ch, const float *cq, const float *sq, Pose3 &T)
+__device__ __forceinline__ void pose3_fk_chain(const ChainDev &ch, const float *qv, const float *cq, const float *sq, Pose3 &T)
 {
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
-        pose3_rotate_z(T, cq[j], sq[j]);
+        if ((ch.prismatic >> j) & 1) {     // S/robot/transformation_matrix.py:38-55: translate by q along the joint axis (uniform branch)
+            T.pxy = vfma(T.c2, f2(qv[j]), T.pxy);
+            T.pz = fmaf(T.r2, qv[j], T.pz);
+        } else {
+            pose3_rotate_z(T, cq[j], sq[j]);
+        }
         if (j + 1 < NJ || !ch.last_identity) pose3_compose_const(T, ch.R[j + 1], ch.t[j + 1]);
     }
 }

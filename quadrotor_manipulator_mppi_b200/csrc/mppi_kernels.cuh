@@ -14,7 +14,11 @@
 
 namespace mppi {
 
-constexpr int kRolloutThreads = 128;
+#ifndef MPPI_ROLLOUT_THREADS
+#define MPPI_ROLLOUT_THREADS 128
+#define MPPI_ROLLOUT_MINB 4
+#endif
+constexpr int kRolloutThreads = MPPI_ROLLOUT_THREADS;
 constexpr int kWeightTile = 2048;
 constexpr float kFixScale = 8589934592.0f;   // 2^33: fixed-point scale of the weighting accumulators       // samples whose weights are staged in smem at a time
 
@@ -45,7 +49,7 @@ constexpr int kNoiseStages = 4;
 // 4 blocks/SM (<= 128 registers): measured best -- with a 72-register cap (7 blocks/SM) ptxas cannot interleave the
 // Philox multiplies with the FK arithmetic and the FMA pipe stalls more (0.421 -> 0.393 ms on the bench case).
 template <int MODEL, int NOISE, bool BAKED, bool EXTRA>
-__global__ void __launch_bounds__(kRolloutThreads, 4)
+__global__ void __launch_bounds__(kRolloutThreads, MPPI_ROLLOUT_MINB)
 rollout_cost_kernel(const __grid_constant__ StepParams P, const __grid_constant__ DynBlock D,
                     const float *__restrict__ u_nom, const float *__restrict__ noise,
                     float *__restrict__ cost_out, int32_t *__restrict__ rho_enc,
@@ -285,8 +289,14 @@ rollout_cost_kernel(const __grid_constant__ StepParams P, const __grid_constant_
                 if constexpr (BAKED) pose3_compose_tab<FkKinova, 0>(Tp);
                 else pose3_compose_const(Tp, P.chain.R[0], P.chain.t[0]);
             }
-            if constexpr (BAKED) pose3_fk_tab<FkKinova>(cq, sq, Tp);
-            else pose3_fk_chain<7>(P.chain, cq, sq, Tp);
+            if constexpr (BAKED) {
+                pose3_fk_tab<FkKinova>(cq, sq, Tp);
+            } else {
+                float qv[7];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { qv[pairA(i)] = qp[i].v.x; if (pairB(i) >= 0) qv[pairB(i)] = qp[i].v.y; }
+                pose3_fk_chain<7>(P.chain, qv, cq, sq, Tp);
+            }
             float pos, ori;
             pose3_terms(Tp, D, pos, ori);
             // S/cost/cost_manager.py:30-33,78-89
@@ -389,9 +399,11 @@ __device__ void finalize_block(const StepParams &P, const DynBlock &D, const flo
         if (out != nullptr && threadIdx.x == 32) {
             // check_reach (mppi.py:95-120): L1 position error of FK(base, qdes) to the target
             constexpr int A0 = (MODEL == MPPI_MODEL_WB11) ? 4 : 0, Q0 = (MODEL == MPPI_MODEL_WB11) ? 12 : 0;
-            float cq[7], sq[7], R[9], p[3];
-            for (int i = 0; i < 7; ++i)
-                sincos_pi(D.state[Q0 + i] + u0_old[A0 + i] * dt + 0.5f * un[A0 + i] * dt * dt, sq[i], cq[i]);
+            float qv[7], cq[7], sq[7], R[9], p[3];
+            for (int i = 0; i < 7; ++i) {
+                qv[i] = D.state[Q0 + i] + u0_old[A0 + i] * dt + 0.5f * un[A0 + i] * dt * dt;
+                sincos_pi(qv[i], sq[i], cq[i]);
+            }
             if constexpr (MODEL == MPPI_MODEL_ARM7) {
                 quat_matrix(&D.state[14], R);
                 p[0] = D.state[14]; p[1] = D.state[15]; p[2] = D.state[16];
@@ -407,7 +419,7 @@ __device__ void finalize_block(const StepParams &P, const DynBlock &D, const flo
                 pose3_fk_tab<FkKinova>(cq, sq, Tp);
             } else {
                 pose3_compose_const(Tp, P.chain.R[0], P.chain.t[0]);
-                pose3_fk_chain<7>(P.chain, cq, sq, Tp);
+                pose3_fk_chain<7>(P.chain, qv, cq, sq, Tp);
             }
             out[MPPI_OUT_REACH] = fabsf(Tp.pxy.v.x - D.target_pos[0]) + fabsf(Tp.pxy.v.y - D.target_pos[1]) + fabsf(Tp.pz - D.target_pos[2]);
         }

@@ -427,10 +427,13 @@ def _chain_variant(oracle, which):
     elif which == "tilted_axes":     # non-z joint axes and non-right-angle origins: exercises the axis alignment fold
         axis[2] = [0, 1, 0]; axis[4] = [1, 0, 0]; axis[6] = [0.6, 0.0, 0.8]
         rpy[3] = [0.3, -0.2, 0.5]; xyz[5] = [0.01, 0.2, -0.03]
+    elif which == "prismatic":       # two sliding joints (one about a tilted axis): urdfparser.py:152-157
+        jt[3] = 2; jt[6] = 2
+        axis[3] = [0, 0, 1]; axis[6] = [0.0, 0.6, 0.8]
     return oracle.Chain(jt, qi, xyz, rpy, axis)
 
 
-@pytest.mark.parametrize("which", ["end_effector", "tilted_axes"])
+@pytest.mark.parametrize("which", ["end_effector", "tilted_axes", "prismatic"])
 def test_generic_chain_against_oracle(which, oracle, native):
     """other end links / arms work through mppi_set_chain without editing CUDA."""
     from quadrotor_manipulator_mppi_b200.core import NativeSolver
@@ -443,14 +446,20 @@ def test_generic_chain_against_oracle(which, oracle, native):
     base = np.array([0.3, -0.2, 1.7, 0.0499792, -0.0998334, 0.1494381, 0.9824485], np.float32)
     s.set_state(np.concatenate([q, qd, base]))
     noise = _rand_noise(T, K, (0.1,) * 7, 17)
-    s.step(s.prepare_noise(noise))
+    out = s.step(s.prepare_noise(noise)).copy()
     S = s.costs.cpu().numpy()
     want = oracle.arm_costs(noise, np.zeros((T, 7), np.float32), q, qd, base, chain=ch)
     assert rel_inf(S, want) < 5e-6
+    # check_reach (mppi.py:95-120) runs through the same chain: L1 distance of FK(base, qdes) to the target
+    Tw = oracle.xyzquat_to_matrix(base).astype(np.float64) @ oracle.fk(out[0:7], ch).astype(np.float64)
+    reach = np.abs(Tw[:3, 3] - np.asarray(oracle.ARM_TARGET_POS)).sum()
+    assert out[native.MPPI_OUT_REACH] == pytest.approx(reach, abs=2e-5)
     # and the baked chain really is a different answer (the test would be vacuous otherwise)
     assert rel_inf(want, oracle.arm_costs(noise, np.zeros((T, 7), np.float32), q, qd, base)) > 1e-3
-    with pytest.raises(native.MppiError):        # prismatic joints are rejected, not silently mis-handled
-        s.set_chain([0, 2, 1, 1, 1, 1, 1, 1], ch.xyz[:8], ch.rpy[:8], ch.axis[:8])
+    with pytest.raises(native.MppiError):        # unknown joint types and wrong joint counts are rejected
+        s.set_chain([0, 3, 1, 1, 1, 1, 1, 1], ch.xyz[:8], ch.rpy[:8], ch.axis[:8])
+    with pytest.raises(native.MppiError):
+        s.set_chain([0, 1, 1, 1, 1, 1, 1, 0], ch.xyz[:8], ch.rpy[:8], ch.axis[:8])
 
 
 def test_update_config_and_targets_take_effect(oracle, native):
