@@ -8,8 +8,9 @@ __global__ void __launch_bounds__(256) probe(float *out, int iters, float a, flo
 {
     float2 x[8];
     unsigned y[8];
+    unsigned long long w[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { x[i] = make_float2(threadIdx.x + i, threadIdx.x - i); y[i] = threadIdx.x * 7 + i; }
+    for (int i = 0; i < 8; ++i) { x[i] = make_float2(threadIdx.x + i, threadIdx.x - i); y[i] = threadIdx.x * 7 + i; w[i] = (unsigned long long)y[i] * 0x9E3779B97F4A7C15ull; }
     const float2 a2 = make_float2(a, a), b2 = make_float2(b, b);
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
@@ -22,13 +23,19 @@ __global__ void __launch_bounds__(256) probe(float *out, int iters, float a, flo
                 if (MODE == 3) { x[i].x = fmaf(x[i].x, a, b); x[i].y = fmaf(x[i].y, a, b); }
                 if (MODE == 4) { unsigned long long p = (unsigned long long)y[i] * 0xD2511F53u; y[i] = (unsigned)(p >> 32) ^ (unsigned)p ^ m; }
                 if (MODE == 5) { x[i] = __ffma2_rn(x[i], a2, b2); y[i] = (y[i] ^ m) + 0x9e3779b9u; }     // FFMA2 + 1 ALU op
+                if (MODE == 7) { w[i] = (unsigned long long)(unsigned)w[i] * 0xD2511F53u + w[i]; }        // one IMAD.WIDE.U32, no ALU op
+                if (MODE == 8) { y[i] = __umulhi(y[i], 0xD2511F53u); }                                     // IMAD.HI.U32
+                if (MODE == 9) { y[i] = y[i] * 0xCD9E8D57u + m; }                                          // IMAD (low 32 bits)
+                if (MODE == 10) { y[i] = y[i] ^ y[(i + 1) & 7] ^ m; }                                      // LOP3
+                if (MODE == 11) { y[i] = __funnelshift_l(y[i], y[(i + 1) & 7], 7); }                       // SHF
+                if (MODE == 12) { w[i] = (unsigned long long)(unsigned)w[i] * 0xD2511F53u + w[i]; x[i] = __ffma2_rn(x[i], a2, b2); }   // IMAD.WIDE + FFMA2
                 if (MODE == 6) { x[i].x = fmaf(x[i].x, a, b); x[i].y = fmaf(x[i].y, a, b); y[i] = (y[i] ^ m) + 0x9e3779b9u; }
             }
         }
     }
     float s = 0; unsigned t = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { s += x[i].x + x[i].y; t ^= y[i]; }
+    for (int i = 0; i < 8; ++i) { s += x[i].x + x[i].y; t ^= y[i] ^ (unsigned)w[i] ^ (unsigned)(w[i] >> 32); }
     if (s == 1234.5f && t == 77u) out[0] = s;
 }
 
@@ -55,9 +62,11 @@ int main()
     const int sms = p.multiProcessorCount, iters = 2048;
     int khz = 0; cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0);
     // per iteration each thread executes 64 "slots" of the mode; warps per SMSP = 8*256/32/4 = 16
-    const char *names[] = {"FFMA2", "FMUL2", "FADD2", "2x FFMA", "IMAD.WIDE + 2 LOP", "FFMA2 + ALU", "2x FFMA + ALU"};
-    float t[7] = {run<0>(sms, iters), run<1>(sms, iters), run<2>(sms, iters), run<3>(sms, iters), run<4>(sms, iters), run<5>(sms, iters), run<6>(sms, iters)};
-    for (int i = 0; i < 7; ++i) {
+    const char *names[] = {"FFMA2", "FMUL2", "FADD2", "2x FFMA", "IMAD.WIDE + 2 LOP", "FFMA2 + ALU", "2x FFMA + ALU",
+                           "IMAD.WIDE.U32", "IMAD.HI.U32", "IMAD", "LOP3", "SHF", "IMAD.WIDE + FFMA2"};
+    float t[13] = {run<0>(sms, iters), run<1>(sms, iters), run<2>(sms, iters), run<3>(sms, iters), run<4>(sms, iters), run<5>(sms, iters), run<6>(sms, iters),
+                   run<7>(sms, iters), run<8>(sms, iters), run<9>(sms, iters), run<10>(sms, iters), run<11>(sms, iters), run<12>(sms, iters)};
+    for (int i = 0; i < 13; ++i) {
         const double cyc = t[i] * 1e-3 * 1.965e9;                        // assumes 1965 MHz
         const double per_slot = cyc / (double)iters / 64.0 / 16.0;      // cycles per warp-slot per scheduler
         printf("%-20s %.3f ms  %.2f cycles per slot per scheduler\n", names[i], t[i], per_slot);
