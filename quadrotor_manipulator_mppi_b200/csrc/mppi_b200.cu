@@ -209,7 +209,7 @@ void load_extra_costs(mppi_ctx *h, const mppi_config_t *cfg)
     std::memcpy(h->cfg.q_upper, cfg->q_upper, sizeof(cfg->q_upper));
 }
 
-void set_target_locked(mppi_ctx *h, const float *pos, const float *quat, const float *drone_target)
+void apply_target(mppi_ctx *h, const float *pos, const float *quat, const float *drone_target)
 {
     if (pos) for (int i = 0; i < 3; ++i) { h->cfg.target_pos[i] = pos[i]; h->dyn.target_pos[i] = pos[i]; }
     if (quat) {
@@ -263,9 +263,9 @@ mppi_status_t set_chain_impl(mppi_ctx *h, int n, const int32_t *types, const flo
         for (int i = 0; i < 9; ++i) baked = baked && std::fabs(ch.R[j][i] - FkKinova::R[j][i]) < 1e-6f;
         for (int i = 0; i < 3; ++i) baked = baked && std::fabs(ch.t[j][i] - FkKinova::t[j][i]) < 1e-6f;
     }
+    if (nrev != 7) return fail(h, MPPI_ERR_UNSUPPORTED, "the arm kernels are built for 7 actuated joints");   // handle unchanged
     h->baked_fk = baked;
     ch.baked = baked ? 1 : 0;
-    if (nrev != 7) return fail(h, MPPI_ERR_UNSUPPORTED, "the arm kernels are built for 7 actuated joints");
     h->P.chain = ch;
     return MPPI_OK;
 }
@@ -562,7 +562,7 @@ mppi_status_t mppi_create(const mppi_config_t *cfg, mppi_handle_t *out)
     std::memcpy(P.quad, cfg->quad_params, sizeof(P.quad));
     std::memcpy(P.taps, taps, sizeof(taps));
     load_extra_costs(h, cfg);
-    set_target_locked(h, cfg->target_pos, cfg->target_quat, cfg->drone_target);
+    apply_target(h, cfg->target_pos, cfg->target_quat, cfg->drone_target);
     if (set_chain_impl(h, 8, kKinovaTypes, &kKinovaXyz[0][0], &kKinovaRpy[0][0], &kKinovaAxis[0][0]) != MPPI_OK) {
         g_create_error = h->err; delete h; return MPPI_ERR_INVALID_ARG;
     }
@@ -656,7 +656,7 @@ mppi_status_t mppi_set_target(mppi_handle_t h, const float *pos, const float *qu
     if (!h) return MPPI_ERR_INVALID_ARG;
     if (quat && !(quat[0] * quat[0] + quat[1] * quat[1] + quat[2] * quat[2] + quat[3] * quat[3] > 0.f))
         return fail(h, MPPI_ERR_INVALID_ARG, "zero target quaternion");
-    set_target_locked(h, pos, quat, drone_target);
+    apply_target(h, pos, quat, drone_target);
     return MPPI_OK;
 }
 
@@ -747,6 +747,8 @@ mppi_status_t mppi_p2p_bind(mppi_handle_t h, int32_t world, int32_t rank, const 
         return fail(h, MPPI_ERR_INVALID_ARG, "mppi_p2p_bind: call mppi_p2p_export first; world in [2, 8]");
     DeviceGuard guard(h->cfg.device);
     P2PParams X = h->X;
+    for (int r = 0; r < kMaxRanks; ++r)          // re-binding: drop the mappings of the previous world
+        if (h->p2p_peer[r]) { cudaIpcCloseMemHandle(h->p2p_peer[r]); h->p2p_peer[r] = nullptr; }
     for (int r = 0; r < world; ++r) {
         if (r == rank) { X.base[r] = h->p2p_buf; continue; }
         cudaIpcMemHandle_t ih;

@@ -339,40 +339,6 @@ __device__ __forceinline__ void compose_tab(V R[9], V p[3])
         R[3 * r + 2] = tab_rot_col<Tab, J, 2>(a, b, c);
     }
 }
-// R <- R Rz(q): rotate columns 0/1 (S/robot/transformation_matrix.py:58-95 for a z axis)
-template <class V>
-__device__ __forceinline__ void rotate_z(V R[9], V c, V s)
-{
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        const V a = R[3 * r], b = R[3 * r + 1];
-        R[3 * r] = vfma(c, a, vmul(s, b));
-        R[3 * r + 1] = vfma(c, b, vneg(vmul(s, a)));
-    }
-}
-template <class Tab, int J = 0, class V>
-__device__ __forceinline__ void fk_tab(const V *cq, const V *sq, V R[9], V p[3])
-{
-    if constexpr (J < Tab::kJoints) {
-        rotate_z(R, cq[J], sq[J]);
-        compose_tab<Tab, J + 1>(R, p);
-        fk_tab<Tab, J + 1>(cq, sq, R, p);
-    }
-}
-
-// Forward kinematics of the folded chain; on entry (R,p) = world pose of the chain root
-// already composed with C0.  S/robot/urdfparser.py:133-161 + transformation_matrix.py:58-95
-// collapse to "rotate columns 0/1 by q, then apply the next constant transform".
-template <int NJ, class V>
-__device__ __forceinline__ void fk_chain(const ChainDev &ch, const V *cq, const V *sq, V R[9], V p[3])
-{
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-        rotate_z(R, cq[j], sq[j]);
-        if (j + 1 < NJ || !ch.last_identity) compose_const(R, p, ch.R[j + 1], ch.t[j + 1]);
-    }
-}
-
 // ---- Pose in packed layout ----------------------------------------------------------------
 // One sample per thread, but the FK still packs: each rotation column is held as the pair
 // (row 0, row 1) plus a row-2 scalar, the position as (x, y) + z.  Rotating by a joint angle is then
@@ -456,7 +422,8 @@ __device__ __forceinline__ void pose3_fk_chain(const ChainDev &ch, const float *
         if (j + 1 < NJ || !ch.last_identity) pose3_compose_const(T, ch.R[j + 1], ch.t[j + 1]);
     }
 }
-// Pose cost terms on a Pose3; the two atan2 of the ZYX Euler extraction run as one packed evaluation.
+// ||p - p*||_2 and ||euler_ZYX(R^T R*)||_2 on a Pose3 (S/cost/pose_cost.py:24-63, S/utils/rotation_conversions.py:277-319;
+// inv(R) of a rotation is its transpose); the two atan2 of the ZYX Euler extraction run as one packed evaluation.
 __device__ __forceinline__ void pose3_terms(const Pose3 &T, const DynBlock &D, float &pos, float &ori)
 {
     const float *Tg = D.target_R;
@@ -475,25 +442,6 @@ __device__ __forceinline__ void pose3_terms(const Pose3 &T, const DynBlock &D, f
     const float e1 = asin_poly(fminf(fmaxf(-d20, -1.0f), 1.0f));
     const f2 ee = vmul(e02, e02);
     ori = sqrt_approx(fmaf(e1, e1, ee.v.x + ee.v.y));
-}
-
-// ||p - p*||_2 and ||euler_ZYX(R^T R*)||_2  (S/cost/pose_cost.py:24-63,
-// S/utils/rotation_conversions.py:277-319; inv(R) of a rotation is its transpose).
-template <class V>
-__device__ __forceinline__ void pose_terms(const V R[9], const V p[3], const DynBlock &D, V &pos, V &ori)
-{
-    const float *Tg = D.target_R;
-    const V dx = vsub(p[0], V(D.target_pos[0])), dy = vsub(p[1], V(D.target_pos[1])), dz = vsub(p[2], V(D.target_pos[2]));
-    pos = vsqrt(vfma(dx, dx, vfma(dy, dy, vmul(dz, dz))));
-    const V d00 = vfma(R[0], V(Tg[0]), vfma(R[3], V(Tg[3]), vmul(R[6], V(Tg[6]))));
-    const V d10 = vfma(R[1], V(Tg[0]), vfma(R[4], V(Tg[3]), vmul(R[7], V(Tg[6]))));
-    const V d20 = vfma(R[2], V(Tg[0]), vfma(R[5], V(Tg[3]), vmul(R[8], V(Tg[6]))));
-    const V d21 = vfma(R[2], V(Tg[1]), vfma(R[5], V(Tg[4]), vmul(R[8], V(Tg[7]))));
-    const V d22 = vfma(R[2], V(Tg[2]), vfma(R[5], V(Tg[5]), vmul(R[8], V(Tg[8]))));
-    const V e0 = atan2_poly(d10, d00);
-    const V e1 = asin_poly(vmin(vmax(vneg(d20), V(-1.0f)), V(1.0f)));
-    const V e2 = atan2_poly(d21, d22);
-    ori = vsqrt(vfma(e0, e0, vfma(e1, e1, vmul(e2, e2))));
 }
 
 // Quadrotor rigid body, one step (restated from the dead draft S/mppi_solver/drone_mppi.py:57-83;

@@ -2,10 +2,10 @@
 //
 // Blackwell (sm_100) adds packed FP32x2 arithmetic (FFMA2 / FADD2 / FMUL2 on 64-bit register
 // pairs, with 32-bit immediate or broadcast-scalar operands).  It has the same FLOP rate as scalar
-// FFMA but needs half the issue slots (tools/probe_ffma2.cu), and the rollout kernel is
-// issue-bound.  So the hot kernel can carry TWO samples per thread: every device function of the
-// rollout is written once over a value type V, instantiated with V = float (one sample per
-// thread: small K, latency-bound) and V = f2 (two samples per thread: large K, issue-bound).
+// FFMA but needs half the issue slots (tools/probe_ffma2.cu, tools/probe_pipes.cu).  The rollout
+// kernel packs the work of ONE sample into these instructions (joint pairs, rotation-column pairs,
+// paired atan2 / Box-Muller), so the scalar math helpers are written once over a value type V and
+// instantiated with V = float and V = f2.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -28,8 +28,6 @@ template <> struct Lanes<f2>    { static constexpr int n = 2; using mask = b2;  
 // ---- lane access
 __device__ __forceinline__ float lane(float v, int) { return v; }
 __device__ __forceinline__ float lane(const f2 &v, int i) { return i ? v.v.y : v.v.x; }
-__device__ __forceinline__ void set_lane(float &v, int, float x) { v = x; }
-__device__ __forceinline__ void set_lane(f2 &v, int i, float x) { if (i) v.v.y = x; else v.v.x = x; }
 
 // ---- arithmetic (explicit names: fusion and rounding are part of the contract)
 __device__ __forceinline__ float vfma(float a, float b, float c) { return fmaf(a, b, c); }
@@ -37,14 +35,12 @@ __device__ __forceinline__ float vmul(float a, float b) { return a * b; }
 __device__ __forceinline__ float vadd(float a, float b) { return a + b; }
 __device__ __forceinline__ float vsub(float a, float b) { return a - b; }
 __device__ __forceinline__ float vneg(float a) { return -a; }
-__device__ __forceinline__ float vadd_rn(float a, float b) { return __fadd_rn(a, b); }
 
 __device__ __forceinline__ f2 vfma(f2 a, f2 b, f2 c) { f2 r; r.v = __ffma2_rn(a.v, b.v, c.v); return r; }
 __device__ __forceinline__ f2 vmul(f2 a, f2 b) { f2 r; r.v = __fmul2_rn(a.v, b.v); return r; }
 __device__ __forceinline__ f2 vadd(f2 a, f2 b) { f2 r; r.v = __fadd2_rn(a.v, b.v); return r; }
 __device__ __forceinline__ f2 vneg(f2 a) { return f2(-a.v.x, -a.v.y); }
 __device__ __forceinline__ f2 vsub(f2 a, f2 b) { return vadd(a, vneg(b)); }
-__device__ __forceinline__ f2 vadd_rn(f2 a, f2 b) { return vadd(a, b); }
 
 __device__ __forceinline__ f2 operator+(f2 a, f2 b) { return vadd(a, b); }
 __device__ __forceinline__ f2 operator-(f2 a, f2 b) { return vsub(a, b); }
@@ -84,12 +80,8 @@ __device__ __forceinline__ bool vgt(float a, float b) { return a > b; }
 __device__ __forceinline__ bool vlt(float a, float b) { return a < b; }
 __device__ __forceinline__ b2 vgt(f2 a, f2 b) { return b2{a.v.x > b.v.x, a.v.y > b.v.y}; }
 __device__ __forceinline__ b2 vlt(f2 a, f2 b) { return b2{a.v.x < b.v.x, a.v.y < b.v.y}; }
-__device__ __forceinline__ bool vor(bool a, bool b) { return a || b; }
-__device__ __forceinline__ b2 vor(b2 a, b2 b) { return b2{a.x || b.x, a.y || b.y}; }
 __device__ __forceinline__ float vsel(bool m, float a, float b) { return m ? a : b; }
 __device__ __forceinline__ f2 vsel(b2 m, f2 a, f2 b) { return f2(m.x ? a.v.x : b.v.x, m.y ? a.v.y : b.v.y); }
-__device__ __forceinline__ bool mask_false(bool) { return false; }
-__device__ __forceinline__ b2 mask_false(b2) { return b2{false, false}; }
 
 // ---- bit tricks
 __device__ __forceinline__ int vbits(float a) { return __float_as_int(a); }
