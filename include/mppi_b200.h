@@ -203,8 +203,11 @@ mppi_status_t mppi_step_p2p(mppi_handle_t h, const float *d_u_nom, const float *
                             void *stream);
 
 /* compute_control_input as ONE blocking call for a caller that keeps u_prev on the device (the Python
- * drop-in classes): stages state_host (may be NULL), runs mppi_step on `stream`, copies out[] to host
- * memory and synchronises the stream.  h2d = the state block (kernel parameter), d2h = out[].      */
+ * drop-in classes): stages state_host (may be NULL) and runs mppi_step on `stream`; the last block of the
+ * step stores out[] straight into mapped pinned host memory and publishes a sequence word the call spins
+ * on (no D2H copy, no stream synchronisation; the stream is polled so a failed kernel returns an error).
+ * Returns once out_host is complete; d_u_new is complete in stream order.
+ * h2d = the state block (kernel parameter), d2h = out[] (zero-copy store).                          */
 mppi_status_t mppi_step_sync(mppi_handle_t h, const float *state_host, int32_t n_state,
                              const float *d_u_nom, const float *d_noise, uint64_t step_counter,
                              float *d_u_new, float *out_host, void *stream);

@@ -77,8 +77,10 @@ class NativeSolver:
         self._cur = 0
         self._outs = [torch.zeros(_native.MPPI_OUT_FLOATS, device=self.device) for _ in range(4)]
         self._out_i = 0
+        self._u_ptr = [u.data_ptr() for u in self._u]
         self._out_host = torch.zeros(_native.MPPI_OUT_FLOATS)
         self._out_host_np = self._out_host.numpy()
+        self._out_host_ptr = self._out_host.data_ptr()
         self._state_np = np.zeros(_native.MODEL_STATE[model], np.float32)
         self._state_lock = threading.Lock()
         self._state_ptr = _native.fptr(self._state_np)
@@ -191,35 +193,64 @@ class NativeSolver:
         return out
 
     # ------------------------------------------------------------------ stepping
+    # The per-step entry points call the C ABI directly (ctypes, cached device pointers): a control step at small K is
+    # tens of microseconds, and a trip through the torch dispatcher costs about as much.  The same calls are also
+    # registered as torch custom ops (ops.py) for callers that want them in a traced / scheduled program.
+    def _noise_ptr(self, noise):
+        if noise is None:
+            return None
+        if noise.device != self.device:
+            raise ValueError(f"noise is on {noise.device}, the solver on {self.device}")
+        return ops._chk(noise, "noise", self.T * self.K * self.nu)
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _advance(self, sc: int) -> None:
+        self._cur ^= 1
+        self.step_counter = sc + 1
+
     def step_async(self, noise=None, step_counter=None) -> torch.Tensor:
         """One control step, asynchronous on the current stream.  Returns the device `out` vector."""
         sc = self.step_counter if step_counter is None else int(step_counter)
-        nxt = self._cur ^ 1
         out = self._outs[self._out_i]
         self._out_i = (self._out_i + 1) & 3
-        ops.step(self.handle, self._u[self._cur], noise, sc, self._u[nxt], out, None)
-        self._cur = nxt
-        self.step_counter = sc + 1
+        rc = self._lib.mppi_step(self.handle, self._u_ptr[self._cur], self._noise_ptr(noise), sc, None,
+                                 self._u_ptr[self._cur ^ 1], out.data_ptr(), self._stream())
+        if rc:
+            _native.check(rc, self.handle)
+        self._advance(sc)
         return out
 
-    def step(self, noise=None, step_counter=None) -> np.ndarray:
-        """One control step; returns the `out` vector on the host (pinned copy + stream sync)."""
+    def step(self, noise=None, step_counter=None, state=None) -> np.ndarray:
+        """One blocking control step; returns the `out` vector on the host (pinned copy + stream sync).
+
+        `state`: optional float32 numpy state vector used for exactly this step (the same call stages it and
+        snapshots it), so a caller that keeps its own sensor snapshot needs no separate set_state."""
         sc = self.step_counter if step_counter is None else int(step_counter)
-        nxt = self._cur ^ 1
-        ops.step_sync(self.handle, self._u[self._cur], noise, sc, self._u[nxt], self._out_host)
-        self._cur = nxt
-        self.step_counter = sc + 1
+        if state is None:
+            sp, sn = None, 0
+        else:
+            if state.dtype != np.float32 or not state.flags.c_contiguous or state.size != self._state_np.size:
+                raise ValueError(f"state must be a contiguous float32 array of {self._state_np.size} entries")
+            sp, sn = _native.fptr(state), state.size
+        rc = self._lib.mppi_step_sync(self.handle, sp, sn, self._u_ptr[self._cur], self._noise_ptr(noise), sc,
+                                      self._u_ptr[self._cur ^ 1], self._out_host_ptr, self._stream())
+        if rc:
+            _native.check(rc, self.handle)
+        self._advance(sc)
         return self._out_host_np
 
     def step_p2p_async(self, noise=None, step_counter=None) -> torch.Tensor:
         """Sharded step with the NVLink peer exchange fused in (after sharded.enable_p2p)."""
         sc = self.step_counter if step_counter is None else int(step_counter)
-        nxt = self._cur ^ 1
         out = self._outs[self._out_i]
         self._out_i = (self._out_i + 1) & 3
-        ops.step_p2p(self.handle, self._u[self._cur], noise, sc, self._u[nxt], out)
-        self._cur = nxt
-        self.step_counter = sc + 1
+        rc = self._lib.mppi_step_p2p(self.handle, self._u_ptr[self._cur], self._noise_ptr(noise), sc, None,
+                                     self._u_ptr[self._cur ^ 1], out.data_ptr(), self._stream())
+        if rc:
+            _native.check(rc, self.handle)
+        self._advance(sc)
         return out
 
     # ---- the three phases, for K-sharded replicas (see sharded.py)

@@ -3,6 +3,7 @@
 // Build:  nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
 //         (see quadrotor_manipulator_mppi_b200/build.py).  No CPU path exists in this file: every entry point
 // either launches on the device or returns an error.
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -158,6 +159,9 @@ struct mppi_ctx {
     size_t d_noise_bytes = 0;
     float *h_pinned = nullptr;      // pinned staging for the host-buffer API
     size_t h_pinned_floats = 0;
+    float *h_zc = nullptr;          // pinned + mapped: [MPPI_OUT_FLOATS] out vector + 1 sequence word (mppi_step_sync)
+    float *d_zc = nullptr;          // the same memory as the device addresses it
+    unsigned zc_seq = 0;
     int max_parts = 0;
     // NVLink peer exchange (mppi_p2p_export / mppi_p2p_bind)
     float *p2p_buf = nullptr;       // this rank's exchange buffer (cudaMalloc, exported through CUDA IPC)
@@ -593,6 +597,9 @@ mppi_status_t mppi_create(const mppi_config_t *cfg, mppi_handle_t *out)
     if ((e = cudaMemset(h->d_qtraj, 0, (size_t)P.T * 7 * sizeof(float))) != cudaSuccess) return cleanup(e, "cudaMemset(qtraj)");
     h->h_pinned_floats = (size_t)P.T * nu + MPPI_OUT_FLOATS;
     if ((e = cudaMallocHost(&h->h_pinned, h->h_pinned_floats * sizeof(float))) != cudaSuccess) return cleanup(e, "cudaMallocHost");
+    if ((e = cudaHostAlloc(&h->h_zc, (MPPI_OUT_FLOATS + 16) * sizeof(float), cudaHostAllocMapped)) != cudaSuccess) return cleanup(e, "cudaHostAlloc(mapped)");
+    std::memset(h->h_zc, 0, (MPPI_OUT_FLOATS + 16) * sizeof(float));
+    if ((e = cudaHostGetDevicePointer(&h->d_zc, h->h_zc, 0)) != cudaSuccess) return cleanup(e, "cudaHostGetDevicePointer");
     if ((e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return cleanup(e, "cudaStreamCreate");
     const int32_t init[4] = {kRhoInit, 0, 0, 0};
     if ((e = cudaMemcpy(h->d_rho, init, sizeof(init), cudaMemcpyHostToDevice)) != cudaSuccess) return cleanup(e, "cudaMemcpy(init)");
@@ -612,6 +619,7 @@ mppi_status_t mppi_destroy(mppi_handle_t h)
         for (int r = 0; r < kMaxRanks; ++r) if (h->p2p_peer[r]) cudaIpcCloseMemHandle(h->p2p_peer[r]);
         cudaFree(h->p2p_buf);
         if (h->h_pinned) cudaFreeHost(h->h_pinned);
+        if (h->h_zc) cudaFreeHost(h->h_zc);
         if (h->own_stream) cudaStreamDestroy(h->own_stream);
     }
     delete h;
@@ -789,14 +797,31 @@ mppi_status_t mppi_step_sync(mppi_handle_t h, const float *state_host, int32_t n
         mppi_status_t rc = mppi_set_state(h, state_host, n_state);
         if (rc != MPPI_OK) return rc;
     }
+    // The finalize block writes out[] into mapped pinned memory and then a sequence word; spin on it (the GIL is
+    // released by ctypes, a subscriber thread keeps running).  cudaStreamQuery is polled at a coarse interval so a
+    // failed launch or a faulting kernel ends the wait with an error instead of a hang.
+    const unsigned seq = ++h->zc_seq ? h->zc_seq : ++h->zc_seq;          // never 0
+    h->dyn.host_out = h->d_zc;
+    h->dyn.host_seq = seq;
     mppi_status_t rc = mppi_step(h, d_u_nom, d_noise, step_counter, nullptr, d_u_new, h->d_out, stream);
+    h->dyn.host_out = nullptr;
     if (rc != MPPI_OK) return rc;
     DeviceGuard guard(h->cfg.device);
     cudaStream_t st = (cudaStream_t)stream;
-    float *pin = h->h_pinned + (size_t)h->P.T * h->nu;
-    MPPI_CUDA(h, cudaMemcpyAsync(pin, h->d_out, MPPI_OUT_FLOATS * sizeof(float), cudaMemcpyDeviceToHost, st));
-    MPPI_CUDA(h, cudaStreamSynchronize(st));
-    std::memcpy(out_host, pin, MPPI_OUT_FLOATS * sizeof(float));
+    volatile unsigned *flag = reinterpret_cast<volatile unsigned *>(h->h_zc + MPPI_OUT_FLOATS);
+    for (unsigned it = 1; *flag != seq; ++it) {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+        if ((it & 255u) == 0) {
+            const cudaError_t q = cudaStreamQuery(st);
+            if (q == cudaErrorNotReady) continue;
+            if (q != cudaSuccess) return fail(h, MPPI_ERR_CUDA, std::string("control step failed: ") + cudaGetErrorString(q));
+            if (*flag != seq) return fail(h, MPPI_ERR_CUDA, "control step finished without publishing its result");
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    std::memcpy(out_host, h->h_zc, MPPI_OUT_FLOATS * sizeof(float));
     return MPPI_OK;
 }
 

@@ -57,6 +57,11 @@ struct DynBlock {
     float target_R[9];           // quaternion_to_matrix(target xyzw), S/utils/rotation_conversions.py:45-75
     float drone_target[3];
     unsigned step_lo, step_hi;   // Philox counter words 2,3
+    // Blocking steps (mppi_step_sync): the finalize block also stores out[] straight into mapped pinned host memory
+    // and then publishes host_seq at host_out[MPPI_OUT_FLOATS]; the host spins on that word instead of paying a
+    // D2H copy + stream synchronisation.  nullptr = off.
+    float *host_out;
+    unsigned host_seq;
 };
 
 // Peer-to-peer exchange over NVLink (K-sharded replicas, one process per GPU; buffers are

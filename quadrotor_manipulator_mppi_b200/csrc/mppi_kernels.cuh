@@ -434,6 +434,16 @@ __device__ void finalize_block(const StepParams &P, const DynBlock &D, const flo
     }
     __syncthreads();
     if (threadIdx.x == 0) *rho_enc = kRhoInit;          // re-arm the minimum for the next step
+    if (out != nullptr && D.host_out != nullptr) {
+        // zero-copy result for the blocking host call: out[] (complete after the barrier above) -> mapped host memory,
+        // system-scope fence, then the sequence word the host is spinning on
+        if (threadIdx.x < MPPI_OUT_FLOATS) D.host_out[threadIdx.x] = out[threadIdx.x];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned *>(D.host_out + MPPI_OUT_FLOATS) = D.host_seq;
+        }
+    }
 }
 
 template <int MODEL>

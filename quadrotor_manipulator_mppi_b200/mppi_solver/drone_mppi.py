@@ -3,7 +3,7 @@ drop-in for `mppi_solver/drone_mppi.py:7-183`.
 
 Kept: no-arg constructor and defaults (K=1000, T=32, dt=0.01, sigma=30, lambda=0.1;
 drone_mppi.py:16-19,32,34), `set_state(x, v)` (:179-183), `compute_control_input()` returning
-torch tensors `(x, v)` (:169-176), `u_prev` warm start without shift (:142,166), the hard-coded
+torch tensors `(x, v)` (:169-176; host tensors here), `u_prev` warm start without shift (:142,166), the hard-coded
 target (1.0, 2.0, 3.4) (:141, now the `target` attribute), `param_lambda`, `n_timestep`.
 The reference prints rho every step (:123); here it is in `last_stats`.
 """
@@ -14,6 +14,9 @@ import torch
 
 from .. import _native
 from ..core import NativeSolver
+
+
+_STATS = slice(_native.MPPI_OUT_RHO, _native.MPPI_OUT_ESS + 1)
 
 
 class MPPI:
@@ -37,6 +40,7 @@ class MPPI:
         self._solver.set_state(self._state)
         self.last_costs = None
         self.last_stats = {}
+        self._last_out = (float("nan"),) * 3
 
     @property
     def u_prev(self) -> torch.Tensor:
@@ -67,22 +71,26 @@ class MPPI:
 
     def compute_control_input(self, noise=None, noise_layout: str = "tkn", return_costs: bool = False):
         """drone_mppi.py:140-176."""
-        tgt = tuple(float(v) for v in torch.as_tensor(self.target).reshape(-1))
-        if tgt != self._target_sent:
-            self._solver.set_target(drone_target=tgt)
-            self._target_sent = tgt
-        out_dev = self._solver.step_async(self._solver.prepare_noise(noise, noise_layout))
-        x, v = out_dev[0:3], out_dev[3:6]
+        t_ = self.target
+        key = (id(t_), t_._version) if isinstance(t_, torch.Tensor) else tuple(t_)      # in-place edits bump _version
+        if key != self._target_sent:
+            self._solver.set_target(drone_target=tuple(float(v) for v in torch.as_tensor(t_).reshape(-1)))
+            self._target_sent = key
+        # blocking step: the out vector arrives in pinned host memory (zero-copy store), so the caller's
+        # `xdes.to('cpu').tolist()` (drone.py:240) costs nothing more
+        out = self._solver.step(self._solver.prepare_noise(noise, noise_layout))
+        xv = torch.from_numpy(out[0:6].copy())
+        x, v = xv[0:3], xv[3:6]
+        self._last_out = out[_STATS].tolist()
         if return_costs:
             self.last_costs = self._solver.costs.clone()
             return x, v, self.last_costs
         return x, v
 
     def stats(self) -> dict:
-        """rho / eta / effective sample size of the last step (synchronises)."""
-        out = self._solver._outs[(self._solver._out_i - 1) & 3].cpu().numpy()
-        self.last_stats = {"rho": float(out[_native.MPPI_OUT_RHO]), "eta": float(out[_native.MPPI_OUT_ETA]),
-                           "ess": float(out[_native.MPPI_OUT_ESS])}
+        """rho / eta / effective sample size of the last step (the reference prints rho, drone_mppi.py:123)."""
+        rho, eta, ess = self._last_out
+        self.last_stats = {"rho": rho, "eta": eta, "ess": ess}
         return self.last_stats
 
     def compute_weights(self, S: torch.Tensor) -> torch.Tensor:

@@ -23,6 +23,12 @@ from ..core import NativeSolver
 from ..utils.pose import Pose
 
 
+_U0_NEW = slice(_native.MPPI_OUT_U0_NEW, _native.MPPI_OUT_U0_NEW + 7)
+_U0_OLD = slice(_native.MPPI_OUT_U0_OLD, _native.MPPI_OUT_U0_OLD + 7)
+_STATS = slice(_native.MPPI_OUT_REACH, _native.MPPI_OUT_ESS + 1)       # reach, rho, eta, ess are consecutive
+_HALF = np.float32(0.5)
+
+
 class MPPI:
     MODEL = _native.MODEL_ARM7
     COST_TERMS = {"covar": _native.COST_COVAR, "centering": _native.COST_CENTERING, "joint_traj": _native.COST_JOINT_TRAJ,
@@ -55,13 +61,14 @@ class MPPI:
         self.target_pose.orientation = torch.tensor([-0.5, -0.5, 0.5, -0.5])  # mppi.py:72
         self._target_key = None
         self.ee_pose = Pose()
-        self._q64 = np.zeros(7)
-        self._qdot64 = np.zeros(7)
-        self._base64 = np.array([0, 0, 0, 0, 0, 0, 1.0])
-        self._state_dtype = np.float32        # float64 once update_joint() feeds numpy doubles
-        self._push_state()
-        self.qdes = torch.zeros(7)
-        self.vdes = torch.zeros(7)
+        # The measured state is ONE tuple (q, qdot, base xyz+quat, dtype) replaced atomically by update_joint() on the
+        # subscriber thread and read once per step: a step never mixes two sensor messages, and the callback never
+        # calls into the library.  dtype is float32 until update_joint() feeds numpy doubles.
+        self._snap = (np.zeros(7), np.zeros(7), np.array([0, 0, 0, 0, 0, 0, 1.0]), np.float32)
+        self._state32 = np.zeros(21, np.float32)
+        self._qdes_np = np.zeros(7, np.float32)
+        self._vdes_np = np.zeros(7, np.float32)
+        self._dt32 = np.float32(self.dt)
         self.last_costs = None
         self.last_stats = {}
         self.cnt = 0
@@ -80,8 +87,38 @@ class MPPI:
         return self._solver.u_prev[0]
 
     @property
+    def qdes(self) -> torch.Tensor:
+        """mppi.py:158 keeps qdes / vdes as tensors; built on demand from the step's numpy results."""
+        return torch.from_numpy(self._qdes_np)
+
+    @property
+    def vdes(self) -> torch.Tensor:
+        return torch.from_numpy(self._vdes_np)
+
+    @property
     def _qddot(self) -> torch.Tensor:
         return self._solver._u[self._solver._cur ^ 1][0]
+
+    @property
+    def _q64(self):
+        return self._snap[0]
+
+    @property
+    def _qdot64(self):
+        return self._snap[1]
+
+    @property
+    def _base64(self):
+        return self._snap[2]
+
+    @property
+    def _state_dtype(self):
+        return self._snap[3]
+
+    def _replace(self, idx, v):
+        snap = list(self._snap)
+        snap[idx] = np.asarray(torch.as_tensor(v).detach().cpu().numpy(), np.float64).copy()
+        self._snap = tuple(snap)
 
     @property
     def _q(self) -> torch.Tensor:
@@ -89,8 +126,7 @@ class MPPI:
 
     @_q.setter
     def _q(self, v):
-        self._q64 = np.asarray(torch.as_tensor(v).detach().cpu().numpy(), np.float64).copy()
-        self._push_state()
+        self._replace(0, v)
 
     @property
     def _qdot(self) -> torch.Tensor:
@@ -98,8 +134,7 @@ class MPPI:
 
     @_qdot.setter
     def _qdot(self, v):
-        self._qdot64 = np.asarray(torch.as_tensor(v).detach().cpu().numpy(), np.float64).copy()
-        self._push_state()
+        self._replace(1, v)
 
     @property
     def base_pose(self) -> torch.Tensor:
@@ -107,21 +142,15 @@ class MPPI:
 
     @base_pose.setter
     def base_pose(self, v):
-        self._base64 = np.asarray(torch.as_tensor(v).detach().cpu().numpy(), np.float64).copy()
-        self._push_state()
-
-    def _push_state(self):
-        self._solver.set_state_parts(self._q64, self._qdot64, self._base64)
+        self._replace(2, v)
 
     def update_joint(self, q_full, v_full):
         """mppi.py:196-200.  Safe to call from the subscriber thread while a step is running."""
         q_full = np.asarray(q_full, np.float64)
         v_full = np.asarray(v_full, np.float64)
-        self._q64 = q_full[7:14].copy()
-        self._qdot64 = v_full[6:13].copy()
-        self._base64 = q_full[:7].copy()
-        self._state_dtype = np.float64
-        self._solver.set_state_parts(self._q64, self._qdot64, self._base64)
+        if q_full.shape != (14,) or v_full.shape != (13,):
+            raise ValueError(f"update_joint expects q[14], v[13]; got {q_full.shape}, {v_full.shape}")
+        self._snap = (q_full[7:14].copy(), v_full[6:13].copy(), q_full[:7].copy(), np.float64)
 
     # ------------------------------------------------------------------ the control step
     def _sync_target(self):
@@ -135,20 +164,22 @@ class MPPI:
         """mppi.py:122-169.  `noise`: optional injected noise, [T][K][nu] ("tkn") or the
         reference's [K][T][nu] ("ktn"); default is in-kernel Philox(seed, step counter)."""
         self._sync_target()
-        q0 = self._q64.astype(self._state_dtype)
-        qd0 = self._qdot64.astype(self._state_dtype)
-        out = self._solver.step(self._solver.prepare_noise(noise, noise_layout))
-        f32 = np.float32
-        u0 = out[_native.MPPI_OUT_U0_NEW:_native.MPPI_OUT_U0_NEW + 7].copy()
-        qdd = out[_native.MPPI_OUT_U0_OLD:_native.MPPI_OUT_U0_OLD + 7].copy()
-        # mppi.py:157-158 in the reference's own arithmetic (float32 control terms, state dtype sum)
-        vdes = qd0 + u0 * f32(self.dt)
-        qdes = q0 + qdd * f32(self.dt) + f32(0.5) * u0 * f32(self.dt) * f32(self.dt)
-        self.vdes, self.qdes = torch.from_numpy(vdes), torch.from_numpy(qdes)
-        self.last_stats = {"rho": float(out[_native.MPPI_OUT_RHO]), "eta": float(out[_native.MPPI_OUT_ETA]),
-                           "ess": float(out[_native.MPPI_OUT_ESS]), "reach_err": float(out[_native.MPPI_OUT_REACH])}
+        q64, qd64, base64, dtype = self._snap               # one sensor message for the kernel AND the host epilogue
+        st = self._state32
+        st[0:7] = q64; st[7:14] = qd64; st[14:21] = base64
+        q0, qd0 = q64.astype(dtype), qd64.astype(dtype)
+        out = self._solver.step(self._solver.prepare_noise(noise, noise_layout), state=st)
+        u0 = out[_U0_NEW]                                   # views of the pinned out vector; the arithmetic below copies
+        qdd = out[_U0_OLD]
+        # mppi.py:157-158 in the reference's own arithmetic and order (float32 control terms, state dtype sum)
+        dt = self._dt32
+        vdes = qd0 + u0 * dt
+        qdes = q0 + qdd * dt + _HALF * u0 * dt * dt
+        self._vdes_np, self._qdes_np = vdes, qdes
+        reach, rho, eta, ess = out[_STATS].tolist()
+        self.last_stats = {"rho": rho, "eta": eta, "ess": ess, "reach_err": reach}
         self.cnt += 1
-        if self.last_stats["reach_err"] < 0.005:                               # mppi.py:117,165-166
+        if reach < 0.005:                                                      # mppi.py:117,165-166
             print("Reach !")
         if return_costs:
             self.last_costs = self._solver.costs.clone()

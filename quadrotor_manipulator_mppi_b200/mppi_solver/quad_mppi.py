@@ -48,10 +48,11 @@ class MPPI:
         self._solver.set_state_parts(p, rpy, v, w)
 
     def compute_control_input(self, noise=None, noise_layout: str = "tkn"):
-        """Returns the one-step-ahead state (p, rpy, v, w) as device tensors."""
-        tgt = tuple(float(v) for v in torch.as_tensor(self.target).reshape(-1))
-        if tgt != self._target_sent:
-            self._solver.set_target(drone_target=tgt)
-            self._target_sent = tgt
-        out = self._solver.step_async(self._solver.prepare_noise(noise, noise_layout))
+        """Returns the one-step-ahead state (p, rpy, v, w) as host tensors (blocking step)."""
+        t_ = self.target
+        key = (id(t_), t_._version) if isinstance(t_, torch.Tensor) else tuple(t_)      # in-place edits bump _version
+        if key != self._target_sent:
+            self._solver.set_target(drone_target=tuple(float(v) for v in torch.as_tensor(t_).reshape(-1)))
+            self._target_sent = key
+        out = torch.from_numpy(self._solver.step(self._solver.prepare_noise(noise, noise_layout))[0:12].copy())
         return out[0:3], out[3:6], out[6:9], out[9:12]
