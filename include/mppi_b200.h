@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MPPI_ABI_VERSION 2
+#define MPPI_ABI_VERSION 3
 #define MPPI_MAX_NU 12          /* controls per horizon step (whole body = 11)            */
 #define MPPI_MAX_HORIZON 256
 #define MPPI_MAX_JOINTS 8       /* revolute joints in the arm chain                      */
@@ -49,8 +49,11 @@ typedef enum {
  *  DRONE3 (drone_mppi.py, live nu=3 point mass): state = x[3], v[3]
  *          out = x_des[3], v_des[3]                              (drone_mppi.py:169-170)
  *  ARM7   (mppi.py, Kinova j2s7s300 nu=7):       state = q[7], qdot[7], base[7] (xyz + quat xyzw)
+ *          [, base twist[6] = v_full[:6] of kinova.py:106-116 (linear, angular; base frame) -- 27 floats; only
+ *          the torque law reads it, 21 floats = zero twist]
  *          out = qdes[7], vdes[7]                                (mppi.py:157-158, incl. the
  *                                                                 `_qddot * dt` term)
+ *          out[57..63] = joint torques of the computed-torque law (kinova.py:184) when MPPI_OPT_TORQUE_LAW is set
  *  QUAD4  (rigid body nu=4; restated from the dead draft drone_mppi.py:57-83, PARITY UNPINNED):
  *          state = p[3], rpy[3], v[3], w[3];  u = F, tau_xyz;  out = next state[12]
  *  WB11   (whole body nu=11, not in the reference, PARITY UNPINNED):
@@ -73,6 +76,7 @@ typedef enum {
 #define MPPI_OUT_ETA 54         /* sum of unnormalised weights                           */
 #define MPPI_OUT_ESS 55         /* effective sample size (sum w)^2 / sum w^2             */
 #define MPPI_OUT_STEP 56        /* low 24 bits of the step counter used                  */
+#define MPPI_OUT_TORQUE 57      /* ARM7 + MPPI_OPT_TORQUE_LAW: torque[7] = M[6:,6:] (kp (qdes - q) - kd qdot) + nle[6:] (kinova.py:184) */
 
 /* Replaces the hard-coded constructor constants of mppi.py:37-42,75,
  * sampling/standard_normal_noise.py:17, drone_mppi.py:16-19,32,34 and
@@ -98,7 +102,9 @@ typedef struct mppi_config {
     float target_pos[3];        /* mppi.py:71                                            */
     float target_quat[4];       /* xyzw, mppi.py:72                                      */
     float drone_target[3];      /* drone_mppi.py:141                                     */
-    float reserved[5];
+    float torque_kp;            /* 400   kinova.py:184                                                       */
+    float torque_kd;            /* 40    kinova.py:184                                                       */
+    float reserved[3];
     /* The cost terms the reference constructs but leaves commented out of the sum
      * (cost/cost_manager.py:83-87); enabled per bit, ARM7 / WB11 only.  Defaults are the
      * reference's weights: covar_cost.py:14,20-25, action_cost.py:15-25, joint_space_cost.py:13,18-77. */
@@ -121,6 +127,9 @@ typedef struct mppi_config {
 #define MPPI_COST_JOINT_TRAJ 4   /* joint_traj_weight * sum_t gamma^t |q_t - q_traj_t|^2 (q_traj = 0 unless mppi_set_joint_traj) */
 #define MPPI_COST_ACTION 8       /* action_weight * sum_t gamma^t |v_t|^2                                     */
 #define MPPI_COST_JOINT_LIMIT 16 /* sum_t gamma^t * limit_penalty * [any joint outside q_lower..q_upper]      */
+/* Options that share the cost_flags word (they do not select the extra-cost kernels): */
+#define MPPI_COST_MASK 31
+#define MPPI_OPT_TORQUE_LAW 256  /* ARM7: the finalize block also evaluates the arm node's torque law (kinova.py:126-131,184) */
 
 typedef struct mppi_ctx *mppi_handle_t;
 
@@ -142,6 +151,13 @@ int32_t mppi_abi_version(void);
  * mppi_create() pre-loads the j2s7s300 chain of aerial_manipulator_gpu.urdf.            */
 mppi_status_t mppi_set_chain(mppi_handle_t h, int32_t n_chain_joints, const int32_t *types,
                              const float *xyz, const float *rpy, const float *axis);
+
+/* Rigid-body parameters of the seven arm links for the torque law, in the URDF link frames: mass[7],
+ * com[7][3], inertia[7][6] = (ixx ixy ixz iyy iyz izz) about the centre of mass, fixed children already merged
+ * (what a URDF importer builds; tools/gen_arm_inertia.py).  mppi_create() pre-loads the j2s7s300 values of
+ * aerial_manipulation/urdf/full_robot_floating2.urdf (the model kinova.py:55-70 loads into Pinocchio).
+ * Prismatic chains are not supported by the torque law.                                                    */
+mppi_status_t mppi_set_arm_inertia(mppi_handle_t h, const float *mass, const float *com, const float *inertia);
 
 /* Re-reads the mutable hyper-parameters of cfg (sigma, lambda_, dt, cost_w, quad_params, cost_flags and
  * the extra-cost weights); model,

@@ -15,16 +15,18 @@ MPPI_STATE_FLOATS = 32
 MPPI_OUT_FLOATS = 64
 MPPI_IPC_HANDLE_BYTES = 64
 MPPI_OUT_BASE, MPPI_OUT_U0_NEW, MPPI_OUT_U0_OLD = 16, 28, 40
-MPPI_OUT_REACH, MPPI_OUT_RHO, MPPI_OUT_ETA, MPPI_OUT_ESS, MPPI_OUT_STEP = 52, 53, 54, 55, 56
+MPPI_OUT_REACH, MPPI_OUT_RHO, MPPI_OUT_ETA, MPPI_OUT_ESS, MPPI_OUT_STEP, MPPI_OUT_TORQUE = 52, 53, 54, 55, 56, 57
 MODEL_DRONE3, MODEL_ARM7, MODEL_QUAD4, MODEL_WB11 = 0, 1, 2, 3
 MODEL_NU = {MODEL_DRONE3: 3, MODEL_ARM7: 7, MODEL_QUAD4: 4, MODEL_WB11: 11}
 MODEL_STATE = {MODEL_DRONE3: 6, MODEL_ARM7: 21, MODEL_QUAD4: 12, MODEL_WB11: 26}
-ABI_VERSION = 2
+ABI_VERSION = 3
 COST_COVAR, COST_CENTERING, COST_JOINT_TRAJ, COST_ACTION, COST_JOINT_LIMIT = 1, 2, 4, 8, 16
+OPT_TORQUE_LAW = 256            # shares the cost_flags word; ARM7 only
+ARM_TWIST_FLOATS = 6            # optional tail of the ARM7 state: v_full[:6] (read by the torque law)
 
 EXPORTS = [
     "mppi_abi_version", "mppi_last_error", "mppi_default_config", "mppi_create", "mppi_destroy",
-    "mppi_update_config", "mppi_set_joint_traj", "mppi_set_chain", "mppi_set_target", "mppi_set_state", "mppi_step", "mppi_rollout", "mppi_weight",
+    "mppi_update_config", "mppi_set_joint_traj", "mppi_set_chain", "mppi_set_arm_inertia", "mppi_set_target", "mppi_set_state", "mppi_step", "mppi_rollout", "mppi_weight",
     "mppi_finalize", "mppi_rho_ptr", "mppi_wsum_ptr", "mppi_wsum_count", "mppi_cost_ptr",
     "mppi_p2p_export", "mppi_p2p_bind", "mppi_step_p2p", "mppi_step_sync", "mppi_step_host", "mppi_generate_noise", "mppi_measure_fp32_peak",
     "mppi_algorithmic_flops_per_rollout_step",
@@ -40,7 +42,7 @@ class MppiConfig(C.Structure):
         ("dt", C.c_float), ("lambda_", C.c_float),
         ("sigma", C.c_float * MPPI_MAX_NU), ("cost_w", C.c_float * 8), ("quad_params", C.c_float * 6),
         ("target_pos", C.c_float * 3), ("target_quat", C.c_float * 4), ("drone_target", C.c_float * 3),
-        ("reserved", C.c_float * 5),
+        ("torque_kp", C.c_float), ("torque_kd", C.c_float), ("reserved", C.c_float * 3),
         ("cost_flags", C.c_int32), ("gamma", C.c_float), ("covar_weight", C.c_float), ("alpha", C.c_float),
         ("action_weight", C.c_float), ("centering_weight", C.c_float), ("joint_traj_weight", C.c_float),
         ("limit_penalty", C.c_float), ("q_center", C.c_float * 7), ("q_lower", C.c_float * 7), ("q_upper", C.c_float * 7),
@@ -76,6 +78,7 @@ def load():
     lib.mppi_set_joint_traj.argtypes = [vp, _fp]
     lib.mppi_set_chain.argtypes = [vp, i32, C.POINTER(i32), _fp, _fp, _fp]
     lib.mppi_set_target.argtypes = [vp, _fp, _fp, _fp]
+    lib.mppi_set_arm_inertia.argtypes = [vp, _fp, _fp, _fp]
     lib.mppi_set_state.argtypes = [vp, _fp, i32]
     lib.mppi_step.argtypes = [vp, vp, vp, u64, vp, vp, vp, vp]
     lib.mppi_rollout.argtypes = [vp, vp, vp, u64, vp, vp]

@@ -36,7 +36,8 @@ def _require_cuda(device) -> torch.device:
 class NativeSolver:
     def __init__(self, model: int, *, n_samples=None, n_horizon=None, dt=None, lam=None, sigma=None,
                  seed: int = 0, device=None, k_offset: int = 0, savgol_window=None, cost_w=None,
-                 quad_params=None, target_pos=None, target_quat=None, drone_target=None, cost_flags: int = 0):
+                 quad_params=None, target_pos=None, target_quat=None, drone_target=None, cost_flags: int = 0,
+                 torque_gains=None):
         self.device = _require_cuda(device)
         self._lib = _native.load()
         cfg = _native.default_config(model)
@@ -62,6 +63,8 @@ class NativeSolver:
                 for i, v in enumerate(val):
                     arr[i] = float(v)
         cfg.cost_flags = int(cost_flags)
+        if torque_gains is not None:
+            cfg.torque_kp, cfg.torque_kd = float(torque_gains[0]), float(torque_gains[1])
         cfg.seed = int(seed) & (2 ** 64 - 1)
         cfg.k_offset = int(k_offset)
         cfg.device = self.device.index
@@ -81,7 +84,10 @@ class NativeSolver:
         self._out_host = torch.zeros(_native.MPPI_OUT_FLOATS)
         self._out_host_np = self._out_host.numpy()
         self._out_host_ptr = self._out_host.data_ptr()
-        self._state_np = np.zeros(_native.MODEL_STATE[model], np.float32)
+        n_state = _native.MODEL_STATE[model]
+        if model == _native.MODEL_ARM7 and (cfg.cost_flags & _native.OPT_TORQUE_LAW):
+            n_state += _native.ARM_TWIST_FLOATS                 # + base twist, read by the torque law
+        self._state_np = np.zeros(n_state, np.float32)
         self._state_lock = threading.Lock()
         self._state_ptr = _native.fptr(self._state_np)
         self._set_state_c = self._lib.mppi_set_state
@@ -165,6 +171,14 @@ class NativeSolver:
         if t.shape != (self.T, 7):
             raise ValueError(f"joint trajectory must be [{self.T}][7]")
         _native.check(self._lib.mppi_set_joint_traj(self.handle, _native.fptr(t)), self.handle)
+
+    def set_arm_inertia(self, mass, com, inertia) -> None:
+        """Link masses [7], centres of mass [7][3], inertias [7][6] (xx xy xz yy yz zz about the centre of mass), in the
+        URDF link frames with fixed children merged -- the model the torque law (kinova.py:184) runs on."""
+        m, c, i = (np.ascontiguousarray(v, np.float32).reshape(-1) for v in (mass, com, inertia))
+        if (m.size, c.size, i.size) != (7, 21, 42):
+            raise ValueError("expected mass[7], com[7][3], inertia[7][6]")
+        _native.check(self._lib.mppi_set_arm_inertia(self.handle, _native.fptr(m), _native.fptr(c), _native.fptr(i)), self.handle)
 
     def set_chain(self, types, xyz, rpy, axis) -> None:
         t = np.ascontiguousarray(types, np.int32)

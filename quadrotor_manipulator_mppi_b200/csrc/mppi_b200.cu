@@ -13,6 +13,7 @@
 #include <string>
 #include <vector>
 
+#include "arm_inertia_gen.cuh"
 #include "mppi_kernels.cuh"
 
 using namespace mppi;
@@ -170,6 +171,8 @@ struct mppi_ctx {
     P2PParams X_off{};              // world == 1: exchange disabled
     void *p2p_peer[kMaxRanks] = {};
     bool baked_fk = false;          // runtime chain == compile-time FkKinova tables
+    double align[MPPI_MAX_JOINTS][9] = {};   // A_j: URDF link frame j -> folded link frame (z = joint axis), row-major
+    float inertia_raw[7 * 10] = {};  // mass, com[3], inertia[6] per link, in the URDF link frames
     size_t rollout_smem[12] = {};   // tuned dynamic smem per kernel variant (0 = not yet tuned)
     float *d_qtraj = nullptr;       // [T][7] joint reference trajectory (MPPI_COST_JOINT_TRAJ), zeros by default
     cudaStream_t own_stream = nullptr;
@@ -194,17 +197,20 @@ void load_extra_costs(mppi_ctx *h, const mppi_config_t *cfg)
 {
     StepParams &P = h->P;
     P.cost_flags = cfg->cost_flags;
+    if (h->cfg.model != MPPI_MODEL_ARM7) P.cost_flags &= ~MPPI_OPT_TORQUE_LAW;     // the torque law is the arm node's
     P.gamma = cfg->gamma;
     P.covar_scale = cfg->covar_weight * (cfg->lambda_ * (1.0f - cfg->alpha));     // covar_cost.py:14,23
     P.action_weight = cfg->action_weight;
     P.centering_weight = cfg->centering_weight;
     P.joint_traj_weight = cfg->joint_traj_weight;
     P.limit_penalty = cfg->limit_penalty;
-    const int arm0 = (cfg->model == MPPI_MODEL_WB11) ? 4 : 0;
+    const int arm0 = (h->cfg.model == MPPI_MODEL_WB11) ? 4 : 0;
     for (int i = 0; i < 7; ++i) {
         P.inv_sigma_arm[i] = cfg->sigma[arm0 + i] != 0.f ? 1.0f / cfg->sigma[arm0 + i] : 0.f;
         P.q_center[i] = cfg->q_center[i]; P.q_lower[i] = cfg->q_lower[i]; P.q_upper[i] = cfg->q_upper[i];
     }
+    P.arm_inertia.kp = cfg->torque_kp; P.arm_inertia.kd = cfg->torque_kd; P.arm_inertia.gravity = -cfg->quad_params[5];
+    h->cfg.torque_kp = cfg->torque_kp; h->cfg.torque_kd = cfg->torque_kd;
     h->cfg.cost_flags = cfg->cost_flags; h->cfg.gamma = cfg->gamma; h->cfg.covar_weight = cfg->covar_weight;
     h->cfg.alpha = cfg->alpha; h->cfg.action_weight = cfg->action_weight; h->cfg.centering_weight = cfg->centering_weight;
     h->cfg.joint_traj_weight = cfg->joint_traj_weight; h->cfg.limit_penalty = cfg->limit_penalty;
@@ -229,11 +235,41 @@ void apply_target(mppi_ctx *h, const float *pos, const float *quat, const float 
     if (drone_target) for (int i = 0; i < 3; ++i) { h->cfg.drone_target[i] = drone_target[i]; h->dyn.drone_target[i] = drone_target[i]; }
 }
 
+// Inertial parameters arrive in the URDF link frames; the folded chain's link frame j is that frame rotated by
+// A_j (z onto the joint axis): com' = A^T com, I' = A^T I A.
+void fold_arm_inertia(mppi_ctx *h)
+{
+    ArmInertiaDev &d = h->P.arm_inertia;
+    for (int j = 0; j < 7; ++j) {
+        const float *raw = h->inertia_raw + 10 * j;
+        const double *A = h->align[j];
+        const double I[9] = {raw[4], raw[5], raw[6], raw[5], raw[7], raw[8], raw[6], raw[8], raw[9]};
+        double AtI[9], F[9];
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) {
+                double acc = 0.0;
+                for (int k = 0; k < 3; ++k) acc += A[3 * k + r] * I[3 * k + c];
+                AtI[3 * r + c] = acc;
+            }
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) {
+                double acc = 0.0;
+                for (int k = 0; k < 3; ++k) acc += AtI[3 * r + k] * A[3 * k + c];
+                F[3 * r + c] = acc;
+            }
+        d.mass[j] = raw[0];
+        for (int r = 0; r < 3; ++r) d.com[j][r] = (float)(A[r] * raw[1] + A[3 + r] * raw[2] + A[6 + r] * raw[3]);
+        d.inertia[j][0] = (float)F[0]; d.inertia[j][1] = (float)F[1]; d.inertia[j][2] = (float)F[2];
+        d.inertia[j][3] = (float)F[4]; d.inertia[j][4] = (float)F[5]; d.inertia[j][5] = (float)F[8];
+    }
+}
+
 mppi_status_t set_chain_impl(mppi_ctx *h, int n, const int32_t *types, const float *xyz, const float *rpy, const float *axis)
 {
     ChainDev ch{};
     Mat4 C = mat4_identity();
     int nrev = 0;
+    double align_new[MPPI_MAX_JOINTS][9] = {};
     for (int j = 0; j < n; ++j) {
         C = mat4_mul(C, origin_transform(xyz + 3 * j, rpy + 3 * j));
         if (types[j] == 0) continue;
@@ -245,6 +281,7 @@ mppi_status_t set_chain_impl(mppi_ctx *h, int n, const int32_t *types, const flo
         if (nrm < 1e-12) { ax[0] = 1; ax[1] = 0; ax[2] = 0; nrm = 1; }    // transformation_matrix.py:63-66
         for (double &a : ax) a /= nrm;
         const Mat4 A = align_z_to(ax);
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) align_new[nrev][3 * r + c] = A.m[4 * r + c];
         C = mat4_mul(C, A);
         for (int r = 0; r < 3; ++r) {
             for (int c = 0; c < 3; ++c) ch.R[nrev][3 * r + c] = (float)C.m[4 * r + c];
@@ -271,6 +308,8 @@ mppi_status_t set_chain_impl(mppi_ctx *h, int n, const int32_t *types, const flo
     h->baked_fk = baked;
     ch.baked = baked ? 1 : 0;
     h->P.chain = ch;
+    std::memcpy(h->align, align_new, sizeof(align_new));
+    fold_arm_inertia(h);
     return MPPI_OK;
 }
 
@@ -329,7 +368,7 @@ mppi_status_t launch_rollout_noise(mppi_ctx *h, const float *d_u_nom, const floa
 {
     constexpr bool HAS_ARM = (MODEL == MPPI_MODEL_ARM7 || MODEL == MPPI_MODEL_WB11);
     const bool baked = HAS_ARM && h->baked_fk;      // FK unrolled from the URDF constants (fk_tables_gen.cuh)
-    const bool extra = HAS_ARM && h->P.cost_flags != 0;      // optional cost terms: separate, slower instantiation
+    const bool extra = HAS_ARM && (h->P.cost_flags & MPPI_COST_MASK) != 0;      // optional cost terms: separate, slower instantiation
     const int variant = NOISE * 4 + (baked ? 1 : 0) + (extra ? 2 : 0);
     switch ((baked ? 1 : 0) + (extra ? 2 : 0)) {
         case 0: return launch_rollout_variant<MODEL, NOISE, false, false>(h, variant, d_u_nom, d_noise, d_cost, st);
@@ -483,6 +522,7 @@ mppi_status_t mppi_default_config(int32_t model, mppi_config_t *cfg)
     // aerial_manipulation/src/controller.cpp:159-161,488-490; k_d is undefined in the draft -> 0
     const float qp[6] = {14.7f, 1.0f / 1.57f, 1.0f / 3.93f, 1.0f / 2.59f, 0.0f, -9.81f};
     std::memcpy(cfg->quad_params, qp, sizeof(qp));
+    cfg->torque_kp = 400.0f; cfg->torque_kd = 40.0f;      // kinova.py:184
     cfg->cost_flags = 0;                                  // cost_manager.py:83-87: commented out in the reference
     cfg->gamma = 0.98f; cfg->covar_weight = 0.1f; cfg->alpha = 0.1f; cfg->action_weight = 0.01f;      // cost_manager.py:25-26,36,39
     cfg->centering_weight = 1.0f; cfg->joint_traj_weight = 1.0f; cfg->limit_penalty = 1e10f;          // :42-43, joint_space_cost.py:70
@@ -567,6 +607,12 @@ mppi_status_t mppi_create(const mppi_config_t *cfg, mppi_handle_t *out)
     std::memcpy(P.taps, taps, sizeof(taps));
     load_extra_costs(h, cfg);
     apply_target(h, cfg->target_pos, cfg->target_quat, cfg->drone_target);
+    for (int j = 0; j < 7; ++j) {
+        float *raw = h->inertia_raw + 10 * j;
+        raw[0] = ArmInertiaKinova::mass[j];
+        for (int k = 0; k < 3; ++k) raw[1 + k] = ArmInertiaKinova::com[j][k];
+        for (int k = 0; k < 6; ++k) raw[4 + k] = ArmInertiaKinova::inertia[j][k];
+    }
     if (set_chain_impl(h, 8, kKinovaTypes, &kKinovaXyz[0][0], &kKinovaRpy[0][0], &kKinovaAxis[0][0]) != MPPI_OK) {
         g_create_error = h->err; delete h; return MPPI_ERR_INVALID_ARG;
     }
@@ -632,6 +678,20 @@ mppi_status_t mppi_set_chain(mppi_handle_t h, int32_t n, const int32_t *types, c
     return set_chain_impl(h, n, types, xyz, rpy, axis);
 }
 
+mppi_status_t mppi_set_arm_inertia(mppi_handle_t h, const float *mass, const float *com, const float *inertia)
+{
+    if (!h || !mass || !com || !inertia) return fail(h, MPPI_ERR_INVALID_ARG, "null inertia arrays");
+    for (int j = 0; j < 7; ++j) {
+        if (!(mass[j] > 0.f)) return fail(h, MPPI_ERR_INVALID_ARG, "link masses must be positive");
+        float *raw = h->inertia_raw + 10 * j;
+        raw[0] = mass[j];
+        for (int k = 0; k < 3; ++k) raw[1 + k] = com[3 * j + k];
+        for (int k = 0; k < 6; ++k) raw[4 + k] = inertia[6 * j + k];
+    }
+    fold_arm_inertia(h);
+    return MPPI_OK;
+}
+
 mppi_status_t mppi_update_config(mppi_handle_t h, const mppi_config_t *cfg)
 {
     if (!h || !cfg) return fail(h, MPPI_ERR_INVALID_ARG, "null config");
@@ -671,10 +731,13 @@ mppi_status_t mppi_set_target(mppi_handle_t h, const float *pos, const float *qu
 mppi_status_t mppi_set_state(mppi_handle_t h, const float *state_host, int32_t n)
 {
     if (!h || !state_host) return fail(h, MPPI_ERR_INVALID_ARG, "null state");
-    if (n != model_state_floats(h->cfg.model))
-        return fail(h, MPPI_ERR_INVALID_ARG, "state length " + std::to_string(n) + " != " + std::to_string(model_state_floats(h->cfg.model)));
+    const int want = model_state_floats(h->cfg.model);
+    const bool with_twist = h->cfg.model == MPPI_MODEL_ARM7 && n == want + 6;       // + base twist for the torque law
+    if (n != want && !with_twist)
+        return fail(h, MPPI_ERR_INVALID_ARG, "state length " + std::to_string(n) + " != " + std::to_string(want));
     std::lock_guard<std::mutex> lk(h->state_mu);
     std::memcpy(h->staged_state, state_host, (size_t)n * sizeof(float));
+    if (h->cfg.model == MPPI_MODEL_ARM7 && !with_twist) std::memset(h->staged_state + want, 0, 6 * sizeof(float));
     return MPPI_OK;
 }
 

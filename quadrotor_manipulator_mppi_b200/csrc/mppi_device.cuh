@@ -28,6 +28,15 @@ struct ChainDev {
     int prismatic;       // bit j: joint j slides along its (folded) z axis instead of rotating about it
 };
 
+// Rigid-body parameters of the seven arm links in the folded link frames + the gains of the computed-torque law
+// (S/kinova.py:184); used by mppi_dynamics.cuh when MPPI_OPT_TORQUE_LAW is set.
+struct ArmInertiaDev {
+    float mass[7];
+    float com[7][3];
+    float inertia[7][6];         // xx xy xz yy yz zz about the centre of mass
+    float kp, kd, gravity;
+};
+
 // Everything that is fixed for a handle; passed by value as a kernel parameter (constant bank).
 struct StepParams {
     int K, T, nu, nch;           // nch = ceil(nu/4) Philox calls per (sample, step)
@@ -47,6 +56,7 @@ struct StepParams {
         joint_traj_weight, limit_penalty;
     float inv_sigma_arm[7];      // Sigma^-1 of the reference is 1/sigma (Sigma = sigma * I)
     float q_center[7], q_lower[7], q_upper[7];
+    ArmInertiaDev arm_inertia;
 };
 
 // Everything that changes per control step; also passed by value (192 B), so a step needs

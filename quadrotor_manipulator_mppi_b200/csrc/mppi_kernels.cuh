@@ -11,6 +11,7 @@
 //   K4  finalize              : normalise, Savitzky-Golay, u += w_eps, controller outputs.
 #pragma once
 #include "mppi_device.cuh"
+#include "mppi_dynamics.cuh"
 
 namespace mppi {
 
@@ -368,7 +369,7 @@ __device__ void finalize_block(const StepParams &P, const DynBlock &D, const flo
     }
     __syncthreads();
     // The epilogue is split over three warps so that its serial pieces overlap (this block is the tail of the step):
-    //   warp 0 lane 0: controller outputs;  warp 1 lane 0: check_reach FK;  warp 2: u0 / statistics.
+    //   warp 0 lane 0: controller outputs;  warp 1 lane 0: check_reach FK;  warp 2: u0 / statistics;  warp 3: torque law.
     const float dt = P.dt;
     if (out != nullptr && threadIdx.x == 0) {
         if constexpr (MODEL == MPPI_MODEL_DRONE3) {
@@ -422,6 +423,15 @@ __device__ void finalize_block(const StepParams &P, const DynBlock &D, const flo
                 pose3_fk_chain<7>(P.chain, qv, cq, sq, Tp);
             }
             out[MPPI_OUT_REACH] = fabsf(Tp.pxy.v.x - D.target_pos[0]) + fabsf(Tp.pxy.v.y - D.target_pos[1]) + fabsf(Tp.pz - D.target_pos[2]);
+        }
+    }
+    if constexpr (MODEL == MPPI_MODEL_ARM7) {
+        // computed-torque law of the arm node (kinova.py:184) on a fourth warp: 8 Newton-Euler passes on 8 lanes
+        const int tw = (blockDim.x >= 128) ? 3 : 0;
+        if (out != nullptr && (P.cost_flags & MPPI_OPT_TORQUE_LAW) && P.chain.prismatic == 0 && (threadIdx.x >> 5) == tw) {
+            float dq[7];                     // qdes - q without cancellation: u0_old dt + u0_new dt^2 / 2 (mppi.py:158)
+            for (int i = 0; i < 7; ++i) dq[i] = u0_old[i] * dt + 0.5f * un[i] * dt * dt;
+            arm_torque_warp(P, D.state, dq, out + MPPI_OUT_TORQUE);
         }
     }
     if (out != nullptr && threadIdx.x >= 64 && threadIdx.x < 96) {

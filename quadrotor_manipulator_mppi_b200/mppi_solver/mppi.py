@@ -27,6 +27,7 @@ _U0_NEW = slice(_native.MPPI_OUT_U0_NEW, _native.MPPI_OUT_U0_NEW + 7)
 _U0_OLD = slice(_native.MPPI_OUT_U0_OLD, _native.MPPI_OUT_U0_OLD + 7)
 _STATS = slice(_native.MPPI_OUT_REACH, _native.MPPI_OUT_ESS + 1)       # reach, rho, eta, ess are consecutive
 _HALF = np.float32(0.5)
+_TORQUE = slice(_native.MPPI_OUT_TORQUE, _native.MPPI_OUT_TORQUE + 7)
 
 
 class MPPI:
@@ -35,7 +36,8 @@ class MPPI:
                   "action": _native.COST_ACTION, "joint_limit": _native.COST_JOINT_LIMIT}
 
     def __init__(self, *, n_samples: int = 100, n_horizon: int = 32, dt: float = 0.01, sigma=0.1, lam: float = 0.1,
-                 seed: int = 0, device=None, verbose: bool = True, cost_terms=()):
+                 seed: int = 0, device=None, verbose: bool = True, cost_terms=(), torque_law: bool = False,
+                 torque_gains=(400.0, 40.0)):
         self.n_action = 7
         self.n_manipulator_dof = 7
         self.n_mobile_dof = 0
@@ -48,8 +50,14 @@ class MPPI:
         flags = 0
         for name in cost_terms:
             flags |= self.COST_TERMS[name]
+        # torque_law: also evaluate the arm node's computed-torque law on the device (kinova.py:126-131,184:
+        # M[6:,6:] (kp (qdes - q) - kd qdot) + nle[6:]); the result is `self.torque` after each step
+        self.torque_law = bool(torque_law)
+        if self.torque_law:
+            flags |= _native.OPT_TORQUE_LAW
         self._solver = NativeSolver(self.MODEL, n_samples=n_samples, n_horizon=n_horizon, dt=dt, lam=lam, sigma=sigma,
-                                    seed=seed, device=device, cost_flags=flags)
+                                    seed=seed, device=device, cost_flags=flags, torque_gains=torque_gains)
+        self.torque = np.zeros(7)
         self.device = self._solver.device
         if verbose:
             print(f"[MPPI] Using device: {self.device}")                      # mppi.py:33
@@ -64,8 +72,8 @@ class MPPI:
         # The measured state is ONE tuple (q, qdot, base xyz+quat, dtype) replaced atomically by update_joint() on the
         # subscriber thread and read once per step: a step never mixes two sensor messages, and the callback never
         # calls into the library.  dtype is float32 until update_joint() feeds numpy doubles.
-        self._snap = (np.zeros(7), np.zeros(7), np.array([0, 0, 0, 0, 0, 0, 1.0]), np.float32)
-        self._state32 = np.zeros(21, np.float32)
+        self._snap = (np.zeros(7), np.zeros(7), np.array([0, 0, 0, 0, 0, 0, 1.0]), np.float32, np.zeros(6))
+        self._state32 = np.zeros(27 if self.torque_law else 21, np.float32)
         self._qdes_np = np.zeros(7, np.float32)
         self._vdes_np = np.zeros(7, np.float32)
         self._dt32 = np.float32(self.dt)
@@ -150,7 +158,7 @@ class MPPI:
         v_full = np.asarray(v_full, np.float64)
         if q_full.shape != (14,) or v_full.shape != (13,):
             raise ValueError(f"update_joint expects q[14], v[13]; got {q_full.shape}, {v_full.shape}")
-        self._snap = (q_full[7:14].copy(), v_full[6:13].copy(), q_full[:7].copy(), np.float64)
+        self._snap = (q_full[7:14].copy(), v_full[6:13].copy(), q_full[:7].copy(), np.float64, v_full[:6].copy())
 
     # ------------------------------------------------------------------ the control step
     def _sync_target(self):
@@ -164,9 +172,11 @@ class MPPI:
         """mppi.py:122-169.  `noise`: optional injected noise, [T][K][nu] ("tkn") or the
         reference's [K][T][nu] ("ktn"); default is in-kernel Philox(seed, step counter)."""
         self._sync_target()
-        q64, qd64, base64, dtype = self._snap               # one sensor message for the kernel AND the host epilogue
+        q64, qd64, base64, dtype, twist = self._snap        # one sensor message for the kernel AND the host epilogue
         st = self._state32
         st[0:7] = q64; st[7:14] = qd64; st[14:21] = base64
+        if self.torque_law:
+            st[21:27] = twist
         q0, qd0 = q64.astype(dtype), qd64.astype(dtype)
         out = self._solver.step(self._solver.prepare_noise(noise, noise_layout), state=st)
         u0 = out[_U0_NEW]                                   # views of the pinned out vector; the arithmetic below copies
@@ -176,6 +186,8 @@ class MPPI:
         vdes = qd0 + u0 * dt
         qdes = q0 + qdd * dt + _HALF * u0 * dt * dt
         self._vdes_np, self._qdes_np = vdes, qdes
+        if self.torque_law:
+            self.torque = out[_TORQUE].astype(np.float64)                       # kinova.py:184
         reach, rho, eta, ess = out[_STATS].tolist()
         self.last_stats = {"rho": rho, "eta": eta, "ess": ess, "reach_err": reach}
         self.cnt += 1

@@ -45,13 +45,14 @@ def ros():
 class KinovaNode:
     """Call pattern of kinova.py:60-100 (setup), :106-116 (callback), :118-195 (SE3 phase of the loop)."""
 
-    def __init__(self):
+    def __init__(self, torque_law=False):
         import rospy
         from sensor_msgs.msg import JointState
         from mppi_solver.mppi import MPPI                              # kinova.py:23, resolved by the shim
         rospy.init_node("kinova_controller", anonymous=True)
         self.q = self.v = None
-        self.mppi = MPPI()                                             # kinova.py:88
+        self.torque_law = torque_law
+        self.mppi = MPPI(torque_law=True) if torque_law else MPPI()    # kinova.py:88
         self.rate = rospy.Rate(100)
         self.publisher = rospy.Publisher(CMD, JointState, queue_size=10)
         rospy.Subscriber(STATES, JointState, self.joint_state_callback)
@@ -72,9 +73,12 @@ class KinovaNode:
                 continue
             qdes_, vdes = self.mppi.compute_control_input()            # kinova.py:182
             assert isinstance(qdes_, np.ndarray) and qdes_.shape == (7,) and vdes.shape == (7,)
-            ades = 400 * (qdes_ - self.q[7:]) + 40 * (-self.v[6:])     # kinova.py:184 without M / nle (see module docstring)
+            if self.torque_law:
+                torque = self.mppi.torque                                  # kinova.py:184, evaluated on the device
+            else:
+                torque = 400 * (qdes_ - self.q[7:]) + 40 * (-self.v[6:])   # kinova.py:184 without M / nle (module docstring)
             msg = JointState()
-            msg.effort = [float(t) for t in ades[:7]]
+            msg.effort = [float(t) for t in torque[:7]]
             msg.position = [float(x) for x in qdes_]
             self.publisher.publish(msg)
 
@@ -195,3 +199,46 @@ def test_drone_loop_closed_loop(ros):
     # oracle loop: 2.58 m -> ~0.4 m by step 80, then hovers within 0.1-0.4 m (sigma = 30 m/s^2 of exploration noise)
     assert min(dist) < 0.8 and np.mean(dist[-50:]) < 1.0, (min(dist), np.mean(dist[-50:]))
     assert np.isfinite(node.mppi.u_prev.cpu().numpy()).all()
+
+
+def test_kinova_loop_with_the_device_torque_law(ros, oracle):
+    """The full arm loop of kinova.py: MPPI step + computed-torque law on the device, against a rigid-body plant
+    (forward dynamics from the float64 oracle: qdd = M^-1 (tau - nle)) integrated at 500 Hz between control ticks."""
+    from oracle import arm_dynamics as dyn
+    from sensor_msgs.msg import JointState
+    node = KinovaNode(torque_law=True)
+    base = np.array([0, 0, 2.1, 0, 0, 0, 1.0])
+    plant = {"q": Q_HOME.copy(), "v": np.zeros(7), "tau": None}
+    reach, n_steps = [], 200
+
+    def on_cmd(msg):
+        plant["tau"] = np.array(msg.effort)
+
+    ros.topic(CMD).callbacks.append(on_cmd)
+
+    def simulate(master):
+        if master.ticks > n_steps:
+            master.shutdown = True
+            return
+        master.drain()
+        for _ in range(5):
+            q_full, v_full = np.concatenate([base, plant["q"]]), np.concatenate([np.zeros(6), plant["v"]])
+            if plant["tau"] is not None:
+                qdd = np.linalg.solve(dyn.mass_matrix_arm(plant["q"]), plant["tau"] - dyn.nle_arm(q_full, v_full))
+                plant["v"] = plant["v"] + qdd * 2e-3
+                plant["q"] = plant["q"] + plant["v"] * 2e-3
+            msg = JointState()
+            msg.position = list(base) + list(plant["q"])
+            msg.velocity = [0.0] * 6 + list(plant["v"])
+            master.publish(STATES, msg)
+        reach.append(_arm_reach(oracle, plant["q"], base))
+
+    ros.on_sleep = simulate
+    node.main()
+    ros.drain()
+    assert not ros.errors, ros.errors
+    tau = np.array([m.effort for m in ros.topic(CMD).log])
+    assert np.isfinite(tau).all() and np.abs(tau).max() < 200.0           # gravity compensation scale, no blow-up
+    assert np.abs(tau[0]).max() > 1.0                                       # holds the arm against gravity from the first tick
+    assert np.abs(plant["q"] - Q_HOME).max() < 1.0                          # stays near the start: the loop is stable
+    assert reach[-1] < reach[0] - 0.05, (reach[0], reach[-1])               # and moves the end effector toward the target

@@ -548,3 +548,49 @@ def test_degenerate_weights(oracle, native):
         assert rel_inf(u, want) < 1e-4
         ess = out[native.MPPI_OUT_ESS]
         assert (abs(ess - K) < 1e-2 * K) if lam > 1 else (abs(ess - 1.0) < 1e-6)
+
+
+# ------------------------------------------------------------------ the arm node's torque law
+def test_torque_law_matches_the_dynamics_oracle(native):
+    """kinova.py:126-131,184 on the device (8 Newton-Euler passes in the finalize block) against the float64
+    oracle, which tests/test_oracle_dynamics.py pins against an independent Lagrangian derivation."""
+    from oracle import arm_dynamics as dyn
+    from quadrotor_manipulator_mppi_b200.mppi_solver.mppi import MPPI
+    m = MPPI(n_samples=256, n_horizon=16, torque_law=True, verbose=False)
+    rng = np.random.default_rng(5)
+    for trial in range(6):
+        quat = rng.normal(size=4)
+        quat /= np.linalg.norm(quat)
+        if trial == 0:
+            quat = np.array([0, 0, 0, 1.0])
+        q_full = np.concatenate([rng.uniform(-1, 1, 3) + [0, 0, 2.0], quat, rng.uniform(-3, 3, 7)])
+        v_full = np.concatenate([rng.uniform(-1, 1, 6), rng.uniform(-1, 1, 7)])
+        if trial == 1:
+            v_full[:] = 0.0                                    # pure gravity + kp term
+        m.update_joint(q_full, v_full)
+        qdes, vdes = m.compute_control_input()
+        want = dyn.torque_law(q_full, v_full, qdes)
+        assert np.abs(want).max() > 0.5                        # not a vacuous comparison
+        assert np.allclose(m.torque, want, rtol=2e-4, atol=2e-4), (trial, m.torque, want)
+    # without the option the slots stay untouched and the 21-float state is still accepted
+    m0 = MPPI(n_samples=256, n_horizon=16, verbose=False)
+    m0.update_joint(q_full, v_full)
+    m0.compute_control_input()
+    assert not m0.torque.any()
+
+
+def test_arm_inertia_can_be_replaced(native):
+    from oracle import arm_inertia_gen as gen
+    from quadrotor_manipulator_mppi_b200.mppi_solver.mppi import MPPI
+    q_full = np.concatenate([[0, 0, 2.1, 0, 0, 0, 1.0], [1.57, 1.7, 0.0, 4.4, 0.0, 4.71, 0.0]])
+    v_full = np.concatenate([[0.1, 0.0, -0.2, 0.05, 0.1, -0.1], np.linspace(-0.5, 0.5, 7)])
+    tq = []
+    for scale in (1.0, 2.0):
+        m = MPPI(n_samples=128, n_horizon=16, torque_law=True, verbose=False, seed=11)
+        m._solver.set_arm_inertia(np.array(gen.MASS) * scale, gen.COM, np.array(gen.INERTIA) * scale)
+        m.update_joint(q_full, v_full)
+        m.compute_control_input()
+        tq.append(m.torque.copy())
+    assert np.allclose(tq[1], 2.0 * tq[0], rtol=1e-5, atol=1e-5)      # the law is linear in the inertial parameters
+    with pytest.raises(native.MppiError):
+        m._solver.set_arm_inertia(np.zeros(7), gen.COM, gen.INERTIA)
