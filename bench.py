@@ -497,15 +497,11 @@ def run_native(args):
                "note": "public class compute_control_input(): state passes as a by-value kernel parameter block, u_prev stays device-resident (warm start), out vector is copied to pinned host memory and synchronised"}
     else:
         # multi-rank e2e: the sharded step plus a D2H of the out vector on every rank, wall clock max over ranks
-        host = torch.zeros(_native.MPPI_OUT_FLOATS, pin_memory=True)
         n_e2e = max(10, min(args.steps, 100))
         barrier()
         t0 = time.perf_counter()
         for i in range(n_e2e):
-            solver.set_state(st)
-            out = stepper.step_async(noise)
-            host.copy_(out, non_blocking=True)
-            stream.synchronize()
+            stepper.step(noise, state=st)                  # host state in, host out vector back, on every rank
         e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
         e2e_s = float(e2e_s.item())

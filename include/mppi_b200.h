@@ -228,6 +228,11 @@ mppi_status_t mppi_step_sync(mppi_handle_t h, const float *state_host, int32_t n
                              const float *d_u_nom, const float *d_noise, uint64_t step_counter,
                              float *d_u_new, float *out_host, void *stream);
 
+/* The same blocking form of mppi_step_p2p (every rank calls it; each gets the identical out[]).      */
+mppi_status_t mppi_step_p2p_sync(mppi_handle_t h, const float *state_host, int32_t n_state,
+                                 const float *d_u_nom, const float *d_noise, uint64_t step_counter,
+                                 float *d_u_new, float *out_host, void *stream);
+
 /* Host-buffer form (what a non-torch caller uses; also the end-to-end timing path):
  * copies state (if given) and u_inout to the device, steps, copies u_new / out / costs back
  * and synchronises.  noise_host may be NULL (Philox).                                   */

@@ -42,17 +42,25 @@ def quat_matrix(q):
 
 
 def placements(chain=KINOVA_CHAIN):
-    """Joint placements (R_i, p_i), i = 1..7: pose of joint i's frame at q_i = 0 in the frame of its parent body
-    (the base body for i = 1; the fixed `joint_base` is folded in).  Joint axes must be +z."""
+    """Joint placements (R_i, p_i, axis_i), i = 1..7: pose of joint i's frame at q_i = 0 in the frame of its parent
+    body (the base body for i = 1; fixed joints are folded in) and the unit joint axis in that frame."""
     out, R, p = [], np.eye(3), np.zeros(3)
     for j in range(chain.n):
         Ro, to = _rpy(*chain.rpy[j].astype(float)), chain.xyz[j].astype(float)
         p, R = p + R @ to, R @ Ro
         if chain.jtype[j] == 1:
-            assert np.allclose(chain.axis[j], [0, 0, 1]), "the dynamics oracle handles z-axis joints"
-            out.append((R, p))
+            ax = chain.axis[j].astype(float)
+            out.append((R, p, ax / np.linalg.norm(ax)))
             R, p = np.eye(3), np.zeros(3)
+        else:
+            assert chain.jtype[j] == 0, "the dynamics oracle handles fixed and revolute joints"
     return out
+
+
+def _axis_rotation(ax, q):
+    """Rodrigues rotation about the unit axis (transformation_matrix.py:68-84)."""
+    K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0.0]])
+    return np.eye(3) + np.sin(q) * K + (1 - np.cos(q)) * (K @ K)
 
 
 def _inertia(i):
@@ -71,17 +79,15 @@ def rnea_arm(q_arm, qd_arm, qdd_arm, base_R=np.eye(3), base_twist=np.zeros(6), g
     """Arm rows of rnea(q, v, a) with zero base acceleration (Featherstone table 5.1, free-flyer root).
 
     base_twist = (linear, angular) velocity of the base in the base frame (Pinocchio's v[:6])."""
-    z = np.array([0.0, 0.0, 1.0])
     pl = placements(chain)
     w_p, v_p = np.asarray(base_twist[3:6], float), np.asarray(base_twist[0:3], float)
     al_p = np.zeros(3)
     a_p = base_R.T @ np.array([0.0, 0.0, GRAVITY]) if gravity else np.zeros(3)      # a_0 = -a_gravity
     Rs, n_l, f_l = [], [], []
     for i in range(7):
-        R0, p = pl[i]
-        c, s = np.cos(q_arm[i]), np.sin(q_arm[i])
-        R = R0 @ np.array([[c, -s, 0], [s, c, 0], [0, 0, 1.0]])       # child axes in the parent frame
-        Rs.append((R, p))
+        R0, p, z = pl[i]
+        R = R0 @ _axis_rotation(z, q_arm[i])                          # child axes in the parent frame
+        Rs.append((R, p, z))
         w = R.T @ w_p + z * qd_arm[i]
         v = R.T @ (v_p + np.cross(w_p, p))
         al = R.T @ al_p + z * qdd_arm[i] + np.cross(w, z * qd_arm[i])
@@ -94,9 +100,9 @@ def rnea_arm(q_arm, qd_arm, qdd_arm, base_R=np.eye(3), base_twist=np.zeros(6), g
         w_p, v_p, al_p, a_p = w, v, al, a
     tau = np.zeros(7)
     for i in range(6, -1, -1):
-        tau[i] = n_l[i][2]
+        R, p, z = Rs[i]
+        tau[i] = n_l[i] @ z
         if i > 0:
-            R, p = Rs[i]
             fp = R @ f_l[i]
             n_l[i - 1] = n_l[i - 1] + R @ n_l[i] + np.cross(p, fp)
             f_l[i - 1] = f_l[i - 1] + fp
@@ -127,36 +133,35 @@ def torque_law(q_full, v_full, qdes, kp=KP, kd=KD, chain=KINOVA_CHAIN):
 
 # --------------------------------------------------------------------------- independent Lagrangian check
 def link_frames(q_arm, base_R=np.eye(3), base_p=np.zeros(3), chain=KINOVA_CHAIN):
-    """World pose (R, p) of every arm link frame."""
+    """World pose (R, p) of every arm link frame and the joint axis in world axes."""
     out, R, p = [], base_R, base_p
-    for i, (R0, p0) in enumerate(placements(chain)):
-        c, s = np.cos(q_arm[i]), np.sin(q_arm[i])
+    for i, (R0, p0, ax) in enumerate(placements(chain)):
         p = p + R @ p0
-        R = R @ R0 @ np.array([[c, -s, 0], [s, c, 0], [0, 0, 1.0]])
-        out.append((R, p))
+        R = R @ R0 @ _axis_rotation(ax, q_arm[i])
+        out.append((R, p, R @ ax))
     return out
 
 
-def lagrangian_mass_matrix(q_arm):
+def lagrangian_mass_matrix(q_arm, chain=KINOVA_CHAIN):
     """M = sum_i m_i Jv_i^T Jv_i + Jw_i^T (R_i Ic_i R_i^T) Jw_i with geometric Jacobians (fixed base)."""
-    fr = link_frames(q_arm)
+    fr = link_frames(q_arm, chain=chain)
     M = np.zeros((7, 7))
     for i in range(7):
         m, cm, Ic = _inertia(i)
-        Ri, pi = fr[i]
+        Ri, pi, _ = fr[i]
         com = pi + Ri @ cm
         Jv, Jw = np.zeros((3, 7)), np.zeros((3, 7))
         for j in range(i + 1):
-            zj, pj = fr[j][0][:, 2], fr[j][1]
+            zj, pj = fr[j][2], fr[j][1]
             Jw[:, j] = zj
             Jv[:, j] = np.cross(zj, com - pj)
         M += m * Jv.T @ Jv + Jw.T @ (Ri @ Ic @ Ri.T) @ Jw
     return M
 
 
-def potential_energy(q_arm, base_R=np.eye(3)):
+def potential_energy(q_arm, base_R=np.eye(3), chain=KINOVA_CHAIN):
     U = 0.0
-    for i, (Ri, pi) in enumerate(link_frames(q_arm, base_R)):
+    for i, (Ri, pi, _) in enumerate(link_frames(q_arm, base_R, chain=chain)):
         m, cm, _ = _inertia(i)
         U += m * GRAVITY * (pi + Ri @ cm)[2]
     return U
@@ -165,7 +170,7 @@ def potential_energy(q_arm, base_R=np.eye(3)):
 def arm_inertia_about_base(q_arm):
     """Rotational inertia tensor of the whole arm about the base origin, in base axes."""
     I = np.zeros((3, 3))
-    for i, (Ri, pi) in enumerate(link_frames(q_arm)):
+    for i, (Ri, pi, _) in enumerate(link_frames(q_arm)):
         m, cm, Ic = _inertia(i)
         r = pi + Ri @ cm
         I += Ri @ Ic @ Ri.T + m * (r @ r * np.eye(3) - np.outer(r, r))

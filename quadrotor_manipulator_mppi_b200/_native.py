@@ -28,7 +28,7 @@ EXPORTS = [
     "mppi_abi_version", "mppi_last_error", "mppi_default_config", "mppi_create", "mppi_destroy",
     "mppi_update_config", "mppi_set_joint_traj", "mppi_set_chain", "mppi_set_arm_inertia", "mppi_set_target", "mppi_set_state", "mppi_step", "mppi_rollout", "mppi_weight",
     "mppi_finalize", "mppi_rho_ptr", "mppi_wsum_ptr", "mppi_wsum_count", "mppi_cost_ptr",
-    "mppi_p2p_export", "mppi_p2p_bind", "mppi_step_p2p", "mppi_step_sync", "mppi_step_host", "mppi_generate_noise", "mppi_measure_fp32_peak",
+    "mppi_p2p_export", "mppi_p2p_bind", "mppi_step_p2p", "mppi_step_p2p_sync", "mppi_step_sync", "mppi_step_host", "mppi_generate_noise", "mppi_measure_fp32_peak",
     "mppi_algorithmic_flops_per_rollout_step",
 ]
 
@@ -96,6 +96,7 @@ def load():
     lib.mppi_p2p_bind.argtypes = [vp, i32, i32, vp]
     lib.mppi_step_p2p.argtypes = [vp, vp, vp, u64, vp, vp, vp, vp]
     lib.mppi_step_sync.argtypes = [vp, _fp, i32, vp, vp, u64, vp, vp, vp]
+    lib.mppi_step_p2p_sync.argtypes = [vp, _fp, i32, vp, vp, u64, vp, vp, vp]
     lib.mppi_step_host.argtypes = [vp, _fp, i32, _fp, _fp, u64, _fp, _fp]
     lib.mppi_generate_noise.argtypes = [vp, u64, vp, vp]
     lib.mppi_measure_fp32_peak.argtypes = [i32, _fp]

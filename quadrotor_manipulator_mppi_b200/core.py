@@ -236,11 +236,13 @@ class NativeSolver:
         self._advance(sc)
         return out
 
-    def step(self, noise=None, step_counter=None, state=None) -> np.ndarray:
-        """One blocking control step; returns the `out` vector on the host (pinned copy + stream sync).
+    def step(self, noise=None, step_counter=None, state=None, p2p: bool = False) -> np.ndarray:
+        """One blocking control step; returns the `out` vector on the host (stored there by the last block of the
+        step; the call spins on its sequence word).
 
         `state`: optional float32 numpy state vector used for exactly this step (the same call stages it and
-        snapshots it), so a caller that keeps its own sensor snapshot needs no separate set_state."""
+        snapshots it), so a caller that keeps its own sensor snapshot needs no separate set_state.
+        `p2p`: this solver is one K-shard bound to its peers (sharded.enable_p2p); every rank makes the call."""
         sc = self.step_counter if step_counter is None else int(step_counter)
         if state is None:
             sp, sn = None, 0
@@ -248,8 +250,9 @@ class NativeSolver:
             if state.dtype != np.float32 or not state.flags.c_contiguous or state.size != self._state_np.size:
                 raise ValueError(f"state must be a contiguous float32 array of {self._state_np.size} entries")
             sp, sn = _native.fptr(state), state.size
-        rc = self._lib.mppi_step_sync(self.handle, sp, sn, self._u_ptr[self._cur], self._noise_ptr(noise), sc,
-                                      self._u_ptr[self._cur ^ 1], self._out_host_ptr, self._stream())
+        fn = self._lib.mppi_step_p2p_sync if p2p else self._lib.mppi_step_sync
+        rc = fn(self.handle, sp, sn, self._u_ptr[self._cur], self._noise_ptr(noise), sc,
+                self._u_ptr[self._cur ^ 1], self._out_host_ptr, self._stream())
         if rc:
             _native.check(rc, self.handle)
         self._advance(sc)

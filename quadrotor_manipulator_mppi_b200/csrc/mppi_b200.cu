@@ -491,6 +491,37 @@ struct DeviceGuard {
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
+// Blocking steps: the finalize block writes out[] into mapped pinned memory and then a sequence word; the host
+// spins on it (ctypes releases the GIL, a subscriber thread keeps running).  cudaStreamQuery is polled at a coarse
+// interval so a failed launch or a faulting kernel ends the wait with an error instead of a hang.
+unsigned arm_publish(mppi_ctx *h)
+{
+    if (++h->zc_seq == 0) ++h->zc_seq;           // never 0
+    h->dyn.host_out = h->d_zc;
+    h->dyn.host_seq = h->zc_seq;
+    return h->zc_seq;
+}
+
+mppi_status_t wait_published(mppi_ctx *h, unsigned seq, cudaStream_t st, float *out_host)
+{
+    DeviceGuard guard(h->cfg.device);
+    volatile unsigned *flag = reinterpret_cast<volatile unsigned *>(h->h_zc + MPPI_OUT_FLOATS);
+    for (unsigned it = 1; *flag != seq; ++it) {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+        if ((it & 255u) == 0) {
+            const cudaError_t q = cudaStreamQuery(st);
+            if (q == cudaErrorNotReady) continue;
+            if (q != cudaSuccess) return fail(h, MPPI_ERR_CUDA, std::string("control step failed: ") + cudaGetErrorString(q));
+            if (*flag != seq) return fail(h, MPPI_ERR_CUDA, "control step finished without publishing its result");
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    std::memcpy(out_host, h->h_zc, MPPI_OUT_FLOATS * sizeof(float));
+    return MPPI_OK;
+}
+
 }  // namespace
 
 // ============================================================================ C ABI
@@ -860,32 +891,26 @@ mppi_status_t mppi_step_sync(mppi_handle_t h, const float *state_host, int32_t n
         mppi_status_t rc = mppi_set_state(h, state_host, n_state);
         if (rc != MPPI_OK) return rc;
     }
-    // The finalize block writes out[] into mapped pinned memory and then a sequence word; spin on it (the GIL is
-    // released by ctypes, a subscriber thread keeps running).  cudaStreamQuery is polled at a coarse interval so a
-    // failed launch or a faulting kernel ends the wait with an error instead of a hang.
-    const unsigned seq = ++h->zc_seq ? h->zc_seq : ++h->zc_seq;          // never 0
-    h->dyn.host_out = h->d_zc;
-    h->dyn.host_seq = seq;
+    const unsigned seq = arm_publish(h);
     mppi_status_t rc = mppi_step(h, d_u_nom, d_noise, step_counter, nullptr, d_u_new, h->d_out, stream);
     h->dyn.host_out = nullptr;
     if (rc != MPPI_OK) return rc;
-    DeviceGuard guard(h->cfg.device);
-    cudaStream_t st = (cudaStream_t)stream;
-    volatile unsigned *flag = reinterpret_cast<volatile unsigned *>(h->h_zc + MPPI_OUT_FLOATS);
-    for (unsigned it = 1; *flag != seq; ++it) {
-#if defined(__x86_64__) || defined(__i386__)
-        __builtin_ia32_pause();
-#endif
-        if ((it & 255u) == 0) {
-            const cudaError_t q = cudaStreamQuery(st);
-            if (q == cudaErrorNotReady) continue;
-            if (q != cudaSuccess) return fail(h, MPPI_ERR_CUDA, std::string("control step failed: ") + cudaGetErrorString(q));
-            if (*flag != seq) return fail(h, MPPI_ERR_CUDA, "control step finished without publishing its result");
-        }
+    return wait_published(h, seq, (cudaStream_t)stream, out_host);
+}
+
+mppi_status_t mppi_step_p2p_sync(mppi_handle_t h, const float *state_host, int32_t n_state, const float *d_u_nom,
+                                 const float *d_noise, uint64_t step_counter, float *d_u_new, float *out_host, void *stream)
+{
+    if (!h || !out_host) return fail(h, MPPI_ERR_INVALID_ARG, "null out buffer");
+    if (state_host) {
+        mppi_status_t rc = mppi_set_state(h, state_host, n_state);
+        if (rc != MPPI_OK) return rc;
     }
-    std::atomic_thread_fence(std::memory_order_acquire);
-    std::memcpy(out_host, h->h_zc, MPPI_OUT_FLOATS * sizeof(float));
-    return MPPI_OK;
+    const unsigned seq = arm_publish(h);
+    mppi_status_t rc = mppi_step_p2p(h, d_u_nom, d_noise, step_counter, nullptr, d_u_new, h->d_out, stream);
+    h->dyn.host_out = nullptr;
+    if (rc != MPPI_OK) return rc;
+    return wait_published(h, seq, (cudaStream_t)stream, out_host);
 }
 
 mppi_status_t mppi_step_host(mppi_handle_t h, const float *state_host, int32_t n_state, float *u_inout_host,

@@ -110,6 +110,16 @@ class ShardedStepper:
             dist.all_reduce(s.wsum, op=dist.ReduceOp.SUM, group=self.group)
         return s.finalize()
 
+    def step(self, noise=None, state=None):
+        """Blocking step: returns the out vector as a host numpy array (identical on every rank)."""
+        s = self.solver
+        if self.exchange == "p2p":
+            return s.step(noise, state=state, p2p=True)
+        if state is not None:
+            s.set_state(state)
+        out = self.step_async(noise)
+        return out.cpu().numpy()
+
     @property
     def u_prev(self):
         return self.solver.u_prev

@@ -28,10 +28,13 @@ def _worker(rank, world, port, K, T, out_dir, exchange):
         state[2] = 2.1
         state[12:19] = [1.57, 1.7, 0, 4.4, 0, 4.71, 0]
         st.solver.set_state(state)
-        for _ in range(3):
+        for _ in range(2):
             out = st.step_async()
         torch.cuda.synchronize()
         assert float(out[_native.MPPI_OUT_STEP]) >= 0.0          # -1 = peer exchange timed out
+        host = st.step(state=state)                               # blocking form: out vector lands in host memory
+        assert host.shape == (_native.MPPI_OUT_FLOATS,) and float(host[_native.MPPI_OUT_STEP]) == 2.0
+        np.save(os.path.join(out_dir, f"out_{rank}.npy"), host.copy())
         np.save(os.path.join(out_dir, f"u_{rank}.npy"), st.u_prev.cpu().numpy())
         np.save(os.path.join(out_dir, f"S_{rank}.npy"), st.solver.costs.cpu().numpy())
     finally:
@@ -51,6 +54,8 @@ def test_two_gpu_matches_single_gpu(tmp_path, exchange):
     mp.spawn(_worker, args=(world, port, K, T, str(tmp_path), exchange), nprocs=world, join=True)
     u = [np.load(tmp_path / f"u_{r}.npy") for r in range(world)]
     assert np.array_equal(u[0], u[1])
+    o = [np.load(tmp_path / f"out_{r}.npy") for r in range(world)]
+    assert np.array_equal(o[0], o[1])                             # every rank returns the same controller outputs
     full = NativeSolver(_native.MODEL_WB11, n_samples=K, n_horizon=T, seed=21)
     state = np.zeros(26, np.float32)
     state[2] = 2.1

@@ -579,6 +579,25 @@ def test_torque_law_matches_the_dynamics_oracle(native):
     assert not m0.torque.any()
 
 
+def test_torque_law_on_a_chain_with_tilted_axes(oracle, native):
+    """Inertial parameters are given in the URDF link frames; the library folds them into its z-axis link frames."""
+    from oracle import arm_dynamics as dyn
+    from quadrotor_manipulator_mppi_b200.mppi_solver.mppi import MPPI
+    ch = _chain_variant(oracle, "tilted_axes")
+    m = MPPI(n_samples=128, n_horizon=16, torque_law=True, verbose=False)
+    m._solver.set_chain(ch.jtype, ch.xyz, ch.rpy, ch.axis)
+    rng = np.random.default_rng(9)
+    quat = rng.normal(size=4)
+    quat /= np.linalg.norm(quat)
+    q_full = np.concatenate([[0.1, -0.3, 1.9], quat, rng.uniform(-3, 3, 7)])
+    v_full = rng.uniform(-1, 1, 13)
+    m.update_joint(q_full, v_full)
+    qdes, _ = m.compute_control_input()
+    want = dyn.torque_law(q_full, v_full, qdes, chain=ch)
+    assert np.allclose(m.torque, want, rtol=2e-4, atol=2e-4), (m.torque, want)
+    assert not np.allclose(want, dyn.torque_law(q_full, v_full, qdes), atol=1e-2)     # a different answer from the j2s7s300's
+
+
 def test_arm_inertia_can_be_replaced(native):
     from oracle import arm_inertia_gen as gen
     from quadrotor_manipulator_mppi_b200.mppi_solver.mppi import MPPI

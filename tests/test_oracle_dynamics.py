@@ -68,7 +68,7 @@ def test_base_linear_velocity_only_enters_through_omega_cross_v():
 
     def field_potential(q):
         U = 0.0
-        for i, (Ri, pi) in enumerate(dyn.link_frames(q)):
+        for i, (Ri, pi, _) in enumerate(dyn.link_frames(q)):
             m, cm, _ = dyn._inertia(i)
             U += m * a @ (pi + Ri @ cm)
         return U
@@ -83,3 +83,17 @@ def test_torque_law_composition():
     M = dyn.mass_matrix_arm(Q)
     assert np.allclose(tau, M @ (400 * (qdes - Q) - 40 * QD) + dyn.nle_arm(q_full, v_full))
     assert np.isfinite(tau).all()
+
+
+def test_general_joint_axes():
+    """Chains whose joint axes are not +z (the folded-frame path of the library): same Lagrangian pins."""
+    from oracle import oracle as orc
+    base = orc.KINOVA_CHAIN
+    axis, rpy, xyz = base.axis.copy(), base.rpy.copy(), base.xyz.copy()
+    axis[2] = [0, 1, 0]; axis[4] = [1, 0, 0]; axis[6] = [0.6, 0.0, 0.8]
+    rpy[3] = [0.3, -0.2, 0.5]; xyz[5] = [0.01, 0.2, -0.03]
+    ch = orc.Chain(base.jtype, base.qidx, xyz, rpy, axis)
+    M = dyn.mass_matrix_arm(Q, ch)
+    assert np.allclose(M, dyn.lagrangian_mass_matrix(Q, ch), atol=1e-12)
+    g = dyn.rnea_arm(Q, np.zeros(7), np.zeros(7), chain=ch)
+    assert np.allclose(g, _grad(lambda q: dyn.potential_energy(q, chain=ch), Q), atol=1e-7)
