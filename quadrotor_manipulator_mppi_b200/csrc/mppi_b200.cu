@@ -411,15 +411,27 @@ mppi_status_t launch_weight(mppi_ctx *h, const float *d_noise, bool fuse, const 
         blocks = (K + chunk - 1) / chunk;
         size_t smem_floats = (size_t)2 * kWeightTile + (size_t)R * TC * 6;
         if (smem_floats < fin_floats) smem_floats = fin_floats;
-        weight_philox_kernel<MODEL><<<blocks, threads, smem_floats * sizeof(float), st>>>(
-            h->P, h->dyn, h->d_cost, h->d_rho, chunk, h->d_fix, h->d_counter, h->d_wsum, fuse ? 1 : 0, d_u_nom, d_u_new, d_out, X);
+        // fused steps launch it as a programmatic dependent of the rollout kernel: its launch overlaps the rollout's drain
+        cudaLaunchConfig_t lc{};
+        lc.gridDim = dim3(blocks); lc.blockDim = dim3(threads); lc.dynamicSmemBytes = smem_floats * sizeof(float); lc.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = at; lc.numAttrs = fuse ? 1 : 0;
+        MPPI_CUDA(h, cudaLaunchKernelEx(&lc, weight_philox_kernel<MODEL>, h->P, h->dyn, (const float *)h->d_cost, h->d_rho, chunk, h->d_fix,
+                                        h->d_counter, h->d_wsum, fuse ? 1 : 0, d_u_nom, d_u_new, d_out, X));
     } else {
         const bool vec4 = ((size_t)K * NU) % 4 == 0 && (reinterpret_cast<uintptr_t>(d_noise) & 15u) == 0;
         // weights once, then one resident wave of (G x T) streaming blocks
         int wblocks = (K + 1023) / 1024;
         if (wblocks > h->num_sms) wblocks = h->num_sms;
-        weights_kernel<<<wblocks, 256, 0, st>>>(h->P, h->d_cost, h->d_rho, h->d_w, h->d_eta_part);
-        MPPI_CUDA(h, cudaGetLastError());
+        cudaLaunchConfig_t lc{};
+        lc.gridDim = dim3(wblocks); lc.blockDim = dim3(256); lc.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = at; lc.numAttrs = fuse ? 1 : 0;
+        MPPI_CUDA(h, cudaLaunchKernelEx(&lc, weights_kernel, h->P, (const float *)h->d_cost, (const int32_t *)h->d_rho, h->d_w, h->d_eta_part));
         const int threads = 32 * NU;
         size_t smem_floats = (size_t)threads * 4;
         if (smem_floats < fin_floats) smem_floats = fin_floats;

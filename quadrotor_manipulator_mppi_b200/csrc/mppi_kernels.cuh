@@ -309,6 +309,9 @@ rollout_cost_kernel(const __grid_constant__ StepParams P, const __grid_constant_
             S = tS;
         }
     }
+    // programmatic dependent launch: the weighting kernel of this step may start its launch now; it still waits
+    // (griddepcontrol.wait) for this whole grid and its memory before it reads S or rho
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if constexpr (MODEL == MPPI_MODEL_DRONE3 || MODEL == MPPI_MODEL_QUAD4) {
         S = fmaf(Sd, P.cost_w[4], term_d * P.cost_w[5]);
     } else if constexpr (MODEL == MPPI_MODEL_WB11) {
@@ -636,6 +639,7 @@ weight_philox_kernel(const __grid_constant__ StepParams P, const __grid_constant
     const int r = tid / TC, tc = tid - r * TC;
     const int c = tc % NCH;
     const int t = tc / NCH;
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // PDL: launched while the rollout kernel drains (no-op otherwise)
     const float rho = decode_ordered(*rho_enc);
     const int k0 = blockIdx.x * chunk;
     const int k1 = min(P.K, k0 + chunk);
@@ -732,6 +736,7 @@ weights_kernel(const __grid_constant__ StepParams P, const float *__restrict__ S
                float *__restrict__ w, float *__restrict__ eta_part)
 {
     __shared__ float s_e[8], s_e2[8];
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // PDL: launched while the rollout kernel drains (no-op otherwise)
     const float rho = decode_ordered(*rho_enc);
     float eta = 0.f, eta2 = 0.f;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < P.K; k += gridDim.x * blockDim.x) {
