@@ -22,6 +22,7 @@ from __future__ import annotations
 
 import struct
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -118,7 +119,7 @@ class ShardedStepper:
         if state is not None:
             s.set_state(state)
         out = self.step_async(noise)
-        return out.cpu().numpy()
+        return out.cpu().numpy() if isinstance(out, torch.Tensor) else np.asarray(out)
 
     @property
     def u_prev(self):
