@@ -4,11 +4,14 @@
 //                               forward kinematics + cost, one thread per sample, state in
 //                               registers over the horizon loop; S[K] and the cost minimum
 //                               are the only things written.
-//   K3  weight_philox_kernel  : w = exp((rho-S)/lambda), weighted-noise sums with the noise
-//       weight_injected_kernel  regenerated (compute-bound) or re-read (HBM-bound, float4).
-//                               The last block to finish reduces the per-block partials in a
-//                               fixed order and, on a single GPU, runs K4 in place.
-//   K4  finalize              : normalise, Savitzky-Golay, u += w_eps, controller outputs.
+//   K3  weight_philox_kernel  : w = exp((rho-S)/lambda) and the weighted-noise sums with the noise REGENERATED for the
+//                               samples whose weight is not zero (compute-bound; fixed-point integer atomics), or
+//       weights_kernel + weighted_noise_kernel : the same with injected noise re-read once from HBM (float4 stream,
+//                               per-block partials reduced in a fixed order).
+//                               The last block to finish runs K4 in place on a single GPU; with K sharded over GPUs it
+//                               first exchanges its row with the peers over NVLink (p2p_exchange).
+//   K4  finalize_block        : normalise, Savitzky-Golay, u += w_eps, controller outputs, check_reach, statistics,
+//                               the arm node's torque law (mppi_dynamics.cuh), zero-copy result for blocking callers.
 #pragma once
 #include "mppi_device.cuh"
 #include "mppi_dynamics.cuh"
@@ -20,8 +23,8 @@ namespace mppi {
 #define MPPI_ROLLOUT_MINB 4
 #endif
 constexpr int kRolloutThreads = MPPI_ROLLOUT_THREADS;
-constexpr int kWeightTile = 2048;
-constexpr float kFixScale = 8589934592.0f;   // 2^33: fixed-point scale of the weighting accumulators       // samples whose weights are staged in smem at a time
+constexpr int kWeightTile = 2048;             // samples whose weights are staged in shared memory at a time
+constexpr float kFixScale = 8589934592.0f;   // 2^33: fixed-point scale of the weighting accumulators
 
 // ------------------------------------------------------------------------------------------
 // K2: fused noise + rollout + FK + cost.
