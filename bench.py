@@ -494,7 +494,7 @@ def run_native(args):
         e2e = {"value": K * T * n_e2e / e2e_s, "unit": "rollout-steps/s",
                "h2d_bytes_per_step": int(st.size * 4), "d2h_bytes_per_step": int(_native.MPPI_OUT_FLOATS * 4),
                "ms_per_step": e2e_s / n_e2e * 1e3, "steps": n_e2e,
-               "note": "public class compute_control_input(): state passes as a by-value kernel parameter block, u_prev stays device-resident (warm start), out vector is copied to pinned host memory and synchronised"}
+               "note": "public class compute_control_input(): state passes as a by-value kernel parameter block, u_prev stays device-resident (warm start), the last block of the step stores the out vector into mapped pinned host memory and the call spins on its sequence word"}
     else:
         # multi-rank e2e: the sharded step plus a D2H of the out vector on every rank, wall clock max over ranks
         n_e2e = max(10, min(args.steps, 100))
