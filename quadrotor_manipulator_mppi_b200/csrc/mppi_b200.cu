@@ -442,8 +442,21 @@ mppi_status_t launch_weight(mppi_ctx *h, const float *d_noise, bool fuse, const 
             if (oe != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 2; }
             h->wn_resident = per_sm * h->num_sms;
         }
-        int G = h->wn_resident / T;
+        int G = h->wn_resident / T;                       // small problems: one resident wave (latency)
         if (G < 1) G = 1;
+        // Large problems: ~300 KB of noise per block and a block count that is a multiple of the SM count, so every SM
+        // streams the same number of equal blocks (measured on wb K=262144, T=64: one wave of 11 x 64 blocks 5.27 TB/s,
+        // 37 x 64 blocks = 16 per SM 5.81 TB/s, 148 x 64 blocks 4.65 TB/s -- profiles/r01/README.md).
+        {
+            const double g_target = (double)K / std::fmax(1024.0, 300e3 / (NU * 4.0));
+            if (g_target * T >= 8.0 * h->num_sms) {
+                int a = h->num_sms, b = T;
+                while (b) { const int r = a % b; a = b; b = r; }
+                const int g0 = h->num_sms / a;             // smallest G with G*T % num_sms == 0
+                const int m = (int)std::floor(g_target / g0 + 0.5);
+                G = m >= 1 ? m * g0 : (int)(g_target + 0.5);
+            }
+        }
         if (G > h->max_parts) G = h->max_parts;
         const int gmax = (K + 127) / 128;
         if (G > gmax) G = gmax;
