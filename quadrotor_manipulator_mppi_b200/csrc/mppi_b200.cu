@@ -394,11 +394,10 @@ mppi_status_t launch_weight(mppi_ctx *h, const float *d_noise, bool fuse, const 
                             float *d_out, cudaStream_t st, const P2PParams &X)
 {
     constexpr int NU = ModelNu<MODEL>::value;
-    constexpr int NCH = philox_calls(NU);
     const int K = h->P.K, T = h->P.T;
     const size_t fin_floats = (size_t)2 * T * NU + NU;
     if (!d_noise) {
-        const int TC = T * NCH;
+        const int TC = T;                       // one thread per horizon step (all Philox calls of the step), R sample sub-ranges
         int R = 512 / TC;
         if (R < 1) R = 1;
         int threads = ((TC * R + 31) / 32) * 32;
@@ -409,7 +408,7 @@ mppi_status_t launch_weight(mppi_ctx *h, const float *d_noise, bool fuse, const 
         if (blocks < 1) blocks = 1;
         const int chunk = (K + blocks - 1) / blocks;
         blocks = (K + chunk - 1) / chunk;
-        size_t smem_floats = (size_t)2 * kWeightTile + (size_t)R * TC * 6;
+        size_t smem_floats = (size_t)2 * kWeightTile + (size_t)R * TC * (4 * ((NU + 3) / 4));
         if (smem_floats < fin_floats) smem_floats = fin_floats;
         // fused steps launch it as a programmatic dependent of the rollout kernel: its launch overlaps the rollout's drain
         cudaLaunchConfig_t lc{};

@@ -614,9 +614,10 @@ __device__ void reduce_partials_and_finalize(const StepParams &P, const DynBlock
 }
 
 // ------------------------------------------------------------------------------------------
-// K3 (Philox): thread = (horizon step t, Philox chunk c) x R sub-ranges of the block's sample
-// chunk; the noise is regenerated from its address, zero-weight samples are skipped (exact:
-// w == 0.0f contributes 0).  part[b][T*nu+2].
+// K3 (Philox): thread = horizon step t x R sub-ranges of the block's sample chunk; the noise of
+// (sample, t) is regenerated from its address exactly as the rollout kernel generates it (all Philox
+// calls of the step in one thread, packed Box-Muller on the pairs that are needed: 4 of 6 for nu = 7),
+// zero-weight samples are skipped (exact: w == 0.0f contributes 0).
 // S/mppi_solver/mppi.py:143-148,173-193.
 // ------------------------------------------------------------------------------------------
 template <int MODEL>
@@ -627,7 +628,8 @@ weight_philox_kernel(const __grid_constant__ StepParams P, const __grid_constant
                      const float *u_nom, float *u_new, float *out, const __grid_constant__ P2PParams X)
 {
     constexpr int NU = ModelNu<MODEL>::value;
-    constexpr int NCH = philox_calls(NU);             // one thread per (horizon step, Philox call): six normals each
+    constexpr int NQ = (NU + 3) / 4;                  // quads of normals per (sample, step), as in the rollout kernel
+    constexpr int NUP = 4 * NQ;
     extern __shared__ __align__(16) float s_dyn[];      // [kWeightTile] weights | [kWeightTile] indices | reduction / finalize scratch
     float *s_w = s_dyn;
     int *s_idx = reinterpret_cast<int *>(s_dyn + kWeightTile);
@@ -635,19 +637,19 @@ weight_philox_kernel(const __grid_constant__ StepParams P, const __grid_constant
     __shared__ float s_eta[32], s_eta2[32];
     __shared__ int s_cnt[32];
 
-    const int TC = P.T * NCH;
+    const int TC = P.T;
     const int R = blockDim.x / TC;
     const int tid = threadIdx.x;
     const bool worker = tid < R * TC;
-    const int r = tid / TC, tc = tid - r * TC;
-    const int c = tc % NCH;
-    const int t = tc / NCH;
+    const int r = tid / TC, t = tid - r * TC;
     asm volatile("griddepcontrol.wait;" ::: "memory");      // PDL: launched while the rollout kernel drains (no-op otherwise)
     const float rho = decode_ordered(*rho_enc);
     const int k0 = blockIdx.x * chunk;
     const int k1 = min(P.K, k0 + chunk);
 
-    float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float acc[NUP];
+#pragma unroll
+    for (int i = 0; i < NUP; ++i) acc[i] = 0.f;
     float eta = 0.f, eta2 = 0.f;
 
     for (int base = k0; base < k1; base += kWeightTile) {
@@ -686,11 +688,18 @@ weight_philox_kernel(const __grid_constant__ StepParams P, const __grid_constant
         if (worker) {
             for (int j = r; j < n_nz; j += R) {
                 const float w = s_w[j];
-                float n6[6];
-                normal6(static_cast<uint32_t>(P.k_offset + base + s_idx[j]), static_cast<uint32_t>(tc),
-                        D.step_lo, D.step_hi, P.rkeys, n6);
+                float unif[6 * philox_calls(NU)];
+                philox_step_uniforms<philox_calls(NU)>(static_cast<uint32_t>(P.k_offset + base + s_idx[j]), static_cast<uint32_t>(t),
+                                                       D.step_lo, D.step_hi, P.rkeys, unif);
 #pragma unroll
-                for (int jj = 0; jj < 6; ++jj) acc[jj] = fmaf(w, n6[jj], acc[jj]);      // sigma is applied once, after the reduction
+                for (int e = 0; e < NQ; ++e) {         // sigma is applied once, after the reduction
+                    f2 n02, n13;
+                    normals_quad(unif, e, n02, n13);
+                    acc[4 * e] = fmaf(w, n02.v.x, acc[4 * e]);
+                    acc[4 * e + 1] = fmaf(w, n13.v.x, acc[4 * e + 1]);
+                    acc[4 * e + 2] = fmaf(w, n02.v.y, acc[4 * e + 2]);
+                    acc[4 * e + 3] = fmaf(w, n13.v.y, acc[4 * e + 3]);
+                }
             }
         }
     }
@@ -701,7 +710,7 @@ weight_philox_kernel(const __grid_constant__ StepParams P, const __grid_constant
     __syncthreads();
     if (worker) {
 #pragma unroll
-        for (int j = 0; j < 6; ++j) s_red[(r * TC + tc) * 6 + j] = acc[j];
+        for (int i = 0; i < NUP; ++i) s_red[(r * TC + t) * NUP + i] = acc[i];
     }
     __syncthreads();
     // Block sums go into 64-bit FIXED-POINT accumulators with integer atomics: integer addition is
@@ -709,15 +718,11 @@ weight_philox_kernel(const __grid_constant__ StepParams P, const __grid_constant
     // nothing left to reduce (a float row-per-block scheme costs ~15 us of serial L2 round trips here).
     // |sum w n| <= K * 5.7 < 2^29 for K <= 2^26, scale 2^33 -> below 2^62; resolution 1.2e-10.
     const int row = P.T * NU + 2;
-    if (tid < TC) {
-#pragma unroll
-        for (int j = 0; j < 6; ++j) {
-            if (6 * c + j < NU) {
-                float v = 0.f;
-                for (int rr = 0; rr < R; ++rr) v += s_red[(rr * TC + tc) * 6 + j];
-                if (v != 0.f) atomicAdd(fix + t * NU + 6 * c + j, static_cast<unsigned long long>(__float2ll_rn(v * kFixScale)));
-            }
-        }
+    for (int o = tid; o < TC * NU; o += blockDim.x) {          // one output (t, i) per thread
+        const int tt = o / NU, i = o - tt * NU;
+        float v = 0.f;
+        for (int rr = 0; rr < R; ++rr) v += s_red[(rr * TC + tt) * NUP + i];
+        if (v != 0.f) atomicAdd(fix + o, static_cast<unsigned long long>(__float2ll_rn(v * kFixScale)));
     }
     if (tid == 0) {
         float e = 0.f, e2 = 0.f;
