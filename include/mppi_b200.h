@@ -76,7 +76,7 @@ typedef enum {
 #define MPPI_OUT_ETA 54         /* sum of unnormalised weights                           */
 #define MPPI_OUT_ESS 55         /* effective sample size (sum w)^2 / sum w^2             */
 #define MPPI_OUT_STEP 56        /* low 24 bits of the step counter used                  */
-#define MPPI_OUT_TORQUE 57      /* ARM7 + MPPI_OPT_TORQUE_LAW: torque[7] = M[6:,6:] (kp (qdes - q) - kd qdot) + nle[6:] (kinova.py:184) */
+#define MPPI_OUT_TORQUE 57      /* ARM7 / WB11 + MPPI_OPT_TORQUE_LAW: torque[7] = M[6:,6:] (kp (qdes - q) - kd qdot) + nle[6:] (kinova.py:184) */
 
 /* Replaces the hard-coded constructor constants of mppi.py:37-42,75,
  * sampling/standard_normal_noise.py:17, drone_mppi.py:16-19,32,34 and
@@ -129,7 +129,8 @@ typedef struct mppi_config {
 #define MPPI_COST_JOINT_LIMIT 16 /* sum_t gamma^t * limit_penalty * [any joint outside q_lower..q_upper]      */
 /* Options that share the cost_flags word (they do not select the extra-cost kernels): */
 #define MPPI_COST_MASK 31
-#define MPPI_OPT_TORQUE_LAW 256  /* ARM7: the finalize block also evaluates the arm node's torque law (kinova.py:126-131,184) */
+#define MPPI_OPT_TORQUE_LAW 256  /* ARM7 / WB11: the finalize block also evaluates the arm node's torque law (kinova.py:126-131,184);
+                                    WB11 takes the base attitude and twist from its own state (rpy, R^T v, w) */
 
 typedef struct mppi_ctx *mppi_handle_t;
 

@@ -197,7 +197,7 @@ void load_extra_costs(mppi_ctx *h, const mppi_config_t *cfg)
 {
     StepParams &P = h->P;
     P.cost_flags = cfg->cost_flags;
-    if (h->cfg.model != MPPI_MODEL_ARM7) P.cost_flags &= ~MPPI_OPT_TORQUE_LAW;     // the torque law is the arm node's
+    if (h->cfg.model != MPPI_MODEL_ARM7 && h->cfg.model != MPPI_MODEL_WB11) P.cost_flags &= ~MPPI_OPT_TORQUE_LAW;   // needs an arm
     P.gamma = cfg->gamma;
     P.covar_scale = cfg->covar_weight * (cfg->lambda_ * (1.0f - cfg->alpha));     // covar_cost.py:14,23
     P.action_weight = cfg->action_weight;

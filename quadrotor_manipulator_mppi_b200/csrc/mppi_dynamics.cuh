@@ -101,33 +101,30 @@ __device__ __noinline__ void rnea_arm7(const ChainDev &ch, const ArmInertiaDev &
     }
 }
 
-// Called by ONE full warp.  state = q[7], qdot[7], base xyz + quat xyzw, base twist (linear, angular; base frame).
-// dq = qdes - q.  Writes torque[7] = M (kp dq - kd qdot) + nle.
-__device__ __forceinline__ void arm_torque_warp(const StepParams &P, const float *state, const float *dq, float *torque)
+// Called by ONE full warp.  q / qd: measured joint state; a0: gravity as an upward base acceleration in the base frame;
+// v0, w0: base twist (linear, angular; base frame); dq = qdes - q.  Writes torque[7] = M (kp dq - kd qdot) + nle.
+__device__ __forceinline__ void arm_torque_warp(const StepParams &P, const float *q, const float *qdot, const float *a0_in,
+                                                const float *v0_in, const float *w0_in, const float *dq, float *torque)
 {
     const int lane = threadIdx.x & 31;
-    float cq[7], sq[7], qd[7], qdd[7], w0[3] = {0.f, 0.f, 0.f}, v0[3] = {0.f, 0.f, 0.f}, a0[3] = {0.f, 0.f, 0.f};
+    float cq[7], sq[7], qd[7], qdd[7], w0[3], v0[3], a0[3];
 #pragma unroll
     for (int i = 0; i < 7; ++i) {
-        sincos_pi(state[i], sq[i], cq[i]);
-        qd[i] = (lane == 0) ? state[7 + i] : 0.f;
+        sincos_pi(q[i], sq[i], cq[i]);
+        qd[i] = (lane == 0) ? qdot[i] : 0.f;                  // lane 0: nle = rnea(q, v, 0); lanes 1..7: columns of M
         qdd[i] = (lane == i + 1) ? 1.f : 0.f;
     }
-    if (lane == 0) {
-        // gravity as an upward base acceleration, expressed in the base frame: R_base^T (0, 0, g); R from the unit quaternion
-        const float x = state[17], y = state[18], z = state[19], wq = state[20];
-        const float s2 = 2.0f / fmaxf(x * x + y * y + z * z + wq * wq, 1e-30f);
-        a0[0] = P.arm_inertia.gravity * s2 * (x * z - y * wq);
-        a0[1] = P.arm_inertia.gravity * s2 * (y * z + x * wq);
-        a0[2] = P.arm_inertia.gravity * (1.0f - s2 * (x * x + y * y));
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { v0[k] = state[21 + k]; w0[k] = state[24 + k]; }
+    for (int k = 0; k < 3; ++k) {
+        a0[k] = (lane == 0) ? a0_in[k] : 0.f;
+        v0[k] = (lane == 0) ? v0_in[k] : 0.f;
+        w0[k] = (lane == 0) ? w0_in[k] : 0.f;
     }
     float tau[7];
     rnea_arm7(P.chain, P.arm_inertia, cq, sq, qd, qdd, w0, v0, a0, tau);
     // lane 0 holds nle, lane j holds column j - 1 of M: scale the columns by the desired acceleration and sum lanes 0..7
     const int j = (lane >= 1 && lane <= 7) ? lane - 1 : 0;
-    const float ades = P.arm_inertia.kp * dq[j] - P.arm_inertia.kd * state[7 + j];
+    const float ades = P.arm_inertia.kp * dq[j] - P.arm_inertia.kd * qdot[j];
     const float scale = (lane == 0) ? 1.0f : (lane <= 7 ? ades : 0.0f);
 #pragma unroll
     for (int i = 0; i < 7; ++i) {
@@ -137,6 +134,31 @@ __device__ __forceinline__ void arm_torque_warp(const StepParams &P, const float
         t += __shfl_xor_sync(0xffffffffu, t, 4);
         if (lane == 0) torque[i] = t;
     }
+}
+
+// ARM7 state: q[7], qdot[7], base xyz + quat xyzw, base twist (linear, angular; base frame -- Pinocchio's v[:6]).
+__device__ __forceinline__ void arm_torque_from_arm_state(const StepParams &P, const float *state, const float *dq, float *torque)
+{
+    // R_base^T (0, 0, g) = g * (third row of R); R from the normalised quaternion
+    const float x = state[17], y = state[18], z = state[19], wq = state[20];
+    const float s2 = 2.0f / fmaxf(x * x + y * y + z * z + wq * wq, 1e-30f), g = P.arm_inertia.gravity;
+    const float a0[3] = {g * s2 * (x * z - y * wq), g * s2 * (y * z + x * wq), g * (1.0f - s2 * (x * x + y * y))};
+    arm_torque_warp(P, state, state + 7, a0, state + 21, state + 24, dq, torque);
+}
+
+// WB11 state: p[3], rpy[3], v[3] (world), w[3] (body rates), q[7], qdot[7]: attitude R = Rz(yaw) Ry(pitch) Rx(roll),
+// base twist = (R^T v, w).
+__device__ __forceinline__ void arm_torque_from_wb_state(const StepParams &P, const float *state, const float *dq, float *torque)
+{
+    float sr, cr, sp, cp, sy, cy, R[9];
+    sincos_pi(state[3], sr, cr); sincos_pi(state[4], sp, cp); sincos_pi(state[5], sy, cy);
+    rpy_matrix(sr, cr, sp, cp, sy, cy, R);
+    const float g = P.arm_inertia.gravity;
+    const float a0[3] = {g * R[6], g * R[7], g * R[8]};
+    const float *v = state + 6;
+    const float v0[3] = {R[0] * v[0] + R[3] * v[1] + R[6] * v[2], R[1] * v[0] + R[4] * v[1] + R[7] * v[2],
+                         R[2] * v[0] + R[5] * v[1] + R[8] * v[2]};
+    arm_torque_warp(P, state + 12, state + 19, a0, v0, state + 9, dq, torque);
 }
 
 }  // namespace mppi

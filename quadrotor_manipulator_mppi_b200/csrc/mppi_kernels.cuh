@@ -431,13 +431,15 @@ __device__ void finalize_block(const StepParams &P, const DynBlock &D, const flo
             out[MPPI_OUT_REACH] = fabsf(Tp.pxy.v.x - D.target_pos[0]) + fabsf(Tp.pxy.v.y - D.target_pos[1]) + fabsf(Tp.pz - D.target_pos[2]);
         }
     }
-    if constexpr (MODEL == MPPI_MODEL_ARM7) {
+    if constexpr (MODEL == MPPI_MODEL_ARM7 || MODEL == MPPI_MODEL_WB11) {
         // computed-torque law of the arm node (kinova.py:184) on a fourth warp: 8 Newton-Euler passes on 8 lanes
+        constexpr int A0 = (MODEL == MPPI_MODEL_WB11) ? 4 : 0;
         const int tw = (blockDim.x >= 128) ? 3 : 0;
         if (out != nullptr && (P.cost_flags & MPPI_OPT_TORQUE_LAW) && P.chain.prismatic == 0 && (threadIdx.x >> 5) == tw) {
             float dq[7];                     // qdes - q without cancellation: u0_old dt + u0_new dt^2 / 2 (mppi.py:158)
-            for (int i = 0; i < 7; ++i) dq[i] = u0_old[i] * dt + 0.5f * un[i] * dt * dt;
-            arm_torque_warp(P, D.state, dq, out + MPPI_OUT_TORQUE);
+            for (int i = 0; i < 7; ++i) dq[i] = u0_old[A0 + i] * dt + 0.5f * un[A0 + i] * dt * dt;
+            if constexpr (MODEL == MPPI_MODEL_ARM7) arm_torque_from_arm_state(P, D.state, dq, out + MPPI_OUT_TORQUE);
+            else arm_torque_from_wb_state(P, D.state, dq, out + MPPI_OUT_TORQUE);
         }
     }
     if (out != nullptr && threadIdx.x >= 64 && threadIdx.x < 96) {

@@ -20,7 +20,8 @@ class MPPI:
     MODEL = _native.MODEL_WB11
 
     def __init__(self, *, n_samples: int = 1000, n_horizon: int = 32, dt: float = 0.01, sigma=None,
-                 lam: float = 0.1, seed: int = 0, device=None, mass: float = 14.7 + 5.5, k_offset: int = 0):
+                 lam: float = 0.1, seed: int = 0, device=None, mass: float = 14.7 + 5.5, k_offset: int = 0,
+                 torque_law: bool = False, torque_gains=(400.0, 40.0)):
         self.n_samples, self.n_horizon, self.dt, self.n_action = int(n_samples), int(n_horizon), float(dt), 11
         self._lambda = float(lam)
         self.mass = float(mass)
@@ -28,7 +29,10 @@ class MPPI:
             sigma = (30.0 * mass, 1.0, 1.0, 1.0) + (0.1,) * 7
         qp = (mass, 1.0 / 1.57, 1.0 / 3.93, 1.0 / 2.59, 0.0, -9.81)
         self._solver = NativeSolver(self.MODEL, n_samples=n_samples, n_horizon=n_horizon, dt=dt, lam=lam,
-                                    sigma=sigma, seed=seed, device=device, quad_params=qp, k_offset=k_offset)
+                                    sigma=sigma, seed=seed, device=device, quad_params=qp, k_offset=k_offset,
+                                    cost_flags=_native.OPT_TORQUE_LAW if torque_law else 0, torque_gains=torque_gains)
+        self.torque_law = bool(torque_law)
+        self.torque = np.zeros(7)         # joint torques of the arm's computed-torque law (kinova.py:184) when enabled
         self.device = self._solver.device
         self.target_pose = Pose()
         self.target_pose.pose = torch.tensor([0.1029, 0.4055, 1.6498])
@@ -64,4 +68,6 @@ class MPPI:
         """Returns (qdes[7], vdes[7], next_base_state[12]) as numpy arrays."""
         self._sync_target()
         out = self._solver.step(self._solver.prepare_noise(noise, noise_layout))
+        if self.torque_law:
+            self.torque = out[_native.MPPI_OUT_TORQUE:_native.MPPI_OUT_TORQUE + 7].astype(np.float64)
         return out[0:7].copy(), out[7:14].copy(), out[_native.MPPI_OUT_BASE:_native.MPPI_OUT_BASE + 12].copy()

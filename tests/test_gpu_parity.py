@@ -598,6 +598,27 @@ def test_torque_law_on_a_chain_with_tilted_axes(oracle, native):
     assert not np.allclose(want, dyn.torque_law(q_full, v_full, qdes), atol=1e-2)     # a different answer from the j2s7s300's
 
 
+def test_torque_law_for_the_whole_body_model(native):
+    """WB11: base attitude from rpy, base twist (R^T v, w) from the quadrotor state."""
+    from oracle import arm_dynamics as dyn
+    from quadrotor_manipulator_mppi_b200.mppi_solver.wholebody_mppi import MPPI
+    m = MPPI(n_samples=256, n_horizon=16, torque_law=True)
+    rng = np.random.default_rng(13)
+    p, rpy = rng.uniform(-1, 1, 3) + [0, 0, 2.0], rng.uniform(-0.6, 0.6, 3)
+    v, w = rng.uniform(-1, 1, 3), rng.uniform(-1, 1, 3)
+    q, qd = rng.uniform(-3, 3, 7), rng.uniform(-1, 1, 7)
+    m.set_state(p, rpy, v, w, q, qd)
+    qdes, vdes, _ = m.compute_control_input()
+    R = dyn._rpy(*rpy)
+    twist = np.concatenate([R.T @ v, w])
+    M = dyn.mass_matrix_arm(q)
+    # the device forms qdes - q from the controls; take the same difference from the float32 outputs' source terms
+    want = M @ (400.0 * (qdes.astype(np.float64) - q.astype(np.float32).astype(np.float64)) - 40.0 * qd) \
+        + dyn.rnea_arm(q, qd, np.zeros(7), base_R=R, base_twist=twist)
+    assert np.abs(want).max() > 0.5
+    assert np.allclose(m.torque, want, rtol=2e-3, atol=2e-3), (m.torque, want)
+
+
 def test_arm_inertia_can_be_replaced(native):
     from oracle import arm_inertia_gen as gen
     from quadrotor_manipulator_mppi_b200.mppi_solver.mppi import MPPI
