@@ -34,6 +34,7 @@ def test_config_struct_mirror_and_defaults():
     assert (arm.n_samples, arm.n_horizon, arm.savgol_window) == (100, 32, 9)      # mppi.py:40-41,149
     assert abs(arm.sigma[0] - 0.1) < 1e-7 and abs(arm.lambda_ - 0.1) < 1e-7 and abs(arm.dt - 0.01) < 1e-9
     assert list(arm.cost_w)[:4] == [50.0, 30.0, 40.0, 30.0]                      # cost_manager.py:30-33
+    assert (arm.torque_kp, arm.torque_kd, arm.cost_flags) == (400.0, 40.0, 0)     # kinova.py:184; the torque law is opt-in
     drone = _native.default_config(_native.MODEL_DRONE3)
     assert (drone.n_samples, drone.n_horizon, drone.savgol_window) == (1000, 32, 5)  # drone_mppi.py:16-17,160
     assert drone.sigma[0] == 30.0 and list(drone.drone_target) == pytest.approx([1.0, 2.0, 3.4], rel=1e-6)
