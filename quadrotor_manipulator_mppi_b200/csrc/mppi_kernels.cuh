@@ -775,8 +775,14 @@ weights_kernel(const __grid_constant__ StepParams P, const float *__restrict__ S
 // of a thread's VEC lanes keeps the same input index i for the whole loop (coalesced float4 loads,
 // four in flight per thread); sums stay in registers until one fixed-order block reduction.
 // ------------------------------------------------------------------------------------------
+// At least 3 blocks per SM (<= 62 registers at nu = 11): the streaming loop needs ~45; without the bound the finalize code
+// inlined into the last block (check_reach FK, torque law) sets the kernel's register count and costs a resident block
+// -- measured 0.202 ms vs 0.131 ms for the whole-body re-read (2 vs 3 blocks per SM; 4 and 5 spill: 0.141, 0.153).
+#ifndef MPPI_WN_MINB
+#define MPPI_WN_MINB 3
+#endif
 template <int MODEL, int VEC>
-__global__ void __launch_bounds__(32 * ModelNu<MODEL>::value)
+__global__ void __launch_bounds__(32 * ModelNu<MODEL>::value, MPPI_WN_MINB)
 weighted_noise_kernel(const __grid_constant__ StepParams P, const __grid_constant__ DynBlock D,
                       const float *__restrict__ w, const float *__restrict__ noise, int32_t *rho_enc,
                       int chunk, float *__restrict__ part, const float *__restrict__ eta_part, int n_eta,
