@@ -1,0 +1,43 @@
+"""Guards on the compiled kernels' resource usage (cuobjdump, no GPU needed): a register count that creeps over an
+occupancy step is a silent performance regression -- the streaming weighting kernel once lost a resident block
+(0.130 -> 0.202 ms) when code inlined into its last block grew the kernel from 56 to 80 registers."""
+import re
+import shutil
+import subprocess
+
+import pytest
+
+
+def _resources():
+    from quadrotor_manipulator_mppi_b200 import build
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    r = subprocess.run([exe, "-res-usage", build.build()], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    out = {}
+    for name, regs, stack in re.findall(r"Function (\S+):\s*\n\s*REG:(\d+) STACK:(\d+)", r.stdout):
+        out[name] = (int(regs), int(stack))
+    return out
+
+
+def _one(res, *needles):
+    hits = [v for k, v in res.items() if all(n in k for n in needles)]
+    assert len(hits) == 1, (needles, [k for k in res if needles[0] in k])
+    return hits[0]
+
+
+def test_register_budgets_of_the_hot_kernels():
+    res = _resources()
+    # fused rollout, Philox, baked FK: 4 blocks of 128 threads per SM need <= 128 registers; no stack (no spills, no local arrays)
+    for model in (1, 3):                                        # ARM7, WB11
+        regs, stack = _one(res, f"rollout_cost_kernelILi{model}ELi0ELb1ELb0E")
+        assert regs <= 128 and stack == 0
+    for model in (0, 2):                                        # DRONE3, QUAD4
+        regs, stack = _one(res, f"rollout_cost_kernelILi{model}ELi0ELb0ELb0E")
+        assert regs <= 128 and stack == 0
+    # streaming weighting pass: 3 blocks of 32*nu threads per SM
+    assert _one(res, "weighted_noise_kernelILi3ELi4E")[0] <= 62          # nu = 11: 352 threads
+    assert _one(res, "weighted_noise_kernelILi1ELi4E")[0] <= 97          # nu = 7: 224 threads
+    # Philox weighting pass: blocks of up to 1024 threads
+    for model in range(4):
+        assert _one(res, f"weight_philox_kernelILi{model}E")[0] <= 64
