@@ -56,6 +56,13 @@ def parse_args():
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU shard exchange: fused NVLink peer exchange, or NCCL allreduce-MIN + allreduce-SUM")
     ap.add_argument("--no-flush", action="store_true", help="skip the L2 flush between steps (latency experiments)")
+    ap.add_argument("--lam", type=float, default=None, help="soft-min temperature (default: the reference's 0.1)")
+    ap.add_argument("--philox-rounds", type=int, default=None, choices=[7, 10], help="Philox4x32 round count (library default if omitted)")
+    ap.add_argument("--fused", type=int, default=-1, choices=[-1, 0, 1], help="single-launch step: -1 library default, 0 off, 1 on")
+    ap.add_argument("--time-parallel", type=int, default=-2, choices=[-2, -1, 0, 1], help="warp-per-sample kernel: -2 library default, -1 auto, 0 off, 1 on")
+    ap.add_argument("--latency-steps", type=int, default=1000, help="timed steps of the separate latency loop (0 = skip)")
+    ap.add_argument("--no-dense", action="store_true", help="skip the dense-weights (ESS >= 1e3) timing")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity self-check")
     return ap.parse_args()
 
 
@@ -263,15 +270,20 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ native arm
-def make_controller(model, K, T, device, k_offset=0, seed=0):
+def make_controller(model, K, T, device, k_offset=0, seed=0, lam=None, opts=None):
     from quadrotor_manipulator_mppi_b200.mppi_solver import drone_mppi, mppi, quad_mppi, wholebody_mppi
+    kw = dict(opts or {})
+    if lam is not None:
+        kw["lam"] = lam
     if model == "wb":
-        return wholebody_mppi.MPPI(n_samples=K, n_horizon=T, seed=seed, device=device, k_offset=k_offset)
+        kw.pop("time_parallel", None)
+        return wholebody_mppi.MPPI(n_samples=K, n_horizon=T, seed=seed, device=device, k_offset=k_offset, **kw)
     if model == "arm":
-        return mppi.MPPI(n_samples=K, n_horizon=T, seed=seed, device=device, verbose=False)
+        return mppi.MPPI(n_samples=K, n_horizon=T, seed=seed, device=device, verbose=False, **kw)
     if model == "drone":
-        return drone_mppi.MPPI(n_samples=K, n_timestep=T, seed=seed, device=device)
-    return quad_mppi.MPPI(n_samples=K, n_timestep=T, seed=seed, device=device)
+        return drone_mppi.MPPI(n_samples=K, n_timestep=T, seed=seed, device=device, **kw)
+    kw.pop("time_parallel", None)
+    return quad_mppi.MPPI(n_samples=K, n_timestep=T, seed=seed, device=device, **kw)
 
 
 def sensor_message(model, st):
@@ -292,11 +304,87 @@ def feed_state(ctrl, model, msg):
         ctrl.set_state(*msg)
 
 
+def dense_lambda(costs, target_ess: float = 2000.0) -> float:
+    """A lambda at which the soft-min keeps ESS ~ target on these costs (bisection; used for the dense-weights timing)."""
+    import torch
+    S = costs.double()
+    S = S - S.min()
+    lo, hi = 1e-4, 1e10
+    for _ in range(70):
+        mid = (lo * hi) ** 0.5
+        w = torch.exp(-S / mid)
+        if (w.sum() ** 2 / (w * w).sum()).item() < target_ess:
+            lo = mid
+        else:
+            hi = mid
+    return hi
+
+
+def timed_steps(step_fn, n, stream, device, flush, before=None):
+    """n steps, each bracketed by CUDA events on the launch stream (L2 flushed outside the events).  Returns ms[n]."""
+    import torch
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+    for i in range(n):
+        if before is not None:
+            before(i)
+        if flush is not None:
+            flush.zero_()
+        ev[i][0].record(stream)
+        step_fn()
+        ev[i][1].record(stream)
+    torch.cuda.synchronize(device)
+    return np.array([a.elapsed_time(b) for a, b in ev])
+
+
+def oracle_parity(model, solver_factory, K, T, nu, rank_costs_fn=None, budget_s=20.0):
+    """One GPU step (seed 0, step 0, nominal controls, synthetic state) against the CPU oracle on the SAME Philox noise
+    (oracle/mppi_oracle.c regenerates it from the same counters): per-sample costs on all K samples, and the updated
+    controls stage-isolated (the oracle's weighting on the GPU's costs) -- SURVEY 8(c) protocol.  Checker only."""
+    import torch
+    from oracle import oracle as orc
+    orc.build()
+    orc.set_threads(len(os.sched_getaffinity(0)))
+    sigma = {"wb": [30 * 20.2, 1, 1, 1] + [0.1] * 7, "arm": [0.1] * 7, "drone": [30.0] * 3, "quad": [30 * 14.7, 1, 1, 1]}[model]
+    st = synthetic_state(model)
+    u = nominal_controls(model, T)
+    s = solver_factory()
+    s.set_state(st)
+    s.u_prev = torch.from_numpy(u)
+    rounds = s.get_option(1)
+    out = s.step(None, step_counter=0).copy()
+    S_gpu = s.costs.cpu().numpy()
+    u_gpu = s.u_prev.cpu().numpy()
+    t0 = time.perf_counter()
+    noise = orc.philox_noise(K, T, nu, sigma, seed=0, step=0, rounds=rounds)
+    if model == "wb":
+        S_ref = orc.wb_costs(noise, u, st[:12], st[12:19], st[19:26])
+    elif model == "arm":
+        S_ref = orc.arm_costs(noise, u, st[:7], st[7:14], st[14:21])
+    elif model == "drone":
+        S_ref = orc.drone_costs(noise, u, st[:3], st[3:6])
+    else:
+        S_ref = orc.quad_costs(noise, u, st)
+    lam = float(s.cfg.lambda_)
+    iso = orc._update(S_gpu, noise, u, lam, int(s.cfg.savgol_window))
+    cpu_s = time.perf_counter() - t0
+    rel = np.abs(S_gpu.astype(np.float64) - S_ref) / np.maximum(np.abs(S_ref), 1e-30)
+    S_err = float(rel.max())
+    u_err = float(np.abs(u_gpu.astype(np.float64) - iso["u_new"]).max() / max(np.abs(iso["u_new"]).max(), 1e-30))
+    res = {"against": "oracle/mppi_oracle.c on the identical Philox noise (same seed / step / global sample index)",
+           "samples_checked": int(K), "S_rel_err_max": S_err, "S_outliers_gt_1e-5": int((rel > 1e-5).sum()),
+           "u_new_rel_err_stage_isolated": u_err, "rho_equal_min_S": bool(out[53] == S_gpu.min()),
+           "tolerance": {"S": 1e-4, "u_new_stage_isolated": 1e-5}, "oracle_seconds": cpu_s,
+           "ok": bool(S_err < 1e-4 and u_err < 1e-5 and out[53] == S_gpu.min())}
+    s.close()
+    return res
+
+
 def run_native(args):
     import torch
     import torch.distributed as dist
     from quadrotor_manipulator_mppi_b200 import _native
     from quadrotor_manipulator_mppi_b200.core import NativeSolver
+    from quadrotor_manipulator_mppi_b200.sharded import ShardedStepper, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -312,17 +400,21 @@ def run_native(args):
     K = args.samples or spec["K"]
     T = args.horizon or spec["T"]
     nu = spec["nu"]
-    assert K % world == 0, "K must divide across ranks"
-    K_loc = K // world
+    k_off, K_loc = shard_range(K, world, rank)            # contiguous shards; the first K % world ranks hold one more sample
     model_id = {"wb": _native.MODEL_WB11, "arm": _native.MODEL_ARM7, "drone": _native.MODEL_DRONE3, "quad": _native.MODEL_QUAD4}[args.model]
-    qp = None
-    if args.model == "wb":
-        qp = (14.7 + 5.5, 1 / 1.57, 1 / 3.93, 1 / 2.59, 0.0, -9.81)
-    solver = NativeSolver(model_id, n_samples=K_loc, n_horizon=T, seed=0, device=device, k_offset=rank * K_loc, quad_params=qp)
+    qp = (14.7 + 5.5, 1 / 1.57, 1 / 3.93, 1 / 2.59, 0.0, -9.81) if args.model == "wb" else None
+    opts = dict(philox_rounds=args.philox_rounds, fused=None if args.fused < 0 else args.fused,
+                time_parallel=None if args.time_parallel < -1 else args.time_parallel)
+
+    def make_solver(k_local=K_loc, k_offset=k_off, lam=args.lam):
+        return NativeSolver(model_id, n_samples=k_local, n_horizon=T, seed=0, device=device, k_offset=k_offset, quad_params=qp,
+                            lam=lam, **opts)
+
+    solver = make_solver()
     st = synthetic_state(args.model)
     solver.set_state(st)
-    solver.u_prev = torch.from_numpy(nominal_controls(args.model, T))
-    from quadrotor_manipulator_mppi_b200.sharded import ShardedStepper
+    u_nom0 = torch.from_numpy(nominal_controls(args.model, T))
+    solver.u_prev = u_nom0
     stepper = ShardedStepper(solver, exchange=args.exchange)
     noise = None
     if args.noise == "injected":
@@ -332,19 +424,33 @@ def run_native(args):
     stream = torch.cuda.current_stream(device)
     rng = np.random.default_rng(1234)
 
+    def launches_per_step(s):
+        path = s.last_path
+        if path in ("fused", "time_parallel"):
+            return 1
+        base = 2 if noise is None else 3                    # rollout + weighting(+finalize) [+ weights kernel]
+        return base if (world == 1 or stepper.exchange == "p2p") else base + 1      # + finalize kernel on the allreduce path
+
     def one_step():
         if world == 1:
             solver.step_async(noise)
-            return 2 if noise is None else 3        # rollout + weighting(+finalize) [+ weights kernel]
-        stepper.step_async(noise)
-        if stepper.exchange == "p2p":
-            return 2 if noise is None else 3
-        return 3 if noise is None else 4
+        else:
+            stepper.step_async(noise)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(device)
+
+    def jitter(_i=None):
+        # state/goal jitter for latency realism; by-value kernel parameter, no H2D copy
+        jit = st.copy()
+        jit[:3] += rng.uniform(-0.05, 0.05, 3).astype(np.float32)
+        if world > 1:                                       # replicas must see the same sensor message
+            t = torch.from_numpy(jit).to(device)
+            dist.broadcast(t, 0)
+            jit = t.cpu().numpy()
+        solver.set_state(jit)
 
     for _ in range(max(args.warmup, 3)):
         if flush is not None:
@@ -352,32 +458,70 @@ def run_native(args):
         one_step()
     barrier()
 
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    launches = 0
     with ClockSampler(local_rank) as clocks:
         barrier()
         t_wall0 = time.perf_counter()
-        for i in range(args.steps):
-            # state/goal jitter for latency realism; by-value kernel parameter, no H2D copy
-            jit = st.copy()
-            jit[:3] += rng.uniform(-0.05, 0.05, 3).astype(np.float32)
-            solver.set_state(jit)
-            if flush is not None:
-                flush.zero_()
-            ev[i][0].record(stream)
-            launches += one_step()
-            ev[i][1].record(stream)
+        step_ms = timed_steps(one_step, args.steps, stream, device, flush, before=jitter)
         barrier()
         wall = time.perf_counter() - t_wall0
-    step_ms = torch.tensor([a.elapsed_time(b) for a, b in ev], dtype=torch.float64, device=device)
+    launches = launches_per_step(solver) * args.steps
+    step_ms_t = torch.tensor(step_ms, dtype=torch.float64, device=device)
     if world > 1:
-        dist.all_reduce(step_ms, op=dist.ReduceOp.MAX)       # per-step max over ranks
-    step_ms = step_ms.cpu().numpy()
+        dist.all_reduce(step_ms_t, op=dist.ReduceOp.MAX)       # per-step max over ranks
+    step_ms = step_ms_t.cpu().numpy()
     total_ms = float(step_ms.sum())
     value = K * T * args.steps / (total_ms * 1e-3)
+    out_last = solver._outs[(solver._out_i - 1) & 3].cpu().numpy()
+    S_dev = solver.costs
+    weights_info = {"lambda": float(solver.cfg.lambda_), "ess": float(out_last[_native.MPPI_OUT_ESS]),
+                    "nonzero_weights_this_shard": int((torch.exp(-(S_dev - S_dev.min()) / float(solver.cfg.lambda_)) != 0).sum().item()),
+                    "path": solver.last_path}
 
-    # ---- collectives timed on their own (latency-bound, reported separately)
+    # ---- latency distribution on its own: >= 1000 timed steps after >= 50 warm-ups, independent of --steps
+    n_lat = max(args.latency_steps, 0)
+    latency = None
+    if n_lat > 0:
+        for _ in range(50):
+            one_step()
+        barrier()
+        lat = timed_steps(one_step, n_lat, stream, device, flush, before=jitter if world == 1 else None)
+        lat_t = torch.tensor(lat, dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(lat_t, op=dist.ReduceOp.MAX)
+        lat = lat_t.cpu().numpy()
+        latency = {"n": int(n_lat), "warmup": 50, "p50": float(np.percentile(lat, 50)), "p90": float(np.percentile(lat, 90)),
+                   "p99": float(np.percentile(lat, 99)), "max": float(lat.max()), "mean": float(lat.mean()),
+                   "host_wall_ms_per_step_incl_flush": wall / args.steps * 1e3}
+
+    # ---- the same K x T with weights that do NOT collapse (ESS >= 1e3): the weighting pass regenerates all of the noise
+    dense = None
+    if noise is None and not args.no_dense:
+        lam_d = dense_lambda(S_dev, min(2000.0, max(2.0, K_loc / 4.0)))
+        if world > 1:
+            lt = torch.tensor([lam_d], dtype=torch.float64, device=device)
+            dist.broadcast(lt, 0)
+            lam_d = float(lt.item())
+        solver.update_config(lambda_=lam_d)
+        for _ in range(5):
+            one_step()
+        barrier()
+        dms = timed_steps(one_step, max(20, min(args.steps, 100)), stream, device, flush)
+        dms_t = torch.tensor(dms, dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(dms_t, op=dist.ReduceOp.MAX)
+        dms = dms_t.cpu().numpy()
+        od = solver._outs[(solver._out_i - 1) & 3].cpu().numpy()
+        dense = {"lambda": lam_d, "ess": float(od[_native.MPPI_OUT_ESS]), "ms_per_step_dense_weights": float(dms.mean()),
+                 "p50": float(np.percentile(dms, 50)), "p99": float(np.percentile(dms, 99)), "steps": int(len(dms)),
+                 "note": "same K x T; lambda raised until ESS ~ 2e3, so (nearly) every sample keeps a non-zero weight"}
+        solver.update_config(lambda_=args.lam if args.lam is not None else 0.1)
+        solver.u_prev = u_nom0
+        solver.set_state(st)
+
+    # ---- collectives timed on their own (latency-bound, reported separately) + the contract path (allreduce-MIN / -SUM)
     coll = None
+    exchange_nccl = None
+    parity = None
     if world > 1:
         e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         tm, ts = [], []
@@ -392,6 +536,79 @@ def run_native(args):
         solver.rho_enc.fill_(0x7fffffff)
         coll = {"allreduce_min_ms_p50": float(np.percentile(tm[5:], 50)), "allreduce_sum_ms_p50": float(np.percentile(ts[5:], 50)),
                 "allreduce_sum_floats": int(solver.wsum.numel())}
+        # the step through NCCL allreduce-MIN + allreduce-SUM (the exchange BASELINE.json names), same shard, same invocation
+        solver_n = make_solver()
+        solver_n.set_state(st)
+        solver_n.u_prev = u_nom0
+        stepper_n = ShardedStepper(solver_n, exchange="nccl")
+        for _ in range(5):
+            stepper_n.step_async(noise)
+        barrier()
+        nms = timed_steps(lambda: stepper_n.step_async(noise), max(20, min(args.steps, 100)), stream, device, flush)
+        nms_t = torch.tensor(nms, dtype=torch.float64, device=device)
+        dist.all_reduce(nms_t, op=dist.ReduceOp.MAX)
+        nms = nms_t.cpu().numpy()
+        exchange_nccl = {"ms_per_step": float(nms.mean()), "p50": float(np.percentile(nms, 50)), "p99": float(np.percentile(nms, 99)),
+                         "steps": int(len(nms)), "value": K * T / (float(nms.mean()) * 1e-3),
+                         "path": "rollout -> allreduce-MIN(int32) -> weighting -> allreduce-SUM([T*nu+2] f32) -> finalize"}
+
+        # ---- parity self-check (outside every timed region): N ranks == 1 rank, both exchanges
+        checks = {}
+        # (a) no peer-exchange timeout during the timed steps: blocking step raises on the sticky failure word
+        try:
+            o_blk = stepper.step(noise, state=st)
+            checks["exchange_timeouts"] = 0 if float(o_blk[_native.MPPI_OUT_STEP]) >= 0 else 1
+        except _native.MppiError as e:
+            checks["exchange_timeouts"] = 1
+            checks["exchange_error"] = str(e)
+        # (b) one step from identical inputs through p2p, NCCL and (rank 0) a single full-K solver
+        SC = 1000003
+        res = {}
+        for name, stp, slv in (("used", stepper, solver), ("nccl", stepper_n, solver_n)):
+            slv.set_state(st)
+            slv.u_prev = u_nom0
+            slv.step_counter = SC
+            o = stp.step(noise, state=st)
+            res[name] = (slv.u_prev.clone(), torch.from_numpy(np.array(o, copy=True)).to(device), slv.costs.clone())
+        u_used, o_used, S_used = res["used"]
+        u_nccl, o_nccl, _ = res["nccl"]
+        gu = [torch.empty_like(u_used) for _ in range(world)]
+        go = [torch.empty_like(o_used) for _ in range(world)]
+        dist.all_gather(gu, u_used)
+        dist.all_gather(go, o_used)
+        checks["ranks_bit_identical_u_new"] = bool(all(torch.equal(gu[0], g) for g in gu))
+        checks["ranks_bit_identical_out"] = bool(all(torch.equal(go[0], g) for g in go))
+        checks["out_step_nonnegative"] = bool(all(float(g[_native.MPPI_OUT_STEP]) >= 0 for g in go))
+        un = u_nccl.double()
+        checks["p2p_vs_nccl_u_new_rel"] = float(((u_used.double() - un).abs().max() / un.abs().max().clamp_min(1e-30)).item())
+        # costs of every shard -> rank 0 (ragged shards: pad to the largest)
+        kmax = (K + world - 1) // world
+        pad = torch.full((kmax,), float("nan"), device=device)
+        pad[:K_loc] = S_used
+        gs = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(gs, pad)
+        if rank == 0:
+            full = make_solver(k_local=K, k_offset=0)
+            full.set_state(st)
+            full.u_prev = u_nom0
+            full.step(noise if noise is None else None, step_counter=SC)
+            S_all = torch.cat([gs[r][:shard_range(K, world, r)[1]] for r in range(world)])
+            checks["sharded_costs_bitwise_equal_single_rank"] = bool(torch.equal(S_all, full.costs))
+            uf = full.u_prev.double()
+            checks["sharded_vs_single_rank_u_new_rel"] = float(((u_used.double() - uf).abs().max() / uf.abs().max().clamp_min(1e-30)).item())
+            full.close()
+        ok_local = (checks["exchange_timeouts"] == 0 and checks["ranks_bit_identical_u_new"] and checks["ranks_bit_identical_out"]
+                    and checks["out_step_nonnegative"] and checks["p2p_vs_nccl_u_new_rel"] <= 1e-6
+                    and checks.get("sharded_costs_bitwise_equal_single_rank", True)
+                    and checks.get("sharded_vs_single_rank_u_new_rel", 0.0) <= 1e-5)
+        okt = torch.tensor([1 if ok_local else 0], dtype=torch.int32, device=device)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        checks["ok"] = bool(int(okt.item()) == 1)
+        checks["exchange_checked"] = [stepper.exchange, "nccl"]
+        checks["tolerance"] = {"p2p_vs_nccl": 1e-6, "sharded_vs_single_rank_u_new": 1e-5, "costs": "bitwise"}
+        parity = checks
+        solver.set_state(st)
+        solver.u_prev = u_nom0
 
     # ---- roofline of the dominant kernel (fused rollout+cost), timed alone with events on its stream
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -412,27 +629,37 @@ def run_native(args):
         solver.finalize()
     k_ms, w_ms = float(np.mean(kt[2:])), float(np.mean(wt[2:]))
     fp32_peak = _native.measure_fp32_peak(local_rank)
-    alg_flops = _native.algorithmic_flops(model_id) * K_loc * T
-    achieved = alg_flops / (k_ms * 1e-3) / 1e12
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        try:
-            traffic = json.load(open(tpath)).get(f"{args.model}_{args.noise}_K{K_loc}_T{T}")
-        except Exception:
-            traffic = None
+    alg = _native.algorithmic_flops(model_id)
+    achieved = alg * K_loc * T / (k_ms * 1e-3) / 1e12
+    prof = {}
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_metrics.json"))).get(f"{args.model}_{args.noise}_K{K_loc}_T{T}_r{solver.get_option(1)}", {})
+    except Exception:
+        prof = {}
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+    exe = prof.get("executed_flop_per_rollout_step")
     roofline = {"kernel": "rollout_cost_kernel", "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
-                "frac": achieved / fp32_peak if fp32_peak else None, "traffic": traffic,
+                "frac": achieved / fp32_peak if fp32_peak else None, "traffic": prof.get("dram_bytes_per_launch"),
                 "peak_source": "FFMA probe measured in this run (mppi_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 entry; "
                                "nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4 TFLOP/s",
-                "algorithmic_flop_per_rollout_step": _native.algorithmic_flops(model_id),
-                "kernel_ms": k_ms, "share_of_step": k_ms / (k_ms + w_ms),
-                "weighting_kernel_ms": w_ms}
+                "algorithmic_flop_per_rollout_step": alg,
+                "algorithmic_flop_source": "oracle/flop_count.py: static count over the restated maths, general (dense) URDF constants, "
+                                           "FMA = 2, transcendental evaluations excluded (tests/test_flop_count.py); the survey's "
+                                           "pre-build estimate for this model was " + str({"wb": 1000, "arm": 840, "quad": 90, "drone": 40}[args.model]),
+                "structural_flop_per_rollout_step": _native.structural_flops(model_id),
+                "executed_flop_per_rollout_step": exe,
+                "frac_executed": (exe * K_loc * T / (k_ms * 1e-3) / 1e12 / fp32_peak) if (exe and fp32_peak) else None,
+                "fma_pipe_active_pct": prof.get("fma_pipe_active_pct"), "philox_pipe_share": prof.get("philox_pipe_share"),
+                "issue_active_pct": prof.get("issue_active_pct"),
+                "executed_source": prof.get("source", "no ncu capture committed for this configuration (profiles/ncu_metrics.json)"),
+                "kernel_ms": k_ms, "share_of_step": k_ms / (k_ms + w_ms), "weighting_kernel_ms": w_ms,
+                "binding_limit": {"wb": "FP32 FMA pipe (FP32 + Philox IMAD.WIDE)", "arm": "FP32 FMA pipe (FP32 + Philox IMAD.WIDE)",
+                                  "quad": "dependent-issue latency of the per-step chain (Philox IMAD + MUFU Box-Muller + rigid-body step); FP32 is not the binding roofline for this model",
+                                  "drone": "dependent-issue latency (Philox IMAD + MUFU); FP32 is not the binding roofline for this model"}[args.model]}
     # ---- HBM-bound weighting pass (re-read of a materialised [T][K][nu] noise tensor), timed alone.
     # In Philox mode the step has no HBM-bound kernel, so the injected-noise weighting pass is measured
     # here on the side (same K, T) to report the second roofline the north star names.
@@ -453,16 +680,9 @@ def run_native(args):
             solver.finalize()
         w2_ms = float(np.mean(wt2[2:]))
         gbs = K_loc * T * nu * 4 / (w2_ms * 1e-3) / 1e9
-        tkey = f"{args.model}_weighting_K{K_loc}_T{T}"
-        wtraffic = None
-        if os.path.exists(tpath):
-            try:
-                wtraffic = json.load(open(tpath)).get(tkey)
-            except Exception:
-                wtraffic = None
         roofline["weighting_hbm"] = {"kernel": "weights_kernel + weighted_noise_kernel", "bound": "hbm", "achieved": gbs,
                                      "peak": peaks.get("hbm_gbs", 6650.0), "unit": "GB/s", "frac": gbs / peaks.get("hbm_gbs", 6650.0),
-                                     "traffic": wtraffic, "kernel_ms": w2_ms,
+                                     "traffic": prof.get("weighting_dram_bytes_per_launch"), "kernel_ms": w2_ms,
                                      "algorithmic_bytes_per_rollout_step": nu * 4,
                                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"}
         if noise is None:
@@ -472,7 +692,7 @@ def run_native(args):
     # ---- end to end through the public controller class: host state in, host controls out, every step
     e2e = None
     if world == 1:
-        ctrl = make_controller(args.model, K, T, device)
+        ctrl = make_controller(args.model, K, T, device, lam=args.lam, opts=opts)
         feed_state(ctrl, args.model, sensor_message(args.model, st))
         n_e2e = max(10, min(args.steps, 100))
         for _ in range(3):
@@ -496,7 +716,7 @@ def run_native(args):
                "ms_per_step": e2e_s / n_e2e * 1e3, "steps": n_e2e,
                "note": "public class compute_control_input(): state passes as a by-value kernel parameter block, u_prev stays device-resident (warm start), the last block of the step stores the out vector into mapped pinned host memory and the call spins on its sequence word"}
     else:
-        # multi-rank e2e: the sharded step plus a D2H of the out vector on every rank, wall clock max over ranks
+        # multi-rank e2e: the sharded step plus the host-visible out vector on every rank, wall clock max over ranks
         n_e2e = max(10, min(args.steps, 100))
         barrier()
         t0 = time.perf_counter()
@@ -512,27 +732,35 @@ def run_native(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(args.model, K, T, budget_s=12.0, n_steps=2)
         cpu_torch = cpu_baseline_torch(args.model, K, T)
+        if noise is None and not args.no_parity:
+            parity = oracle_parity(args.model, lambda: make_solver(k_local=K, k_offset=0), K, T, nu)
 
     if rank == 0:
         line = {"metric": "rollout_steps_per_s", "value": value, "unit": "rollout-steps/s", "n_gpus": n_gpus,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"{spec['desc']}, K={K}, T={T}", "noise": args.noise,
+                           "philox_rounds": solver.get_option(_native.OPTION_PHILOX_ROUNDS),
                            "K_per_gpu": K_loc, "parallelism": f"k-shard x{world}" if world > 1 else "single GPU",
+                           "step_path": weights_info["path"],
                            "exchange": (stepper.exchange if world > 1 else None),
                            "exchange_fallback": getattr(stepper, "fallback_reason", None),
                            "l2": "no flush" if flush is None else "L2 flushed between steps (256 MiB memset) outside the per-step CUDA events",
                            "timing": "CUDA events around every step on the launch stream, summed, max over ranks"},
-                "latency_ms": {"p50": float(np.percentile(step_ms, 50)), "p99": float(np.percentile(step_ms, 99)),
-                               "max": float(step_ms.max()), "host_wall_ms_per_step_incl_flush": wall / args.steps * 1e3},
+                "latency_ms": latency if latency is not None else {"n": int(args.steps), "p50": float(np.percentile(step_ms, 50)),
+                                                                   "p99": float(np.percentile(step_ms, 99)), "max": float(step_ms.max())},
+                "weights": weights_info, "dense_weights": dense,
                 "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
-                "cpu_baseline": cpu, "cpu_baseline_torch": cpu_torch}
+                "parity_check": parity, "cpu_baseline": cpu, "cpu_baseline_torch": cpu_torch}
         if coll:
             line["collectives"] = coll
+        if exchange_nccl:
+            line["exchange_nccl"] = exchange_nccl
         print(json.dumps(line))
+    failed = parity is not None and not parity.get("ok", True)
     if world > 1:
         dist.destroy_process_group()
-    return 0
+    return 1 if failed else 0
 
 
 def main():

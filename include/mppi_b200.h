@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MPPI_ABI_VERSION 3
+#define MPPI_ABI_VERSION 4
 #define MPPI_MAX_NU 12          /* controls per horizon step (whole body = 11)            */
 #define MPPI_MAX_HORIZON 256
 #define MPPI_MAX_JOINTS 8       /* revolute joints in the arm chain                      */
@@ -42,7 +42,9 @@ typedef enum {
     MPPI_ERR_INVALID_ARG = 1,
     MPPI_ERR_WRONG_ARCH = 2,    /* device is not compute capability 10.x                 */
     MPPI_ERR_CUDA = 3,
-    MPPI_ERR_UNSUPPORTED = 4
+    MPPI_ERR_UNSUPPORTED = 4,
+    MPPI_ERR_PEER = 5           /* K-sharded step: a peer shard never published its row (exchange timed out);
+                                   the controls of that step were not updated                      */
 } mppi_status_t;
 
 /* Models.  state[] / out[] layouts:
@@ -241,6 +243,32 @@ mppi_status_t mppi_step_host(mppi_handle_t h, const float *state_host, int32_t n
                              float *u_inout_host, const float *noise_host, uint64_t step_counter,
                              float *cost_out_host, float *out_host);
 
+/* Run-time options (new; the reference has no configuration system).
+ *   PHILOX_ROUNDS  10 (default; Random123 / cuRAND) or 7 (the smallest Crush-resistant round count, -30 % multiplies)
+ *   FUSED_STEP     1 (default): a Philox step whose rollout grid is co-resident (K_local <= 128 x resident blocks, T <= 128)
+ *                  runs as ONE cooperative launch (rollout, grid barrier, weighting, exchange, finalize); 0 = always two kernels
+ *   TIME_PARALLEL  ARM7 / DRONE3 (linear double integrators), default costs, T <= 64: one WARP per sample, the two
+ *                  cumulative sums of the reference as warp scans, every (sample, step) evaluates FK + cost on its own
+ *                  lane, weighted-noise sums from the registers.  -1 (default) = when K_local <= 16384, 0 = never, 1 = always
+ *   PROFILE        1: CUDA events around the kernels of every step -> mppi_get_kernel_times (SURVEY section 5 tracing hook)
+ *   NVTX           1 (default): NVTX ranges "mppi.*" around the launches
+ *   LAST_PATH      (read-only) MPPI_PATH_* taken by the most recent step                                              */
+#define MPPI_OPTION_PHILOX_ROUNDS 1
+#define MPPI_OPTION_FUSED_STEP 2
+#define MPPI_OPTION_TIME_PARALLEL 3
+#define MPPI_OPTION_PROFILE 4
+#define MPPI_OPTION_NVTX 5
+#define MPPI_OPTION_LAST_PATH 6
+#define MPPI_PATH_TWO_KERNELS 1
+#define MPPI_PATH_FUSED 2
+#define MPPI_PATH_TIMEPARALLEL 3
+mppi_status_t mppi_set_option(mppi_handle_t h, int32_t option, int32_t value);
+mppi_status_t mppi_get_option(mppi_handle_t h, int32_t option, int32_t *value);
+/* With MPPI_OPTION_PROFILE: device time of the most recent step's kernels, microseconds:
+ * us3[0] = rollout kernel (or the whole single-launch step), us3[1] = weighting + finalize (0 for a single launch),
+ * us3[2] = MPPI_PATH_*.  Blocks until that step has finished.                                                        */
+mppi_status_t mppi_get_kernel_times(mppi_handle_t h, float *us3);
+
 /* Writes the Philox noise of (seed, step_counter) for this shard to d_noise [T][K][nu]:
  * the exact values the in-kernel generator uses (equivalence checks).                   */
 mppi_status_t mppi_generate_noise(mppi_handle_t h, uint64_t step_counter, float *d_noise, void *stream);
@@ -249,9 +277,12 @@ mppi_status_t mppi_generate_noise(mppi_handle_t h, uint64_t step_counter, float 
  * fused rollout kernel (MEASURED_PEAKS.json has no FP32 entry).                         */
 mppi_status_t mppi_measure_fp32_peak(int32_t device, float *tflops_out);
 
-/* Algorithmic FLOP per rollout-step (one sample, one horizon step) used for roofline.achieved
- * (dense-constant derivation).                      */
+/* Algorithmic FLOP per rollout-step (one sample, one horizon step) used for roofline.achieved: counted by
+ * oracle/flop_count.py over the restated maths with general (dense) URDF constants, FMA = 2, transcendental
+ * evaluations excluded.  The structural figure is the same count with the exact 0 / +-1
+ * constants of the j2s7s300 chain skipped (what an unrolled kernel executes, again without transcendentals).  */
 double mppi_algorithmic_flops_per_rollout_step(int32_t model);
+double mppi_structural_flops_per_rollout_step(int32_t model);
 
 #ifdef __cplusplus
 }

@@ -688,10 +688,12 @@ int oracle_savgol(int T, int nu, const float *seq /*[T][nu]*/, int window, int p
  * the reference samples with torch.randn (standard_normal_noise.py:24).  Addressing:
  *   counter = (k_global, t * n_calls + call, step_lo, step_hi), key = (seed_lo, seed_hi)
  * yields the six normals for inputs 6*call .. 6*call+5 of sample k at horizon step t. */
-void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+/* `rounds` = 10 is the Random123 / cuRAND default (known-answer vectors in tests/test_oracle_golden.py); 7 is the
+ * smallest round count the paper reports as Crush-resistant (table 2) -- same round function, fewer rounds.        */
+void oracle_philox4x32_r(const uint32_t ctr[4], const uint32_t key[2], int rounds, uint32_t out[4])
 {
     uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < rounds; ++r) {
         uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
         uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
         uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
@@ -699,6 +701,10 @@ void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+    oracle_philox4x32_r(ctr, key, 10, out);
 }
 
 /* One call = 128 bits = six 21-bit uniforms (bits [21 i, 21 i + 21) of the little-endian word, placed in the top
@@ -729,8 +735,8 @@ static void box_muller(float f_radius, float f_angle, float *n0, float *n1)
     *n1 = r * sinf(th);
 }
 
-void oracle_philox_noise(int K, int T, int nu, long long k_offset, uint64_t seed, uint64_t step,
-                         const float *sigma /*[nu]*/, float *noise /*[T][K][nu]*/)
+void oracle_philox_noise_r(int K, int T, int nu, long long k_offset, uint64_t seed, uint64_t step, int rounds,
+                           const float *sigma /*[nu]*/, float *noise /*[T][K][nu]*/)
 {
     int nch = ((nu + 1) / 2 + 2) / 3;      /* Philox calls per (sample, step): three pairs per call */
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
@@ -742,7 +748,7 @@ void oracle_philox_noise(int K, int T, int nu, long long k_offset, uint64_t seed
                                    (uint32_t)step, (uint32_t)(step >> 32)};
                 uint32_t r[4];
                 float f[6], n[6];
-                oracle_philox4x32_10(ctr, key, r);
+                oracle_philox4x32_r(ctr, key, rounds, r);
                 uniforms6(r, f);
                 for (int p = 0; p < 3; ++p) box_muller(f[2 * p], f[2 * p + 1], &n[2 * p], &n[2 * p + 1]);
                 for (int j = 0; j < 6; ++j) {
@@ -750,4 +756,10 @@ void oracle_philox_noise(int K, int T, int nu, long long k_offset, uint64_t seed
                     if (i < nu) noise[((size_t)t * K + k) * nu + i] = sigma[i] * n[j];
                 }
             }
+}
+
+void oracle_philox_noise(int K, int T, int nu, long long k_offset, uint64_t seed, uint64_t step,
+                         const float *sigma /*[nu]*/, float *noise /*[T][K][nu]*/)
+{
+    oracle_philox_noise_r(K, T, nu, k_offset, seed, step, 10, sigma, noise);
 }

@@ -118,6 +118,13 @@ def fk(q, chain: Chain = KINOVA_CHAIN) -> np.ndarray:
     return T.reshape(4, 4)
 
 
+def lib_make_transform(xyz, rpy) -> np.ndarray:
+    """URDF origin -> 4x4 (robot/transformation_matrix.py:4-35)."""
+    T = np.zeros(16, f32)
+    lib().oracle_make_transform(_f(xyz)[1], _f(rpy)[1], T.ctypes.data_as(_fp))
+    return T.reshape(4, 4)
+
+
 def xyzquat_to_matrix(b) -> np.ndarray:
     T = np.zeros(16, f32)
     lib().oracle_xyzquat_to_matrix(_f(b)[1], T.ctypes.data_as(_fp))
@@ -256,11 +263,20 @@ def philox4x32_10(ctr, key) -> np.ndarray:
     return out
 
 
-def philox_noise(K, T, nu, sigma, seed=0, step=0, k_offset=0) -> np.ndarray:
+def philox4x32(ctr, key, rounds=10) -> np.ndarray:
+    ctr = np.ascontiguousarray(ctr, np.uint32)
+    key = np.ascontiguousarray(key, np.uint32)
+    out = np.zeros(4, np.uint32)
+    u32p = C.POINTER(C.c_uint32)
+    lib().oracle_philox4x32_r(ctr.ctypes.data_as(u32p), key.ctypes.data_as(u32p), int(rounds), out.ctypes.data_as(u32p))
+    return out
+
+
+def philox_noise(K, T, nu, sigma, seed=0, step=0, k_offset=0, rounds=10) -> np.ndarray:
     noise = np.zeros((T, K, nu), f32)
     sig = np.broadcast_to(np.asarray(sigma, f32), (nu,)).copy()
-    lib().oracle_philox_noise(K, T, nu, C.c_longlong(k_offset), C.c_uint64(seed), C.c_uint64(step),
-                              _f(sig)[1], noise.ctypes.data_as(_fp))
+    lib().oracle_philox_noise_r(K, T, nu, C.c_longlong(k_offset), C.c_uint64(seed), C.c_uint64(step), int(rounds),
+                                _f(sig)[1], noise.ctypes.data_as(_fp))
     return noise
 
 

@@ -19,7 +19,7 @@ MPPI_OUT_REACH, MPPI_OUT_RHO, MPPI_OUT_ETA, MPPI_OUT_ESS, MPPI_OUT_STEP, MPPI_OU
 MODEL_DRONE3, MODEL_ARM7, MODEL_QUAD4, MODEL_WB11 = 0, 1, 2, 3
 MODEL_NU = {MODEL_DRONE3: 3, MODEL_ARM7: 7, MODEL_QUAD4: 4, MODEL_WB11: 11}
 MODEL_STATE = {MODEL_DRONE3: 6, MODEL_ARM7: 21, MODEL_QUAD4: 12, MODEL_WB11: 26}
-ABI_VERSION = 3
+ABI_VERSION = 4
 COST_COVAR, COST_CENTERING, COST_JOINT_TRAJ, COST_ACTION, COST_JOINT_LIMIT = 1, 2, 4, 8, 16
 OPT_TORQUE_LAW = 256            # shares the cost_flags word; ARM7 only
 ARM_TWIST_FLOATS = 6            # optional tail of the ARM7 state: v_full[:6] (read by the torque law)
@@ -29,8 +29,13 @@ EXPORTS = [
     "mppi_update_config", "mppi_set_joint_traj", "mppi_set_chain", "mppi_set_arm_inertia", "mppi_set_target", "mppi_set_state", "mppi_step", "mppi_rollout", "mppi_weight",
     "mppi_finalize", "mppi_rho_ptr", "mppi_wsum_ptr", "mppi_wsum_count", "mppi_cost_ptr",
     "mppi_p2p_export", "mppi_p2p_bind", "mppi_step_p2p", "mppi_step_p2p_sync", "mppi_step_sync", "mppi_step_host", "mppi_generate_noise", "mppi_measure_fp32_peak",
-    "mppi_algorithmic_flops_per_rollout_step",
+    "mppi_algorithmic_flops_per_rollout_step", "mppi_set_option", "mppi_get_option", "mppi_get_kernel_times",
+    "mppi_structural_flops_per_rollout_step",
 ]
+OPTION_PHILOX_ROUNDS, OPTION_FUSED_STEP, OPTION_TIME_PARALLEL, OPTION_PROFILE, OPTION_NVTX, OPTION_LAST_PATH = 1, 2, 3, 4, 5, 6
+PATH_TWO_KERNELS, PATH_FUSED, PATH_TIMEPARALLEL = 1, 2, 3
+PATH_NAMES = {0: "none", 1: "two_kernels", 2: "fused", 3: "time_parallel"}
+ERR_PEER = 5
 
 
 class MppiConfig(C.Structure):
@@ -63,9 +68,7 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
-    if not os.path.exists(path):
-        _build.build()          # raises if nvcc is unavailable
+    path = _build.build()       # no-op when the library matches the sources' content hash; raises if nvcc is unavailable
     lib = C.CDLL(path)
     vp, u64, i32 = C.c_void_p, C.c_uint64, C.c_int32
     lib.mppi_abi_version.restype = i32
@@ -102,9 +105,14 @@ def load():
     lib.mppi_measure_fp32_peak.argtypes = [i32, _fp]
     lib.mppi_algorithmic_flops_per_rollout_step.restype = C.c_double
     lib.mppi_algorithmic_flops_per_rollout_step.argtypes = [i32]
+    lib.mppi_structural_flops_per_rollout_step.restype = C.c_double
+    lib.mppi_structural_flops_per_rollout_step.argtypes = [i32]
+    lib.mppi_set_option.argtypes = [vp, i32, i32]
+    lib.mppi_get_option.argtypes = [vp, i32, C.POINTER(i32)]
+    lib.mppi_get_kernel_times.argtypes = [vp, _fp]
     for name in EXPORTS:
         if name not in ("mppi_abi_version", "mppi_last_error", "mppi_rho_ptr", "mppi_wsum_ptr", "mppi_wsum_count",
-                        "mppi_cost_ptr", "mppi_algorithmic_flops_per_rollout_step"):
+                        "mppi_cost_ptr", "mppi_algorithmic_flops_per_rollout_step", "mppi_structural_flops_per_rollout_step"):
             getattr(lib, name).restype = i32
     if lib.mppi_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libmppi_b200.so ABI {lib.mppi_abi_version()} != binding ABI {ABI_VERSION}; rebuild")
@@ -117,7 +125,7 @@ class MppiError(RuntimeError):
 
 
 _STATUS = {1: "invalid argument", 2: "wrong architecture (sm_100a only, no CPU fallback)", 3: "CUDA error",
-           4: "unsupported"}
+           4: "unsupported", 5: "peer exchange failed"}
 
 
 def check(rc: int, handle=None):
@@ -144,5 +152,12 @@ def measure_fp32_peak(device: int = 0) -> float:
 
 
 def algorithmic_flops(model: int) -> float:
-    """Algorithmic FLOP per rollout-step; the single figure roofline.achieved uses."""
+    """Algorithmic FLOP per rollout-step: counted over the restated maths with general (dense) URDF
+    constants by oracle/flop_count.py; the single figure roofline.achieved uses."""
     return float(load().mppi_algorithmic_flops_per_rollout_step(model))
+
+
+def structural_flops(model: int) -> float:
+    """FLOP per rollout-step once the exact 0 / +-1 constants of the baked chain are skipped (same counter, sparse
+    constants; transcendental evaluations excluded)."""
+    return float(load().mppi_structural_flops_per_rollout_step(model))

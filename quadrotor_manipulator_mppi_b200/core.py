@@ -37,7 +37,7 @@ class NativeSolver:
     def __init__(self, model: int, *, n_samples=None, n_horizon=None, dt=None, lam=None, sigma=None,
                  seed: int = 0, device=None, k_offset: int = 0, savgol_window=None, cost_w=None,
                  quad_params=None, target_pos=None, target_quat=None, drone_target=None, cost_flags: int = 0,
-                 torque_gains=None):
+                 torque_gains=None, philox_rounds=None, fused=None, time_parallel=None):
         self.device = _require_cuda(device)
         self._lib = _native.load()
         cfg = _native.default_config(model)
@@ -74,6 +74,12 @@ class NativeSolver:
         h = C.c_void_p()
         _native.check(self._lib.mppi_create(C.byref(cfg), C.byref(h)))
         self.handle = h.value
+        if philox_rounds is not None:
+            self.set_option(_native.OPTION_PHILOX_ROUNDS, int(philox_rounds))
+        if fused is not None:
+            self.set_option(_native.OPTION_FUSED_STEP, int(bool(fused)))
+        if time_parallel is not None:
+            self.set_option(_native.OPTION_TIME_PARALLEL, int(time_parallel))
         self.step_counter = 0
         # warm start: two buffers, alternated so a caller holding last step's u_prev keeps valid data
         self._u = [torch.zeros(self.T, self.nu, device=self.device), torch.zeros(self.T, self.nu, device=self.device)]
@@ -108,9 +114,38 @@ class NativeSolver:
         except Exception:
             pass
 
+    # ------------------------------------------------------------------ options / tracing (include/mppi_b200.h MPPI_OPTION_*)
+    def set_option(self, option: int, value: int) -> None:
+        _native.check(self._lib.mppi_set_option(self.handle, int(option), int(value)), self.handle)
+
+    def get_option(self, option: int) -> int:
+        v = C.c_int32()
+        _native.check(self._lib.mppi_get_option(self.handle, int(option), C.byref(v)), self.handle)
+        return int(v.value)
+
+    @property
+    def last_path(self) -> str:
+        """Which kernels the most recent step ran: "two_kernels", "fused" (single launch) or "time_parallel"."""
+        return _native.PATH_NAMES[self.get_option(_native.OPTION_LAST_PATH)]
+
+    def profile(self, on: bool = True) -> None:
+        """CUDA events around the kernels of every step (SURVEY section 5 tracing hook); read with kernel_times()."""
+        self.set_option(_native.OPTION_PROFILE, int(bool(on)))
+
+    def kernel_times(self) -> dict:
+        """Device time of the most recent profiled step's kernels in microseconds (blocks until that step is done)."""
+        us = (C.c_float * 3)()
+        _native.check(self._lib.mppi_get_kernel_times(self.handle, us), self.handle)
+        return {"rollout_us": float(us[0]), "weighting_finalize_us": float(us[1]), "path": _native.PATH_NAMES[int(us[2])]}
+
     # ------------------------------------------------------------------ state / warm start
     @property
     def u_prev(self) -> torch.Tensor:
+        """The nominal control sequence [T][nu] the next step warm-starts from (not shifted).
+
+        This is a VIEW of one of the solver's two ping-pong device buffers, valid until the second step after it was
+        read (the reference hands out a fresh clone every step, mppi.py:153-154); `.clone()` it to keep it longer.
+        The drop-in classes' public `u_prev` / `u` attributes return clones."""
         return self._u[self._cur]
 
     @u_prev.setter

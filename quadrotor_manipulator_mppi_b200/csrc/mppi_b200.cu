@@ -14,13 +14,13 @@
 #include <vector>
 
 #include "arm_inertia_gen.cuh"
-#include "mppi_kernels.cuh"
+#include "mppi_host.cuh"
+#include "mppi_kernels.cuh"      // generate_noise_kernel, ffma_probe_kernel (the step kernels live in the model units)
 
 using namespace mppi;
 
 namespace {
 
-thread_local std::string g_create_error;
 
 struct Mat4 { double m[16]; };
 
@@ -136,62 +136,7 @@ bool savgol_taps(int window, int polyorder, float *taps)
 
 }  // namespace
 
-struct mppi_ctx {
-    mppi_config_t cfg{};
-    StepParams P{};
-    DynBlock dyn{};                 // host copy; passed by value at launch
-    std::mutex state_mu;            // guards staged_state (set_state may come from another thread)
-    float staged_state[MPPI_STATE_FLOATS]{};
-    int nu = 0;
-    int num_sms = 148;
-    // device scratch (allocated once in mppi_create)
-    float *d_cost = nullptr;        // [K]
-    int32_t *d_rho = nullptr;       // order-preserving min (signed int32 encoding)
-    uint32_t *d_counter = nullptr;  // last-block-done counter
-    float *d_part = nullptr;        // [max_parts][T*nu+2]
-    float *d_wsum = nullptr;        // [T*nu+2]
-    unsigned long long *d_fix = nullptr;   // [T*nu+2] fixed-point accumulators of the Philox weighting pass
-    float *d_w = nullptr;           // [K] unnormalised weights (injected-noise path)
-    float *d_eta_part = nullptr;    // [<=SMs][2] partial sums of w, w^2
-    int wn_resident = 0;            // resident blocks of the streaming weighting kernel (one wave)
-    float *d_u = nullptr;           // [T*nu]   (host-buffer API)
-    float *d_out = nullptr;         // [MPPI_OUT_FLOATS]
-    float *d_noise = nullptr;       // host-buffer API with injected noise, grown on demand
-    size_t d_noise_bytes = 0;
-    float *h_pinned = nullptr;      // pinned staging for the host-buffer API
-    size_t h_pinned_floats = 0;
-    float *h_zc = nullptr;          // pinned + mapped: [MPPI_OUT_FLOATS] out vector + 1 sequence word (mppi_step_sync)
-    float *d_zc = nullptr;          // the same memory as the device addresses it
-    unsigned zc_seq = 0;
-    int max_parts = 0;
-    // NVLink peer exchange (mppi_p2p_export / mppi_p2p_bind)
-    float *p2p_buf = nullptr;       // this rank's exchange buffer (cudaMalloc, exported through CUDA IPC)
-    size_t p2p_bytes = 0;
-    P2PParams X{};                  // world == 1 until bound
-    P2PParams X_off{};              // world == 1: exchange disabled
-    void *p2p_peer[kMaxRanks] = {};
-    bool baked_fk = false;          // runtime chain == compile-time FkKinova tables
-    double align[MPPI_MAX_JOINTS][9] = {};   // A_j: URDF link frame j -> folded link frame (z = joint axis), row-major
-    float inertia_raw[7 * 10] = {};  // mass, com[3], inertia[6] per link, in the URDF link frames
-    size_t rollout_smem[12] = {};   // tuned dynamic smem per kernel variant (0 = not yet tuned)
-    float *d_qtraj = nullptr;       // [T][7] joint reference trajectory (MPPI_COST_JOINT_TRAJ), zeros by default
-    cudaStream_t own_stream = nullptr;
-    std::string err;
-};
-
 namespace {
-
-mppi_status_t fail(mppi_handle_t h, mppi_status_t code, const std::string &msg)
-{
-    if (h) h->err = msg; else g_create_error = msg;
-    return code;
-}
-#define MPPI_CUDA(h, call)                                                                             \
-    do {                                                                                               \
-        cudaError_t e_ = (call);                                                                       \
-        if (e_ != cudaSuccess)                                                                         \
-            return fail(h, MPPI_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));        \
-    } while (0)
 
 void load_extra_costs(mppi_ctx *h, const mppi_config_t *cfg)
 {
@@ -313,187 +258,6 @@ mppi_status_t set_chain_impl(mppi_ctx *h, int n, const int32_t *types, const flo
     return MPPI_OK;
 }
 
-// The rollout kernel is issue-bound, so its time is (number of waves) x (blocks resident per SM).
-// Pick the residency o <= o_max that minimises ceil(blocks / (SMs * o)) * o -- i.e. avoid a nearly
-// empty last wave -- and enforce it by padding the dynamic shared memory request.
-template <typename KernelT>
-size_t tuned_rollout_smem(mppi_ctx *h, KernelT kernel, int threads, int grid, size_t smem_needed)
-{
-    int omax = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&omax, kernel, threads, smem_needed) != cudaSuccess || omax < 1) {
-        cudaGetLastError();
-        return smem_needed;
-    }
-    auto cost = [&](int o) { return (long long)((grid + (long long)h->num_sms * o - 1) / ((long long)h->num_sms * o)) * o; };
-    int best_o = omax;
-    long long best = cost(omax);
-    // only one step below the register-limited residency, and never below 4 blocks (16 warps) per SM:
-    // under that the kernel turns latency-bound and the wave model no longer holds
-    for (int o = omax - 1; o >= omax - 1 && o >= 4; --o)
-        if (cost(o) < best) { best = cost(o); best_o = o; }
-    if (best_o == omax) return smem_needed;
-    size_t pad = (size_t)(228 * 1024) / best_o - 1024 - 256;      // 1 KB per block is reserved by the driver
-    pad &= ~(size_t)255;
-    if (pad < smem_needed || pad > 48 * 1024) return smem_needed;
-    int got = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&got, kernel, threads, pad) != cudaSuccess || got != best_o) {
-        cudaGetLastError();
-        return smem_needed;
-    }
-    return pad;
-}
-
-template <int MODEL, int NOISE, bool BAKED, bool EXTRA>
-mppi_status_t launch_rollout_variant(mppi_ctx *h, int variant, const float *d_u_nom, const float *d_noise, float *d_cost,
-                                     cudaStream_t st)
-{
-    constexpr int NU = ModelNu<MODEL>::value;
-    size_t smem = (size_t)h->P.T * NU * sizeof(float);
-    if (NOISE == 2) smem = ((smem + 15) & ~(size_t)15) + (size_t)kNoiseStages * kRolloutThreads * NU * sizeof(float);
-    auto kernel = rollout_cost_kernel<MODEL, NOISE, BAKED, EXTRA>;
-    const int grid = (h->P.K + kRolloutThreads - 1) / kRolloutThreads;
-    size_t &tuned = h->rollout_smem[variant];
-    if (tuned == 0) {
-        if (smem > 48 * 1024)       // long horizons / wide noise tiles: opt in to the large dynamic shared memory carve-out
-            MPPI_CUDA(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tuned = tuned_rollout_smem(h, kernel, kRolloutThreads, grid, smem);
-    }
-    kernel<<<grid, kRolloutThreads, tuned, st>>>(h->P, h->dyn, d_u_nom, d_noise, d_cost, h->d_rho, h->d_qtraj);
-    MPPI_CUDA(h, cudaGetLastError());
-    return MPPI_OK;
-}
-
-template <int MODEL, int NOISE>
-mppi_status_t launch_rollout_noise(mppi_ctx *h, const float *d_u_nom, const float *d_noise, float *d_cost, cudaStream_t st)
-{
-    constexpr bool HAS_ARM = (MODEL == MPPI_MODEL_ARM7 || MODEL == MPPI_MODEL_WB11);
-    const bool baked = HAS_ARM && h->baked_fk;      // FK unrolled from the URDF constants (fk_tables_gen.cuh)
-    const bool extra = HAS_ARM && (h->P.cost_flags & MPPI_COST_MASK) != 0;      // optional cost terms: separate, slower instantiation
-    const int variant = NOISE * 4 + (baked ? 1 : 0) + (extra ? 2 : 0);
-    switch ((baked ? 1 : 0) + (extra ? 2 : 0)) {
-        case 0: return launch_rollout_variant<MODEL, NOISE, false, false>(h, variant, d_u_nom, d_noise, d_cost, st);
-        case 1: return launch_rollout_variant<MODEL, NOISE, HAS_ARM, false>(h, variant, d_u_nom, d_noise, d_cost, st);
-        case 2: return launch_rollout_variant<MODEL, NOISE, false, HAS_ARM>(h, variant, d_u_nom, d_noise, d_cost, st);
-        default: return launch_rollout_variant<MODEL, NOISE, HAS_ARM, HAS_ARM>(h, variant, d_u_nom, d_noise, d_cost, st);
-    }
-}
-
-template <int MODEL>
-mppi_status_t launch_rollout(mppi_ctx *h, const float *d_u_nom, const float *d_noise, float *d_cost, cudaStream_t st)
-{
-    constexpr int NU = ModelNu<MODEL>::value;
-    if (!d_noise) return launch_rollout_noise<MODEL, 0>(h, d_u_nom, nullptr, d_cost, st);
-    // injected [T][K][nu]: TMA-staged tiles when every 128-sample tile is 16-byte aligned and sized
-    const bool tma_ok = ((size_t)h->P.K * NU) % 4 == 0 && (reinterpret_cast<uintptr_t>(d_noise) & 15u) == 0;
-    if (tma_ok) return launch_rollout_noise<MODEL, 2>(h, d_u_nom, d_noise, d_cost, st);
-    return launch_rollout_noise<MODEL, 1>(h, d_u_nom, d_noise, d_cost, st);
-}
-
-template <int MODEL>
-mppi_status_t launch_weight(mppi_ctx *h, const float *d_noise, bool fuse, const float *d_u_nom, float *d_u_new,
-                            float *d_out, cudaStream_t st, const P2PParams &X)
-{
-    constexpr int NU = ModelNu<MODEL>::value;
-    const int K = h->P.K, T = h->P.T;
-    const size_t fin_floats = (size_t)2 * T * NU + NU;
-    if (!d_noise) {
-        const int TC = T;                       // one thread per horizon step (all Philox calls of the step), R sample sub-ranges
-        int R = 512 / TC;
-        if (R < 1) R = 1;
-        int threads = ((TC * R + 31) / 32) * 32;
-        if (threads > 1024) return fail(h, MPPI_ERR_UNSUPPORTED, "horizon too long for the Philox weighting kernel");
-        int blocks = (K + 31) / 32;             // small K: many short blocks (latency), large K: two per SM
-        if (blocks > 2 * h->num_sms) blocks = 2 * h->num_sms;
-        if (blocks > h->max_parts) blocks = h->max_parts;
-        if (blocks < 1) blocks = 1;
-        const int chunk = (K + blocks - 1) / blocks;
-        blocks = (K + chunk - 1) / chunk;
-        size_t smem_floats = (size_t)2 * kWeightTile + (size_t)R * TC * (4 * ((NU + 3) / 4));
-        if (smem_floats < fin_floats) smem_floats = fin_floats;
-        // fused steps launch it as a programmatic dependent of the rollout kernel: its launch overlaps the rollout's drain
-        cudaLaunchConfig_t lc{};
-        lc.gridDim = dim3(blocks); lc.blockDim = dim3(threads); lc.dynamicSmemBytes = smem_floats * sizeof(float); lc.stream = st;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[0].val.programmaticStreamSerializationAllowed = 1;
-        lc.attrs = at; lc.numAttrs = fuse ? 1 : 0;
-        MPPI_CUDA(h, cudaLaunchKernelEx(&lc, weight_philox_kernel<MODEL>, h->P, h->dyn, (const float *)h->d_cost, h->d_rho, chunk, h->d_fix,
-                                        h->d_counter, h->d_wsum, fuse ? 1 : 0, d_u_nom, d_u_new, d_out, X));
-    } else {
-        const bool vec4 = ((size_t)K * NU) % 4 == 0 && (reinterpret_cast<uintptr_t>(d_noise) & 15u) == 0;
-        // weights once, then one resident wave of (G x T) streaming blocks
-        int wblocks = (K + 1023) / 1024;
-        if (wblocks > h->num_sms) wblocks = h->num_sms;
-        cudaLaunchConfig_t lc{};
-        lc.gridDim = dim3(wblocks); lc.blockDim = dim3(256); lc.stream = st;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[0].val.programmaticStreamSerializationAllowed = 1;
-        lc.attrs = at; lc.numAttrs = fuse ? 1 : 0;
-        MPPI_CUDA(h, cudaLaunchKernelEx(&lc, weights_kernel, h->P, (const float *)h->d_cost, (const int32_t *)h->d_rho, h->d_w, h->d_eta_part));
-        const int threads = 32 * NU;
-        size_t smem_floats = (size_t)threads * 4;
-        if (smem_floats < fin_floats) smem_floats = fin_floats;
-        if (h->wn_resident == 0) {
-            int per_sm = 0;
-            cudaError_t oe = vec4 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, weighted_noise_kernel<MODEL, 4>, threads, smem_floats * sizeof(float))
-                                  : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, weighted_noise_kernel<MODEL, 1>, threads, smem_floats * sizeof(float));
-            if (oe != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 2; }
-            h->wn_resident = per_sm * h->num_sms;
-        }
-        int G = h->wn_resident / T;                       // small problems: one resident wave (latency)
-        if (G < 1) G = 1;
-        // Large problems: ~300 KB of noise per block and a block count that is a multiple of the SM count, so every SM
-        // streams the same number of equal blocks (measured on wb K=262144, T=64: one wave of 11 x 64 blocks 5.27 TB/s,
-        // 37 x 64 blocks = 16 per SM 5.81 TB/s, 148 x 64 blocks 4.65 TB/s -- profiles/r01/README.md).
-        {
-            const double g_target = (double)K / std::fmax(1024.0, 300e3 / (NU * 4.0));
-            if (g_target * T >= 8.0 * h->num_sms) {
-                int a = h->num_sms, b = T;
-                while (b) { const int r = a % b; a = b; b = r; }
-                const int g0 = h->num_sms / a;             // smallest G with G*T % num_sms == 0
-                const int m = (int)std::floor(g_target / g0 + 0.5);
-                G = m >= 1 ? m * g0 : (int)(g_target + 0.5);
-            }
-        }
-        if (G > h->max_parts) G = h->max_parts;
-        const int gmax = (K + 127) / 128;
-        if (G > gmax) G = gmax;
-        int chunk = ((K + G - 1) / G + 127) / 128 * 128;
-        G = (K + chunk - 1) / chunk;
-        dim3 grid(G, T);
-        if (vec4)
-            weighted_noise_kernel<MODEL, 4><<<grid, threads, smem_floats * sizeof(float), st>>>(
-                h->P, h->dyn, h->d_w, d_noise, h->d_rho, chunk, h->d_part, h->d_eta_part, wblocks, h->d_counter, h->d_wsum,
-                fuse ? 1 : 0, d_u_nom, d_u_new, d_out, X);
-        else
-            weighted_noise_kernel<MODEL, 1><<<grid, threads, smem_floats * sizeof(float), st>>>(
-                h->P, h->dyn, h->d_w, d_noise, h->d_rho, chunk, h->d_part, h->d_eta_part, wblocks, h->d_counter, h->d_wsum,
-                fuse ? 1 : 0, d_u_nom, d_u_new, d_out, X);
-    }
-    MPPI_CUDA(h, cudaGetLastError());
-    return MPPI_OK;
-}
-
-template <int MODEL>
-mppi_status_t launch_finalize(mppi_ctx *h, const float *d_u_nom, float *d_u_new, float *d_out, cudaStream_t st)
-{
-    constexpr int NU = ModelNu<MODEL>::value;
-    const size_t smem = ((size_t)2 * h->P.T * NU + NU) * sizeof(float);
-    finalize_kernel<MODEL><<<1, 256, smem, st>>>(h->P, h->dyn, h->d_wsum, d_u_nom, d_u_new, d_out, h->d_rho);
-    MPPI_CUDA(h, cudaGetLastError());
-    return MPPI_OK;
-}
-
-#define MPPI_DISPATCH(h, fn, ...)                                                      \
-    switch ((h)->cfg.model) {                                                          \
-        case MPPI_MODEL_DRONE3: return fn<MPPI_MODEL_DRONE3>(__VA_ARGS__);             \
-        case MPPI_MODEL_ARM7:   return fn<MPPI_MODEL_ARM7>(__VA_ARGS__);               \
-        case MPPI_MODEL_QUAD4:  return fn<MPPI_MODEL_QUAD4>(__VA_ARGS__);              \
-        case MPPI_MODEL_WB11:   return fn<MPPI_MODEL_WB11>(__VA_ARGS__);               \
-        default: return fail(h, MPPI_ERR_INVALID_ARG, "unknown model");                \
-    }
-
 // Snapshot the staged state + step counter into the by-value dynamic block.
 void snapshot(mppi_ctx *h, uint64_t step_counter)
 {
@@ -505,9 +269,60 @@ void snapshot(mppi_ctx *h, uint64_t step_counter)
     h->dyn.step_hi = (uint32_t)(step_counter >> 32);
 }
 
-mppi_status_t rollout_dispatch(mppi_ctx *h, const float *u, const float *n, float *c, cudaStream_t st) { MPPI_DISPATCH(h, launch_rollout, h, u, n, c, st) }
-mppi_status_t weight_dispatch(mppi_ctx *h, const float *n, bool fuse, const float *u, float *un, float *o, cudaStream_t st, const P2PParams &X) { MPPI_DISPATCH(h, launch_weight, h, n, fuse, u, un, o, st, X) }
-mppi_status_t finalize_dispatch(mppi_ctx *h, const float *u, float *un, float *o, cudaStream_t st) { MPPI_DISPATCH(h, launch_finalize, h, u, un, o, st) }
+#define MPPI_DISPATCH(h, fn, ...)                                                      \
+    switch ((h)->cfg.model) {                                                          \
+        case MPPI_MODEL_DRONE3: return fn##_0(__VA_ARGS__);                            \
+        case MPPI_MODEL_ARM7:   return fn##_1(__VA_ARGS__);                            \
+        case MPPI_MODEL_QUAD4:  return fn##_2(__VA_ARGS__);                            \
+        case MPPI_MODEL_WB11:   return fn##_3(__VA_ARGS__);                            \
+        default: return fail(h, MPPI_ERR_INVALID_ARG, "unknown model");                \
+    }
+mppi_status_t rollout_dispatch(mppi_ctx *h, const float *u, const float *n, float *c, cudaStream_t st) { MPPI_DISPATCH(h, unit_rollout, h, u, n, c, st) }
+mppi_status_t weight_dispatch(mppi_ctx *h, const float *n, bool fuse, const float *u, float *un, float *o, cudaStream_t st, const P2PParams &X) { MPPI_DISPATCH(h, unit_weight, h, n, fuse, u, un, o, st, X) }
+mppi_status_t finalize_dispatch(mppi_ctx *h, const float *u, float *un, float *o, cudaStream_t st) { MPPI_DISPATCH(h, unit_finalize, h, u, un, o, st) }
+mppi_status_t fused_dispatch(mppi_ctx *h, const float *u, float *un, float *o, cudaStream_t st, const P2PParams &X, bool *l) { MPPI_DISPATCH(h, unit_fused, h, u, un, o, st, X, l) }
+mppi_status_t tp_dispatch(mppi_ctx *h, const float *u, const float *n, float *un, float *o, cudaStream_t st, const P2PParams &X, bool *l) { MPPI_DISPATCH(h, unit_tp, h, u, n, un, o, st, X, l) }
+
+// One control step on `st`: the time-parallel kernel or the single-launch fused kernel when the problem qualifies,
+// else rollout -> weighting (+ finalize in its last block).  X.world > 1 fuses the peer exchange into whichever runs.
+mppi_status_t step_impl(mppi_ctx *h, const float *d_u_nom, const float *d_noise, uint64_t step_counter, float *d_cost_out,
+                        float *d_u_new, float *d_out, cudaStream_t st, const P2PParams &X)
+{
+    snapshot(h, step_counter);
+    if (h->opt_profile) MPPI_CUDA(h, cudaEventRecord(h->ev[0], st));
+    bool launched = false;
+    mppi_status_t rc = tp_dispatch(h, d_u_nom, d_noise, d_u_new, d_out, st, X, &launched);
+    if (rc != MPPI_OK) return rc;
+    h->last_path = MPPI_PATH_TIMEPARALLEL;
+    if (!launched && !d_noise) {
+        rc = fused_dispatch(h, d_u_nom, d_u_new, d_out, st, X, &launched);
+        if (rc != MPPI_OK) return rc;
+        h->last_path = MPPI_PATH_FUSED;
+    }
+    if (launched) {
+        if (h->opt_profile) MPPI_CUDA(h, cudaEventRecord(h->ev[1], st));
+    } else {
+        h->last_path = MPPI_PATH_TWO_KERNELS;
+        rc = rollout_dispatch(h, d_u_nom, d_noise, h->d_cost, st);
+        if (rc != MPPI_OK) return rc;
+        if (h->opt_profile) MPPI_CUDA(h, cudaEventRecord(h->ev[1], st));
+        rc = weight_dispatch(h, d_noise, true, d_u_nom, d_u_new, d_out, st, X);
+        if (rc != MPPI_OK) return rc;
+    }
+    if (h->opt_profile) { MPPI_CUDA(h, cudaEventRecord(h->ev[2], st)); h->ev_valid = true; }
+    if (d_cost_out && d_cost_out != h->d_cost)
+        MPPI_CUDA(h, cudaMemcpyAsync(d_cost_out, h->d_cost, (size_t)h->P.K * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return MPPI_OK;
+}
+
+mppi_status_t peer_failure(mppi_ctx *h)
+{
+    if (h->h_fail && *reinterpret_cast<volatile unsigned *>(h->h_fail) != 0)
+        return fail(h, MPPI_ERR_PEER, "peer exchange timed out at epoch " + std::to_string(*h->h_fail) +
+                                          ": a peer shard never published its row; the controls of that step were NOT updated "
+                                          "(re-bind with mppi_p2p_export / mppi_p2p_bind, or fall back to the allreduce path)");
+    return MPPI_OK;
+}
 
 struct DeviceGuard {
     int prev = -1;
@@ -543,7 +358,7 @@ mppi_status_t wait_published(mppi_ctx *h, unsigned seq, cudaStream_t st, float *
     }
     std::atomic_thread_fence(std::memory_order_acquire);
     std::memcpy(out_host, h->h_zc, MPPI_OUT_FLOATS * sizeof(float));
-    return MPPI_OK;
+    return peer_failure(h);
 }
 
 }  // namespace
@@ -702,6 +517,10 @@ mppi_status_t mppi_create(const mppi_config_t *cfg, mppi_handle_t *out)
     std::memset(h->h_zc, 0, (MPPI_OUT_FLOATS + 16) * sizeof(float));
     if ((e = cudaHostGetDevicePointer(&h->d_zc, h->h_zc, 0)) != cudaSuccess) return cleanup(e, "cudaHostGetDevicePointer");
     if ((e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return cleanup(e, "cudaStreamCreate");
+    if ((e = cudaMalloc(&h->d_sync, 64)) != cudaSuccess) return cleanup(e, "cudaMalloc(sync)");
+    if ((e = cudaMemset(h->d_sync, 0, 64)) != cudaSuccess) return cleanup(e, "cudaMemset(sync)");
+    for (auto &ev : h->ev)
+        if ((e = cudaEventCreate(&ev)) != cudaSuccess) return cleanup(e, "cudaEventCreate");
     const int32_t init[4] = {kRhoInit, 0, 0, 0};
     if ((e = cudaMemcpy(h->d_rho, init, sizeof(init), cudaMemcpyHostToDevice)) != cudaSuccess) return cleanup(e, "cudaMemcpy(init)");
     if ((e = cudaMemset(h->d_out, 0, MPPI_OUT_FLOATS * sizeof(float))) != cudaSuccess) return cleanup(e, "cudaMemset(out)");
@@ -721,6 +540,9 @@ mppi_status_t mppi_destroy(mppi_handle_t h)
         cudaFree(h->p2p_buf);
         if (h->h_pinned) cudaFreeHost(h->h_pinned);
         if (h->h_zc) cudaFreeHost(h->h_zc);
+        if (h->h_fail) cudaFreeHost(h->h_fail);
+        cudaFree(h->d_sync);
+        for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
         if (h->own_stream) cudaStreamDestroy(h->own_stream);
     }
     delete h;
@@ -836,13 +658,7 @@ mppi_status_t mppi_step(mppi_handle_t h, const float *d_u_nom, const float *d_no
 {
     if (!h || !d_u_nom || !d_u_new) return fail(h, MPPI_ERR_INVALID_ARG, "null u buffers");
     DeviceGuard guard(h->cfg.device);
-    cudaStream_t st = (cudaStream_t)stream;
-    snapshot(h, step_counter);
-    mppi_status_t rc = rollout_dispatch(h, d_u_nom, d_noise, h->d_cost, st);
-    if (rc != MPPI_OK) return rc;
-    if (d_cost_out && d_cost_out != h->d_cost)
-        MPPI_CUDA(h, cudaMemcpyAsync(d_cost_out, h->d_cost, (size_t)h->P.K * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    return weight_dispatch(h, d_noise, true, d_u_nom, d_u_new, d_out ? d_out : h->d_out, st, h->X_off);
+    return step_impl(h, d_u_nom, d_noise, step_counter, d_cost_out, d_u_new, d_out ? d_out : h->d_out, (cudaStream_t)stream, h->X_off);
 }
 
 mppi_status_t mppi_p2p_export(mppi_handle_t h, int32_t world, void *ipc_handle_out)
@@ -864,6 +680,12 @@ mppi_status_t mppi_p2p_export(mppi_handle_t h, int32_t world, void *ipc_handle_o
     h->X = P2PParams{};
     h->X.world = 1;
     h->X.rowp = rowp;
+    if (!h->h_fail) {
+        MPPI_CUDA(h, cudaHostAlloc(&h->h_fail, 64, cudaHostAllocMapped));
+        MPPI_CUDA(h, cudaHostGetDevicePointer(&h->d_fail, h->h_fail, 0));
+    }
+    *h->h_fail = 0;
+    h->X.fail_flag = h->d_fail;
     return MPPI_OK;
 }
 
@@ -873,6 +695,13 @@ mppi_status_t mppi_p2p_bind(mppi_handle_t h, int32_t world, int32_t rank, const 
         return fail(h, MPPI_ERR_INVALID_ARG, "mppi_p2p_bind: call mppi_p2p_export first; world in [2, 8]");
     DeviceGuard guard(h->cfg.device);
     P2PParams X = h->X;
+    // (Re-)binding restarts the epochs at 0 on every rank, so the flags and inbox rows a previous binding left in this
+    // rank's buffer must go: an old flag >= a new epoch would let the acquire-spin pass on stale rows.  The caller
+    // barriers between bind and the first step (sharded.enable_p2p), so no peer writes before this completes.
+    MPPI_CUDA(h, cudaDeviceSynchronize());
+    MPPI_CUDA(h, cudaMemset(h->p2p_buf, 0, h->p2p_bytes));
+    MPPI_CUDA(h, cudaDeviceSynchronize());
+    if (h->h_fail) *h->h_fail = 0;
     for (int r = 0; r < kMaxRanks; ++r)          // re-binding: drop the mappings of the previous world
         if (h->p2p_peer[r]) { cudaIpcCloseMemHandle(h->p2p_peer[r]); h->p2p_peer[r] = nullptr; }
     for (int r = 0; r < world; ++r) {
@@ -897,14 +726,12 @@ mppi_status_t mppi_step_p2p(mppi_handle_t h, const float *d_u_nom, const float *
     if (!h || !d_u_nom || !d_u_new) return fail(h, MPPI_ERR_INVALID_ARG, "null u buffers");
     if (h->X.world < 2) return fail(h, MPPI_ERR_INVALID_ARG, "mppi_step_p2p: peers are not bound (mppi_p2p_bind)");
     DeviceGuard guard(h->cfg.device);
-    cudaStream_t st = (cudaStream_t)stream;
-    snapshot(h, step_counter);
-    mppi_status_t rc = rollout_dispatch(h, d_u_nom, d_noise, h->d_cost, st);
+    mppi_status_t rc = peer_failure(h);        // sticky: an earlier (possibly asynchronous) step lost a peer
     if (rc != MPPI_OK) return rc;
-    if (d_cost_out && d_cost_out != h->d_cost)
-        MPPI_CUDA(h, cudaMemcpyAsync(d_cost_out, h->d_cost, (size_t)h->P.K * sizeof(float), cudaMemcpyDeviceToDevice, st));
     h->X.epoch += 1;           // every rank steps in lock-step, so the epochs agree
-    return weight_dispatch(h, d_noise, true, d_u_nom, d_u_new, d_out ? d_out : h->d_out, st, h->X);
+    rc = step_impl(h, d_u_nom, d_noise, step_counter, d_cost_out, d_u_new, d_out ? d_out : h->d_out, (cudaStream_t)stream, h->X);
+    if (rc != MPPI_OK) h->X.epoch -= 1;        // nothing was published under the new epoch: keep the ranks' counters aligned
+    return rc;
 }
 
 mppi_status_t mppi_step_sync(mppi_handle_t h, const float *state_host, int32_t n_state, const float *d_u_nom,
@@ -973,6 +800,54 @@ mppi_status_t mppi_step_host(mppi_handle_t h, const float *state_host, int32_t n
     return MPPI_OK;
 }
 
+mppi_status_t mppi_set_option(mppi_handle_t h, int32_t option, int32_t value)
+{
+    if (!h) return MPPI_ERR_INVALID_ARG;
+    switch (option) {
+        case MPPI_OPTION_PHILOX_ROUNDS:
+            if (value != 7 && value != 10) return fail(h, MPPI_ERR_INVALID_ARG, "philox rounds must be 7 or 10");
+            h->philox_rounds = value; return MPPI_OK;
+        case MPPI_OPTION_FUSED_STEP: h->opt_fused = value ? 1 : 0; return MPPI_OK;
+        case MPPI_OPTION_TIME_PARALLEL:
+            if (value < -1 || value > 1) return fail(h, MPPI_ERR_INVALID_ARG, "time-parallel option is -1 (auto), 0 or 1");
+            h->opt_timepar = value; return MPPI_OK;
+        case MPPI_OPTION_PROFILE: h->opt_profile = value ? 1 : 0; h->ev_valid = false; return MPPI_OK;
+        case MPPI_OPTION_NVTX: h->opt_nvtx = value ? 1 : 0; return MPPI_OK;
+        default: return fail(h, MPPI_ERR_INVALID_ARG, "unknown option");
+    }
+}
+
+mppi_status_t mppi_get_option(mppi_handle_t h, int32_t option, int32_t *value)
+{
+    if (!h || !value) return MPPI_ERR_INVALID_ARG;
+    switch (option) {
+        case MPPI_OPTION_PHILOX_ROUNDS: *value = h->philox_rounds; return MPPI_OK;
+        case MPPI_OPTION_FUSED_STEP: *value = h->opt_fused; return MPPI_OK;
+        case MPPI_OPTION_TIME_PARALLEL: *value = h->opt_timepar; return MPPI_OK;
+        case MPPI_OPTION_PROFILE: *value = h->opt_profile; return MPPI_OK;
+        case MPPI_OPTION_NVTX: *value = h->opt_nvtx; return MPPI_OK;
+        case MPPI_OPTION_LAST_PATH: *value = h->last_path; return MPPI_OK;
+        default: return fail(h, MPPI_ERR_INVALID_ARG, "unknown option");
+    }
+}
+
+mppi_status_t mppi_get_kernel_times(mppi_handle_t h, float *us3)
+{
+    if (!h || !us3) return MPPI_ERR_INVALID_ARG;
+    if (!h->opt_profile || !h->ev_valid) return fail(h, MPPI_ERR_INVALID_ARG, "no profiled step: set MPPI_OPTION_PROFILE and step first");
+    DeviceGuard guard(h->cfg.device);
+    MPPI_CUDA(h, cudaEventSynchronize(h->ev[2]));
+    float a = 0.f, b = 0.f;
+    if (h->last_path == MPPI_PATH_TWO_KERNELS) {
+        MPPI_CUDA(h, cudaEventElapsedTime(&a, h->ev[0], h->ev[1]));
+        MPPI_CUDA(h, cudaEventElapsedTime(&b, h->ev[1], h->ev[2]));
+    } else {
+        MPPI_CUDA(h, cudaEventElapsedTime(&a, h->ev[0], h->ev[2]));      // one launch: the whole step
+    }
+    us3[0] = a * 1e3f; us3[1] = b * 1e3f; us3[2] = (float)h->last_path;
+    return MPPI_OK;
+}
+
 mppi_status_t mppi_generate_noise(mppi_handle_t h, uint64_t step_counter, float *d_noise, void *stream)
 {
     if (!h || !d_noise) return fail(h, MPPI_ERR_INVALID_ARG, "null noise buffer");
@@ -980,13 +855,18 @@ mppi_status_t mppi_generate_noise(mppi_handle_t h, uint64_t step_counter, float 
     cudaStream_t st = (cudaStream_t)stream;
     const uint32_t lo = (uint32_t)step_counter, hi = (uint32_t)(step_counter >> 32);
     const int grid = h->num_sms * 8;
+#define MPPI_GEN(NU_)                                                                                        \
+    if (h->philox_rounds == 7) generate_noise_kernel<NU_, 7><<<grid, 256, 0, st>>>(h->P, lo, hi, d_noise);   \
+    else generate_noise_kernel<NU_, 10><<<grid, 256, 0, st>>>(h->P, lo, hi, d_noise);                        \
+    break
     switch (h->nu) {
-        case 3: generate_noise_kernel<3><<<grid, 256, 0, st>>>(h->P, lo, hi, d_noise); break;
-        case 4: generate_noise_kernel<4><<<grid, 256, 0, st>>>(h->P, lo, hi, d_noise); break;
-        case 7: generate_noise_kernel<7><<<grid, 256, 0, st>>>(h->P, lo, hi, d_noise); break;
-        case 11: generate_noise_kernel<11><<<grid, 256, 0, st>>>(h->P, lo, hi, d_noise); break;
+        case 3: MPPI_GEN(3);
+        case 4: MPPI_GEN(4);
+        case 7: MPPI_GEN(7);
+        case 11: MPPI_GEN(11);
         default: return fail(h, MPPI_ERR_INVALID_ARG, "bad nu");
     }
+#undef MPPI_GEN
     MPPI_CUDA(h, cudaGetLastError());
     return MPPI_OK;
 }
@@ -1027,12 +907,29 @@ mppi_status_t mppi_measure_fp32_peak(int32_t device, float *tflops_out)
 
 double mppi_algorithmic_flops_per_rollout_step(int32_t model)
 {
-    // rollout + cost, dense URDF constants, FMA = 2 FLOP, transcendentals excluded.
+    // Counted, not estimated: oracle/flop_count.py replays the restated maths of one rollout-step on a counting scalar
+    // type with GENERAL (dense) URDF constants -- add / sub / mul = 1 FLOP (FMA = 2), transcendental evaluations
+    // (sin/cos, atan2, asin, sqrt, reciprocal) excluded (SURVEY section 8(d) convention).  tests/test_flop_count.py
+    // holds these constants to the counter.  (The survey's pre-build estimate was 40 / 90 / 840 / 1000.)
     switch (model) {
-        case MPPI_MODEL_DRONE3: return 40.0;
-        case MPPI_MODEL_QUAD4: return 90.0;
-        case MPPI_MODEL_ARM7: return 840.0;
-        case MPPI_MODEL_WB11: return 1000.0;
+        case MPPI_MODEL_DRONE3: return 42.0;
+        case MPPI_MODEL_QUAD4: return 81.0;
+        case MPPI_MODEL_ARM7: return 686.0;
+        case MPPI_MODEL_WB11: return 850.0;
+        default: return 0.0;
+    }
+}
+
+double mppi_structural_flops_per_rollout_step(int32_t model)
+{
+    // The same counter with multiplications by constants that are exactly 0 / +-1 and additions of exact zeros skipped
+    // (the j2s7s300 origins are right-angle rotations): the FLOPs a kernel with the chain unrolled from its URDF
+    // constants still has to execute, again without the transcendental evaluations.
+    switch (model) {
+        case MPPI_MODEL_DRONE3: return 42.0;
+        case MPPI_MODEL_QUAD4: return 75.0;
+        case MPPI_MODEL_ARM7: return 268.0;
+        case MPPI_MODEL_WB11: return 369.0;
         default: return 0.0;
     }
 }

@@ -86,6 +86,7 @@ struct P2PParams {
     unsigned epoch;              // starts at 1, +1 per control step, same on every rank
     int rowp;                    // floats per inbox row (T*nu + 4, padded to a multiple of 4)
     float *base[kMaxRanks];      // base[r] = rank r's exchange buffer as mapped in THIS process
+    unsigned *fail_flag;         // mapped host word: set to the epoch at which a peer never published (sticky)
 };
 __host__ __device__ __forceinline__ int *p2p_flags(float *base) { return reinterpret_cast<int *>(base); }
 __host__ __device__ __forceinline__ float *p2p_inbox(float *base, int world, int rowp, int parity, int src)
@@ -108,10 +109,13 @@ template <> struct ModelNu<MPPI_MODEL_WB11>   { static constexpr int value = 11;
 // ------------------------------------------------------------------------------------------
 // The ten round keys (key + r * Weyl constants) depend only on the seed: the host expands them
 // once into StepParams::rkeys, so a round is 2 IMAD.WIDE + 2 LOP3 with constant-bank operands.
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, const uint32_t *rk)
+// ROUNDS = 10 is the Random123 / cuRAND default; 7 is the smallest round count Salmon et al. (SC'11, table 2)
+// report as Crush-resistant (passes BigCrush) -- selectable per handle (MPPI_OPTION_PHILOX_ROUNDS).
+template <int ROUNDS = 10>
+__device__ __forceinline__ uint4 philox4x32(uint4 c, const uint32_t *rk)
 {
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < ROUNDS; ++r) {
         const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
         const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
         c = make_uint4(hi1 ^ c.y ^ rk[2 * r], lo1, hi0 ^ c.w ^ rk[2 * r + 1], lo0);
@@ -160,13 +164,13 @@ __device__ __forceinline__ void box_muller2(f2 fu, f2 ft, f2 &rc, f2 &rs)
 
 // The 12 uniforms of up to two calls for (global sample kg, horizon step t): call j has
 // counter = (kg, t * ncalls + j, step_lo, step_hi), key = seed.  Pair p = uniforms (2p, 2p+1) -> normals (2p, 2p+1).
-template <int NCALLS>
+template <int NCALLS, int ROUNDS = 10>
 __device__ __forceinline__ void philox_step_uniforms(uint32_t kg, uint32_t t, uint32_t step_lo, uint32_t step_hi,
                                                      const uint32_t *rkeys, float f[6 * NCALLS])
 {
 #pragma unroll
     for (int j = 0; j < NCALLS; ++j)
-        philox_uniforms6(philox4x32_10(make_uint4(kg, t * NCALLS + j, step_lo, step_hi), rkeys), f + 6 * j);
+        philox_uniforms6(philox4x32<ROUNDS>(make_uint4(kg, t * NCALLS + j, step_lo, step_hi), rkeys), f + 6 * j);
 }
 // Normals for inputs 4e .. 4e+3 (pairs 2e and 2e+1) as rc = (n[4e], n[4e+2]), rs = (n[4e+1], n[4e+3]).
 __device__ __forceinline__ void normals_quad(const float *f, int e, f2 &rc, f2 &rs)
@@ -174,11 +178,12 @@ __device__ __forceinline__ void normals_quad(const float *f, int e, f2 &rc, f2 &
     box_muller2(f2(f[4 * e], f[4 * e + 2]), f2(f[4 * e + 1], f[4 * e + 3]), rc, rs);
 }
 // The six normals of ONE call (weighting pass / noise materialisation): n[2p], n[2p+1] from pair p.
+template <int ROUNDS = 10>
 __device__ __forceinline__ void normal6(uint32_t kg, uint32_t tcall, uint32_t step_lo, uint32_t step_hi,
                                         const uint32_t *rkeys, float n[6])
 {
     float f[6];
-    philox_uniforms6(philox4x32_10(make_uint4(kg, tcall, step_lo, step_hi), rkeys), f);
+    philox_uniforms6(philox4x32<ROUNDS>(make_uint4(kg, tcall, step_lo, step_hi), rkeys), f);
     f2 rc, rs;
     box_muller2(f2(f[0], f[2]), f2(f[1], f[3]), rc, rs);
     n[0] = rc.v.x; n[1] = rs.v.x; n[2] = rc.v.y; n[3] = rs.v.y;

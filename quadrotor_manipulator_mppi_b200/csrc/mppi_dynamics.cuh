@@ -55,7 +55,7 @@ __device__ __forceinline__ void inertia_mul(float m, const float *cm, const floa
 // One recursive Newton-Euler pass over the seven arm joints (Featherstone, RBDA table 5.1; joint axes +z of the
 // folded chain): joint torques for joint rates qd, joint accelerations qdd, base twist (w0, v0) and base
 // acceleration a0 (all in the base frame).
-__device__ __noinline__ void rnea_arm7(const ChainDev &ch, const ArmInertiaDev &in, const float *cq, const float *sq,
+static __device__ __noinline__ void rnea_arm7(const ChainDev &ch, const ArmInertiaDev &in, const float *cq, const float *sq,
                                        const float *qd, const float *qdd, const float *w0, const float *v0, const float *a0,
                                        float *tau)
 {

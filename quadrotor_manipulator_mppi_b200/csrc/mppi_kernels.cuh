@@ -50,14 +50,20 @@ __host__ __device__ constexpr int pairB(int i) { return i == 0 ? 2 : i == 1 ? 3 
 //            step, kNoiseStages deep; needs K*nu % 4 == 0 and a 16-byte aligned tensor).
 constexpr int kNoiseStages = 4;
 
-// 4 blocks/SM (<= 128 registers): measured best -- with a 72-register cap (7 blocks/SM) ptxas cannot interleave the
-// Philox multiplies with the FK arithmetic and the FMA pipe stalls more (0.421 -> 0.393 ms on the bench case).
-template <int MODEL, int NOISE, bool BAKED, bool EXTRA>
-__global__ void __launch_bounds__(kRolloutThreads, MPPI_ROLLOUT_MINB)
-rollout_cost_kernel(const __grid_constant__ StepParams P, const __grid_constant__ DynBlock D,
+// Models whose horizon step is a short dependent chain (point mass, rigid body: ~100 instructions behind one Philox
+// call) are latency-bound at any occupancy this path reaches; their noise is generated kNoiseBatch steps at a time so
+// the Philox / Box-Muller chains of several steps overlap (independent counters), then the steps run back to back.
+template <int MODEL, int NOISE> struct NoiseBatch {
+    static constexpr int value = (NOISE == 0 && (MODEL == MPPI_MODEL_DRONE3 || MODEL == MPPI_MODEL_QUAD4)) ? 4 : 1;
+};
+
+// The body of K2, shared by rollout_cost_kernel and the single-launch step_fused_kernel.  Returns the sample's cost
+// (also stored to cost_out[k]); the block minimum has been folded into *rho_enc on return.
+template <int MODEL, int NOISE, bool BAKED, bool EXTRA, int ROUNDS>
+__device__ __forceinline__ float rollout_body(const StepParams &P, const DynBlock &D,
                     const float *__restrict__ u_nom, const float *__restrict__ noise,
                     float *__restrict__ cost_out, int32_t *__restrict__ rho_enc,
-                    const float *__restrict__ q_traj)
+                    const float *__restrict__ q_traj, bool &active_out)
 {
     constexpr int NU = ModelNu<MODEL>::value;
     constexpr int NCH = (NU + 3) / 4;
@@ -150,14 +156,19 @@ rollout_cost_kernel(const __grid_constant__ StepParams P, const __grid_constant_
     float Sd = 0.f;                  // squared-distance stage cost (drone / quad part)
     float term_d = 0.f;
 
-    for (int t = 0; t < P.T; ++t) {
+    constexpr int NB = NoiseBatch<MODEL, NOISE>::value;
+    for (int t0 = 0; t0 < P.T; t0 += NB) {
+      f2 a02b[NB][NCH], a13b[NB][NCH];
+#pragma unroll
+      for (int jb = 0; jb < NB; ++jb) {
+        const int t = min(t0 + jb, P.T - 1);
+        f2 *a02 = a02b[jb], *a13 = a13b[jb];
         // ---- controls of this step: v = u + noise  (S/mppi_solver/mppi.py:130).  Inputs 4c..4c+3 arrive
         // as the pairs (4c, 4c+2) and (4c+1, 4c+3).
-        f2 a02[NCH], a13[NCH];
         if constexpr (NOISE == 2) mbar_wait(&s_full[t % kNoiseStages], (t / kNoiseStages) & 1);
         float unif[6 * philox_calls(NU)];
         if constexpr (PHILOX)
-            philox_step_uniforms<philox_calls(NU)>(kg, static_cast<uint32_t>(t), D.step_lo, D.step_hi, P.rkeys, unif);
+            philox_step_uniforms<philox_calls(NU), ROUNDS>(kg, static_cast<uint32_t>(t), D.step_lo, D.step_hi, P.rkeys, unif);
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
             const int i0 = 4 * c, i1 = 4 * c + 1, i2 = 4 * c + 2, i3 = 4 * c + 3;
@@ -196,6 +207,12 @@ rollout_cost_kernel(const __grid_constant__ StepParams P, const __grid_constant_
                              noise + (static_cast<size_t>(t + kNoiseStages) * P.K + k0_blk) * NU, tile_bytes, &s_full[st]);
             }
         }
+      }
+#pragma unroll
+      for (int jb = 0; jb < NB; ++jb) {
+        const int t = t0 + jb;
+        if (NB > 1 && t >= P.T) break;
+        const f2 *a02 = a02b[jb], *a13 = a13b[jb];
         // scalar view: input i lives in (i & 1 ? a13 : a02)[i >> 2], lane (i >> 1) & 1
         auto input = [&](int i) -> float { return lane((i & 1) ? a13[i >> 2] : a02[i >> 2], (i >> 1) & 1); };
 
@@ -311,6 +328,7 @@ rollout_cost_kernel(const __grid_constant__ StepParams P, const __grid_constant_
             comp = (tS - S) - y;
             S = tS;
         }
+      }
     }
     // programmatic dependent launch: the weighting kernel of this step may start its launch now; it still waits
     // (griddepcontrol.wait) for this whole grid and its memory before it reads S or rho
@@ -340,6 +358,21 @@ rollout_cost_kernel(const __grid_constant__ StepParams P, const __grid_constant_
         for (int w = 1; w < kRolloutThreads / 32; ++w) bm = fminf(bm, s_wmin[w]);
         atomicMin(rho_enc, encode_ordered(bm));
     }
+    active_out = active;
+    return S;
+}
+
+// 4 blocks/SM (<= 128 registers): measured best -- with a 72-register cap (7 blocks/SM) ptxas cannot interleave the
+// Philox multiplies with the FK arithmetic and the FMA pipe stalls more (0.421 -> 0.393 ms on the bench case).
+template <int MODEL, int NOISE, bool BAKED, bool EXTRA, int ROUNDS>
+__global__ void __launch_bounds__(kRolloutThreads, MPPI_ROLLOUT_MINB)
+rollout_cost_kernel(const __grid_constant__ StepParams P, const __grid_constant__ DynBlock D,
+                    const float *__restrict__ u_nom, const float *__restrict__ noise,
+                    float *__restrict__ cost_out, int32_t *__restrict__ rho_enc,
+                    const float *__restrict__ q_traj)
+{
+    bool active;
+    (void)rollout_body<MODEL, NOISE, BAKED, EXTRA, ROUNDS>(P, D, u_nom, noise, cost_out, rho_enc, q_traj, active);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -347,10 +380,12 @@ rollout_cost_kernel(const __grid_constant__ StepParams P, const __grid_constant_
 // S/mppi_solver/mppi.py:148-158, drone_mppi.py:158-170, S/filter/svg_filter.py:13-90.
 //   wsum = [T*nu] raw weighted-noise sums, eta, sum w^2     scratch = 2*T*nu + nu floats of smem
 // ------------------------------------------------------------------------------------------
+// exchange_ok == false (a peer never published its shard row: p2p_exchange gave up): the controls are NOT updated
+// (u_new = u_nom), out[MPPI_OUT_STEP] = -1 is part of the published out vector, and the caller raises.
 template <int MODEL>
 __device__ void finalize_block(const StepParams &P, const DynBlock &D, const float *wsum,
                                const float *u_nom, float *u_new, float *out, int32_t *rho_enc,
-                               float *scratch)
+                               float *scratch, bool exchange_ok = true)
 {
     constexpr int NU = ModelNu<MODEL>::value;
     const int n = P.T * NU;
@@ -369,7 +404,7 @@ __device__ void finalize_block(const StepParams &P, const DynBlock &D, const flo
             s = (s >= P.T) ? (2 * P.T - 1 - s) : s;       // data[-h:].flip(0)
             acc = fmaf(P.taps[jj + P.sg_half], raw[s * NU + i], acc);
         }
-        const float v = u_nom[j] + acc;                   // u += w_eps
+        const float v = exchange_ok ? u_nom[j] + acc : u_nom[j];      // u += w_eps
         un[j] = v;
         u_new[j] = v;
     }
@@ -448,7 +483,7 @@ __device__ void finalize_block(const StepParams &P, const DynBlock &D, const flo
         if (l == 16) out[MPPI_OUT_RHO] = decode_ordered(*rho_enc);
         if (l == 17) out[MPPI_OUT_ETA] = eta;
         if (l == 18) out[MPPI_OUT_ESS] = eta * eta / eta2;
-        if (l == 19) out[MPPI_OUT_STEP] = static_cast<float>(D.step_lo & 0xffffffu);
+        if (l == 19) out[MPPI_OUT_STEP] = exchange_ok ? static_cast<float>(D.step_lo & 0xffffffu) : -1.0f;
     }
     __syncthreads();
     if (threadIdx.x == 0) *rho_enc = kRhoInit;          // re-arm the minimum for the next step
@@ -553,6 +588,10 @@ __device__ bool p2p_exchange(const StepParams &P, const P2PParams &X, float *wsu
         wsum[j] = acc;
     }
     __syncthreads();
+    if (s_ok == 0 && tid == 0 && X.fail_flag != nullptr) {       // sticky, host-visible: the next call on this handle fails
+        *reinterpret_cast<volatile unsigned *>(X.fail_flag) = X.epoch;
+        __threadfence_system();
+    }
     return s_ok != 0;
 }
 
@@ -565,7 +604,7 @@ __device__ void reduce_partials_and_finalize(const StepParams &P, const DynBlock
                                              const float *u_nom, float *u_new, float *out,
                                              int32_t *rho_enc, float *scratch, const P2PParams &X,
                                              const float *eta_part = nullptr, int n_eta = 0,
-                                             unsigned long long *fix = nullptr)
+                                             unsigned long long *fix = nullptr, bool fix_has_sigma = false)
 {
     constexpr int NU = ModelNu<MODEL>::value;
     __shared__ bool s_last;
@@ -584,7 +623,7 @@ __device__ void reduce_partials_and_finalize(const StepParams &P, const DynBlock
         for (int j = threadIdx.x; j < row; j += blockDim.x) {
             const long long q = static_cast<long long>(__ldcg(fix + j));
             fix[j] = 0ull;
-            const float scale = (j < row - 2) ? P.sigma[j % NU] * (1.0f / kFixScale) : (1.0f / kFixScale);
+            const float scale = (j < row - 2 && !fix_has_sigma) ? P.sigma[j % NU] * (1.0f / kFixScale) : (1.0f / kFixScale);
             wsum[j] = static_cast<float>(q) * scale;
         }
     } else
@@ -609,10 +648,7 @@ __device__ void reduce_partials_and_finalize(const StepParams &P, const DynBlock
     __syncthreads();
     bool ok = true;
     if (X.world > 1) ok = p2p_exchange<MODEL>(P, X, wsum, rho_enc);
-    if (fuse) {
-        finalize_block<MODEL>(P, D, wsum, u_nom, u_new, out, rho_enc, scratch);
-        if (!ok && out != nullptr && threadIdx.x == 0) out[MPPI_OUT_STEP] = -1.0f;      // peer exchange timed out
-    }
+    if (fuse) finalize_block<MODEL>(P, D, wsum, u_nom, u_new, out, rho_enc, scratch, ok);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -622,7 +658,7 @@ __device__ void reduce_partials_and_finalize(const StepParams &P, const DynBlock
 // zero-weight samples are skipped (exact: w == 0.0f contributes 0).
 // S/mppi_solver/mppi.py:143-148,173-193.
 // ------------------------------------------------------------------------------------------
-template <int MODEL>
+template <int MODEL, int ROUNDS>
 __global__ void __launch_bounds__(1024)
 weight_philox_kernel(const __grid_constant__ StepParams P, const __grid_constant__ DynBlock D,
                      const float *__restrict__ S, int32_t *rho_enc, int chunk,
@@ -691,8 +727,8 @@ weight_philox_kernel(const __grid_constant__ StepParams P, const __grid_constant
             for (int j = r; j < n_nz; j += R) {
                 const float w = s_w[j];
                 float unif[6 * philox_calls(NU)];
-                philox_step_uniforms<philox_calls(NU)>(static_cast<uint32_t>(P.k_offset + base + s_idx[j]), static_cast<uint32_t>(t),
-                                                       D.step_lo, D.step_hi, P.rkeys, unif);
+                philox_step_uniforms<philox_calls(NU), ROUNDS>(static_cast<uint32_t>(P.k_offset + base + s_idx[j]), static_cast<uint32_t>(t),
+                                                               D.step_lo, D.step_hi, P.rkeys, unif);
 #pragma unroll
                 for (int e = 0; e < NQ; ++e) {         // sigma is applied once, after the reduction
                     f2 n02, n13;
@@ -738,10 +774,363 @@ weight_philox_kernel(const __grid_constant__ StepParams P, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------
+// Single-launch control step for grids that are co-resident (cooperative launch; K_local <= 128 x resident blocks,
+// i.e. the per-GPU shard of the 8-GPU configuration and every reference-sized problem): rollout, ONE grid-wide
+// barrier (the cost minimum is then final), the weighting of the block's own samples with the noise regenerated
+// for the survivors, fixed-point atomics, and the exchange + finalize in the last block to arrive.  Replaces the
+// rollout -> weighting launch pair (and its ~15 us of fixed cost: second launch, S re-read, 1024-thread blocks
+// re-deriving what this block already holds in registers).  S/mppi_solver/mppi.py:122-158.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// Monotonic arrival counter; `target` is the value it reaches when every block of THIS launch has arrived (the host
+// adds gridDim to it per launch; the signed difference makes the wrap-around harmless).
+__device__ __forceinline__ void grid_barrier(unsigned *ctr, unsigned target)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        while (static_cast<int>(ld_acquire_gpu_u32(ctr) - target) < 0) { }
+    }
+    __syncthreads();
+}
+
+template <int MODEL, bool BAKED, bool EXTRA, int ROUNDS>
+__global__ void __launch_bounds__(kRolloutThreads, MPPI_ROLLOUT_MINB)
+step_fused_kernel(const __grid_constant__ StepParams P, const __grid_constant__ DynBlock D,
+                  const float *__restrict__ u_nom, float *__restrict__ cost_out, int32_t *rho_enc,
+                  const float *__restrict__ q_traj, unsigned long long *__restrict__ fix, uint32_t *counter,
+                  unsigned *sync_ctr, unsigned sync_target, float *wsum, float *u_new, float *out,
+                  const __grid_constant__ P2PParams X)
+{
+    constexpr int NU = ModelNu<MODEL>::value;
+    constexpr int NQ = (NU + 3) / 4;
+    constexpr int NUP = 4 * NQ;
+    constexpr int NW = kRolloutThreads / 32;
+    extern __shared__ __align__(16) float s_dyn[];      // rollout: u_nom | then: weights, indices, reduction, finalize scratch
+    __shared__ float s_eta[NW], s_eta2[NW];
+    __shared__ int s_cnt[NW];
+
+    bool active;
+    const float S = rollout_body<MODEL, 0, BAKED, EXTRA, ROUNDS>(P, D, u_nom, nullptr, cost_out, rho_enc, q_traj, active);
+    grid_barrier(sync_ctr, sync_target);                 // every block has folded its minimum into *rho_enc
+    const float rho = decode_ordered(__ldcg(rho_enc));
+
+    float *s_w = s_dyn;
+    int *s_idx = reinterpret_cast<int *>(s_dyn + kRolloutThreads);
+    float *s_red = s_dyn + 2 * kRolloutThreads;
+    const int tid = threadIdx.x;
+    const int TC = P.T;                                  // <= kRolloutThreads (checked by the launcher)
+    const int R = kRolloutThreads / TC;
+    const bool worker = tid < R * TC;
+    const int r = tid / TC, t = tid - r * TC;
+
+    // weights of the block's own samples + order-preserving compaction of the non-zero ones
+    const float w = active ? expf(-P.inv_lambda * (S - rho)) : 0.f;
+    float eta = warp_sum(w), eta2 = warp_sum(w * w);
+    const unsigned ball = __ballot_sync(0xffffffffu, w != 0.f);
+    if ((tid & 31) == 0) { s_cnt[tid >> 5] = __popc(ball); s_eta[tid >> 5] = eta; s_eta2[tid >> 5] = eta2; }
+    __syncthreads();
+    int warp_off = 0, n_nz = 0;
+#pragma unroll
+    for (int wv = 0; wv < NW; ++wv) {
+        if (wv < (tid >> 5)) warp_off += s_cnt[wv];
+        n_nz += s_cnt[wv];
+    }
+    if (w != 0.f) {
+        const int slot = warp_off + __popc(ball & ((1u << (tid & 31)) - 1u));
+        s_idx[slot] = tid;
+        s_w[slot] = w;
+    }
+    __syncthreads();
+    float acc[NUP];
+#pragma unroll
+    for (int i = 0; i < NUP; ++i) acc[i] = 0.f;
+    if (worker) {
+        const uint32_t kg0 = static_cast<uint32_t>(P.k_offset + blockIdx.x * kRolloutThreads);
+        for (int j = r; j < n_nz; j += R) {
+            const float wj = s_w[j];
+            float unif[6 * philox_calls(NU)];
+            philox_step_uniforms<philox_calls(NU), ROUNDS>(kg0 + static_cast<uint32_t>(s_idx[j]), static_cast<uint32_t>(t),
+                                                           D.step_lo, D.step_hi, P.rkeys, unif);
+#pragma unroll
+            for (int e = 0; e < NQ; ++e) {             // sigma is applied once, after the reduction
+                f2 n02, n13;
+                normals_quad(unif, e, n02, n13);
+                acc[4 * e] = fmaf(wj, n02.v.x, acc[4 * e]);
+                acc[4 * e + 1] = fmaf(wj, n13.v.x, acc[4 * e + 1]);
+                acc[4 * e + 2] = fmaf(wj, n02.v.y, acc[4 * e + 2]);
+                acc[4 * e + 3] = fmaf(wj, n13.v.y, acc[4 * e + 3]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < NUP; ++i) s_red[(r * TC + t) * NUP + i] = acc[i];
+    }
+    __syncthreads();
+    const int row = P.T * NU + 2;
+    if (n_nz > 0) {
+        for (int o = tid; o < TC * NU; o += kRolloutThreads) {
+            const int tt = o / NU, i = o - tt * NU;
+            float v = 0.f;
+            for (int rr = 0; rr < R; ++rr) v += s_red[(rr * TC + tt) * NUP + i];
+            if (v != 0.f) atomicAdd(fix + o, static_cast<unsigned long long>(__float2ll_rn(v * kFixScale)));
+        }
+        if (tid == 0) {
+            float e = 0.f, e2 = 0.f;
+#pragma unroll
+            for (int wv = 0; wv < NW; ++wv) { e += s_eta[wv]; e2 += s_eta2[wv]; }
+            if (e != 0.f) atomicAdd(fix + row - 2, static_cast<unsigned long long>(__float2ll_rn(e * kFixScale)));
+            if (e2 != 0.f) atomicAdd(fix + row - 1, static_cast<unsigned long long>(__float2ll_rn(e2 * kFixScale)));
+        }
+    }
+    reduce_partials_and_finalize<MODEL>(P, D, nullptr, 0, counter, wsum, true, u_nom, u_new, out, rho_enc, s_dyn, X,
+                                        nullptr, 0, fix);
+}
+
+// ------------------------------------------------------------------------------------------
+// Time-parallel control step for the models whose dynamics are a LINEAR double integrator (ARM7, DRONE3 -- the two
+// controllers the reference runs): ONE WARP PER SAMPLE, lane l owns the SPL consecutive horizon steps
+// [l*SPL, (l+1)*SPL).  The reference integrates with two cumulative sums over the horizon
+// (S/sampling/standard_normal_noise.py:37-48, S/mppi_solver/drone_mppi.py:47-54); here they are two warp scans, after
+// which every (sample, step) pair evaluates its FK + cost independently -- K*T-way instead of K-way parallelism, which
+// is what a reference-sized problem (K = 100 ... 1000, T = 30) needs to fill 148 SMs: the thread-per-sample kernel
+// runs it as 8 blocks of serial 30-step chains.  The lanes still hold their step's noise when the sample's cost is
+// known, so the weighted-noise sum needs no second pass and no regeneration: each block keeps a running soft-min
+// accumulator (block-local minimum, rescaled when a new minimum arrives), and after ONE grid-wide barrier the block
+// rows are rescaled to the global minimum and added into the fixed-point accumulators; the last block to arrive
+// exchanges with the peer shards (if any) and finalizes.  One launch per control step.
+// NOISE: 0 = in-kernel Philox (same (k, t, call, step) addressing as every other kernel: bit-identical normals),
+//        1 = injected [T][K][nu].
+// S/mppi_solver/mppi.py:122-158, S/mppi_solver/drone_mppi.py:140-170.
+// ------------------------------------------------------------------------------------------
+constexpr int kTpThreads = 128;
+constexpr int kTpWarps = kTpThreads / 32;
+
+__device__ __forceinline__ float warp_excl_scan(float x, int lane)
+{
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const float y = __shfl_up_sync(0xffffffffu, x, d);
+        if (lane >= d) x += y;
+    }
+    const float e = __shfl_up_sync(0xffffffffu, x, 1);
+    return lane ? e : 0.f;
+}
+
+// Sum over the warp with the rounding errors carried along (TwoSum butterfly): the result is the float32 nearest to
+// the exact sum of the 32 inputs (to ~2^-45 relative) in every lane.  The arm's cost is ~1e3 with a spread of ~3 against
+// lambda = 0.1, so one ulp of S moves a weight by 0.12 %: the serial kernel Kahan-compensates for the same reason.
+__device__ __forceinline__ float warp_sum_compensated(float hi, float lo)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float bh = __shfl_xor_sync(0xffffffffu, hi, o), bl = __shfl_xor_sync(0xffffffffu, lo, o);
+        const float s = __fadd_rn(hi, bh);
+        const float bb = __fsub_rn(s, hi);
+        const float e = __fadd_rn(__fsub_rn(hi, __fsub_rn(s, bb)), __fsub_rn(bh, bb));
+        hi = s;
+        lo = __fadd_rn(__fadd_rn(lo, bl), e);
+    }
+    return __fadd_rn(hi, lo);
+}
+
+template <int MODEL, int NOISE, bool BAKED, int SPL, int ROUNDS>
+__global__ void __launch_bounds__(kTpThreads)
+step_tp_kernel(const __grid_constant__ StepParams P, const __grid_constant__ DynBlock D,
+               const float *__restrict__ u_nom, const float *__restrict__ noise, float *__restrict__ cost_out,
+               int32_t *rho_enc, unsigned long long *__restrict__ fix, uint32_t *counter, unsigned *sync_ctr,
+               unsigned sync_target, float *wsum, float *u_new, float *out, const __grid_constant__ P2PParams X)
+{
+    static_assert(MODEL == MPPI_MODEL_ARM7 || MODEL == MPPI_MODEL_DRONE3, "linear-integrator models only");
+    constexpr int NU = ModelNu<MODEL>::value;
+    constexpr int NQ = (NU + 3) / 4;
+    constexpr int NUP = 4 * NQ;
+    constexpr bool PHILOX = (NOISE == 0);
+    constexpr int Q0 = 0, QD0 = (MODEL == MPPI_MODEL_ARM7) ? 7 : 3;
+    extern __shared__ __align__(16) float s_dyn[];       // [n] block accumulator | [kTpWarps][n] tile contributions (finalize scratch later)
+    __shared__ float s_S[kTpWarps], s_W[kTpWarps];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = P.T * NU;
+    float *s_acc = s_dyn, *s_con = s_dyn + n;
+    for (int j = tid; j < n; j += kTpThreads) s_acc[j] = 0.f;
+    float rho_blk = __int_as_float(0x7f800000), eta_blk = 0.f, eta2_blk = 0.f;
+
+    Pose3 base0;                                          // arm: base pose composed with C0 (uniform)
+    if constexpr (MODEL == MPPI_MODEL_ARM7) {
+        float R0[9], p0[3];
+        quat_matrix(&D.state[14], R0);
+        p0[0] = D.state[14]; p0[1] = D.state[15]; p0[2] = D.state[16];
+        if constexpr (BAKED) compose_tab<FkKinova, 0>(R0, p0);
+        else compose_const(R0, p0, P.chain.R[0], P.chain.t[0]);
+        base0 = pose3_from(R0, p0);
+    }
+    __syncthreads();
+
+    const int n_tiles = (P.K + kTpWarps - 1) / kTpWarps;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int k_raw = tile * kTpWarps + warp;
+        const bool active = k_raw < P.K;                  // warp-uniform
+        const int k = active ? k_raw : P.K - 1;
+        const uint32_t kg = static_cast<uint32_t>(P.k_offset + k);
+
+        // ---- noise and controls of this lane's steps: a = u_nom + eps  (mppi.py:130)
+        float nrm[SPL][NUP], a[SPL][NU];
+#pragma unroll
+        for (int s = 0; s < SPL; ++s) {
+            const int t = lane * SPL + s;
+            const bool valid = t < P.T;
+            const int tc = valid ? t : P.T - 1;
+            if constexpr (PHILOX) {
+                float unif[6 * philox_calls(NU)];
+                philox_step_uniforms<philox_calls(NU), ROUNDS>(kg, static_cast<uint32_t>(tc), D.step_lo, D.step_hi, P.rkeys, unif);
+#pragma unroll
+                for (int e = 0; e < NQ; ++e) {
+                    f2 n02, n13;
+                    normals_quad(unif, e, n02, n13);
+                    nrm[s][4 * e] = n02.v.x; nrm[s][4 * e + 1] = n13.v.x; nrm[s][4 * e + 2] = n02.v.y; nrm[s][4 * e + 3] = n13.v.y;
+                }
+            } else {
+                const float *row = noise + (static_cast<size_t>(tc) * P.K + k) * NU;
+#pragma unroll
+                for (int i = 0; i < NUP; ++i) nrm[s][i] = (i < NU) ? __ldg(row + i) : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < NU; ++i) {
+                const float eps = PHILOX ? __fmul_rn(P.sigma[i], nrm[s][i]) : nrm[s][i];
+                a[s][i] = valid ? __fadd_rn(__ldg(u_nom + tc * NU + i), eps) : 0.f;
+                if (!valid) nrm[s][i] = 0.f;
+            }
+        }
+        // ---- double integrator as two scans over the horizon (standard_normal_noise.py:37-48 / drone_mppi.py:47-54)
+        float qs[SPL][NU];                                // position-like state after each of this lane's steps
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+            float lcv[SPL];
+            float c = 0.f;
+#pragma unroll
+            for (int s = 0; s < SPL; ++s) { c = fmaf(a[s][i], P.dt, c); lcv[s] = c; }
+            const float ex_v = warp_excl_scan(c, lane);   // sum a dt over all earlier lanes
+            const float v0 = D.state[QD0 + i];
+            float lcq[SPL];
+            float cq = 0.f;
+#pragma unroll
+            for (int s = 0; s < SPL; ++s) {
+                const float vprev = ((s == 0) ? ex_v : ex_v + lcv[s - 1]) + v0;
+                cq += fmaf(vprev, P.dt, (0.5f * a[s][i]) * P.dt2);
+                lcq[s] = cq;
+            }
+            const float ex_q = warp_excl_scan(cq, lane);
+#pragma unroll
+            for (int s = 0; s < SPL; ++s) qs[s][i] = (ex_q + lcq[s]) + D.state[Q0 + i];
+        }
+        // ---- per-step cost, every (sample, step) pair on its own lane
+        float S;
+        if constexpr (MODEL == MPPI_MODEL_DRONE3) {
+            float Sd = 0.f, term = 0.f;
+#pragma unroll
+            for (int s = 0; s < SPL; ++s) {
+                const int t = lane * SPL + s;
+                float sq = 0.f;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) { const float e = qs[s][i] - D.drone_target[i]; sq = fmaf(e, e, sq); }
+                if (t < P.T - 1) Sd += sq;
+                else if (t == P.T - 1) term = sq;
+            }
+            Sd = warp_sum(Sd); term = warp_sum(term);
+            S = fmaf(Sd, P.cost_w[4], term * P.cost_w[5]);          // drone_mppi.py:87-107
+        } else {
+            float csum = 0.f, ccomp = 0.f;                // Kahan over this lane's steps, TwoSum across the lanes
+#pragma unroll
+            for (int s = 0; s < SPL; ++s) {
+                const int t = lane * SPL + s;
+                float cq[7], sq[7];
+                f2 s2, c2;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    sincos_pi(f2(qs[s][2 * i], qs[s][2 * i + 1]), s2, c2);
+                    sq[2 * i] = s2.v.x; cq[2 * i] = c2.v.x; sq[2 * i + 1] = s2.v.y; cq[2 * i + 1] = c2.v.y;
+                }
+                sincos_pi(qs[s][6], sq[6], cq[6]);
+                Pose3 Tp = base0;
+                if constexpr (BAKED) pose3_fk_tab<FkKinova>(cq, sq, Tp);
+                else pose3_fk_chain<7>(P.chain, qs[s], cq, sq, Tp);
+                float pos, ori;
+                pose3_terms(Tp, D, pos, ori);
+                const float c = (t == P.T - 1) ? fmaf(P.cost_w[2], pos, P.cost_w[3] * ori)
+                                               : fmaf(P.cost_w[0], pos, P.cost_w[1] * ori);      // cost_manager.py:30-33,78-89
+                const float y = __fsub_rn((t < P.T) ? c : 0.f, ccomp);
+                const float tS = __fadd_rn(csum, y);
+                ccomp = __fsub_rn(__fsub_rn(tS, csum), y);
+                csum = tS;
+            }
+            S = warp_sum_compensated(csum, -ccomp);
+        }
+        if (lane == 0 && active) cost_out[k] = S;
+
+        // ---- running soft-min accumulation of the tile (fixed order: deterministic)
+        if (lane == 0) s_S[warp] = active ? S : __int_as_float(0x7f800000);
+        __syncthreads();
+        float tmin = s_S[0];
+#pragma unroll
+        for (int wv = 1; wv < kTpWarps; ++wv) tmin = fminf(tmin, s_S[wv]);
+        const float new_rho = fminf(rho_blk, tmin);
+        const float c_old = (new_rho < rho_blk) ? expf(-P.inv_lambda * (rho_blk - new_rho)) : 1.0f;    // exp(-inf) = 0 on the first tile
+        const float w = active ? expf(-P.inv_lambda * (S - new_rho)) : 0.f;
+        if (lane == 0) s_W[warp] = w;
+#pragma unroll
+        for (int s = 0; s < SPL; ++s) {
+            const int t = lane * SPL + s;
+            if (t < P.T) {
+#pragma unroll
+                for (int i = 0; i < NU; ++i) s_con[warp * n + t * NU + i] = w * nrm[s][i];
+            }
+        }
+        __syncthreads();
+        for (int j = tid; j < n; j += kTpThreads) {
+            float v = s_acc[j] * c_old;
+#pragma unroll
+            for (int wv = 0; wv < kTpWarps; ++wv) v += s_con[wv * n + j];
+            s_acc[j] = v;
+        }
+        eta_blk *= c_old; eta2_blk *= c_old * c_old;
+#pragma unroll
+        for (int wv = 0; wv < kTpWarps; ++wv) { const float ww = s_W[wv]; eta_blk += ww; eta2_blk = fmaf(ww, ww, eta2_blk); }
+        rho_blk = new_rho;
+        __syncthreads();
+    }
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // ---- global minimum, then every block row rescaled to it and added into the fixed-point accumulators
+    if (tid == 0) atomicMin(rho_enc, encode_ordered(rho_blk));
+    grid_barrier(sync_ctr, sync_target);
+    const float rho = decode_ordered(__ldcg(rho_enc));
+    const float cb = expf(-P.inv_lambda * (rho_blk - rho));
+    const int row = n + 2;
+    if (cb != 0.f) {
+        for (int j = tid; j < n; j += kTpThreads) {
+            const float v = s_acc[j] * cb;
+            if (v != 0.f) atomicAdd(fix + j, static_cast<unsigned long long>(__float2ll_rn(v * kFixScale)));
+        }
+        if (tid == 0) {
+            const float e = eta_blk * cb, e2 = eta2_blk * cb * cb;
+            if (e != 0.f) atomicAdd(fix + row - 2, static_cast<unsigned long long>(__float2ll_rn(e * kFixScale)));
+            if (e2 != 0.f) atomicAdd(fix + row - 1, static_cast<unsigned long long>(__float2ll_rn(e2 * kFixScale)));
+        }
+    }
+    reduce_partials_and_finalize<MODEL>(P, D, nullptr, 0, counter, wsum, true, u_nom, u_new, out, rho_enc, s_dyn, X,
+                                        nullptr, 0, fix, /*fix_has_sigma=*/!PHILOX);
+}
+
+// ------------------------------------------------------------------------------------------
 // K3a (injected-noise path): w[k] = exp((rho - S[k]) / lambda) once, plus deterministic partial
 // sums of w and w^2.  S/mppi_solver/mppi.py:173-193.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 weights_kernel(const __grid_constant__ StepParams P, const float *__restrict__ S, const int32_t *__restrict__ rho_enc,
                float *__restrict__ w, float *__restrict__ eta_part)
 {
@@ -861,7 +1250,7 @@ weighted_noise_kernel(const __grid_constant__ StepParams P, const __grid_constan
 }
 
 // Materialise the Philox noise of one step (equivalence checks, HBM-bound experiments).
-template <int NU>
+template <int NU, int ROUNDS>
 __global__ void __launch_bounds__(256)
 generate_noise_kernel(const __grid_constant__ StepParams P, uint32_t step_lo, uint32_t step_hi,
                       float *__restrict__ noise)
@@ -875,7 +1264,7 @@ generate_noise_kernel(const __grid_constant__ StepParams P, uint32_t step_lo, ui
         const int k = static_cast<int>(tk % P.K);
         const int t = static_cast<int>(tk / P.K);
         float n6[6];
-        normal6(static_cast<uint32_t>(P.k_offset + k), static_cast<uint32_t>(t * NCH + c), step_lo, step_hi, P.rkeys, n6);
+        normal6<ROUNDS>(static_cast<uint32_t>(P.k_offset + k), static_cast<uint32_t>(t * NCH + c), step_lo, step_hi, P.rkeys, n6);
 #pragma unroll
         for (int j = 0; j < 6; ++j)
             if (6 * c + j < NU) noise[(static_cast<size_t>(t) * P.K + k) * NU + 6 * c + j] = __fmul_rn(P.sigma[6 * c + j], n6[j]);
@@ -883,7 +1272,7 @@ generate_noise_kernel(const __grid_constant__ StepParams P, uint32_t step_lo, ui
 }
 
 // FP32 FFMA throughput probe: 8 independent chains per thread.
-__global__ void __launch_bounds__(256) ffma_probe_kernel(float *out, int iters, float a, float b)
+static __global__ void __launch_bounds__(256) ffma_probe_kernel(float *out, int iters, float a, float b)
 {
     float x0 = threadIdx.x, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
     for (int i = 0; i < iters; ++i) {

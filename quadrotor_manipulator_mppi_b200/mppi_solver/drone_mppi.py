@@ -14,6 +14,7 @@ import torch
 
 from .. import _native
 from ..core import NativeSolver
+from ..utils.pose import TensorWatch
 
 
 _STATS = slice(_native.MPPI_OUT_RHO, _native.MPPI_OUT_ESS + 1)
@@ -23,7 +24,7 @@ class MPPI:
     MODEL = _native.MODEL_DRONE3
 
     def __init__(self, *, n_samples: int = 1000, n_timestep: int = 32, dt: float = 0.01, sigma=30.0,
-                 lam: float = 0.1, seed: int = 0, device=None):
+                 lam: float = 0.1, seed: int = 0, device=None, philox_rounds=None, fused=None, time_parallel=None):
         self.n_samples = int(n_samples)
         self.n_timestep = int(n_timestep)
         self.dt = float(dt)
@@ -31,11 +32,12 @@ class MPPI:
         self.param_lambda = float(lam)
         self.param_gamma = self.param_lambda * (1.0 - 0.9)                     # drone_mppi.py:35 (unused there too)
         self._solver = NativeSolver(self.MODEL, n_samples=n_samples, n_horizon=n_timestep, dt=dt, lam=lam,
-                                    sigma=sigma, seed=seed, device=device)
+                                    sigma=sigma, seed=seed, device=device, philox_rounds=philox_rounds, fused=fused,
+                                    time_parallel=time_parallel)
         self.device = self._solver.device
         self.sigma = torch.eye(3, device=self.device) * torch.as_tensor(sigma, dtype=torch.float32, device=self.device)
         self.target = torch.tensor([1.0, 2.0, 3.4])                            # drone_mppi.py:141
-        self._target_sent = None
+        self._target_watch = TensorWatch()
         self._state = np.zeros(6, np.float32)
         self._solver.set_state(self._state)
         self.last_costs = None
@@ -44,7 +46,8 @@ class MPPI:
 
     @property
     def u_prev(self) -> torch.Tensor:
-        return self._solver.u_prev
+        """Nominal sequence (warm start, not shifted).  A fresh clone: the solver's ping-pong buffers are reused."""
+        return self._solver.u_prev.clone()
 
     @u_prev.setter
     def u_prev(self, value):
@@ -52,7 +55,7 @@ class MPPI:
 
     @property
     def u(self) -> torch.Tensor:
-        return self._solver.u_prev[0]
+        return self._solver.u_prev[0].clone()
 
     def set_state(self, x, v):
         """drone_mppi.py:179-183."""
@@ -72,10 +75,8 @@ class MPPI:
     def compute_control_input(self, noise=None, noise_layout: str = "tkn", return_costs: bool = False):
         """drone_mppi.py:140-176."""
         t_ = self.target
-        key = (id(t_), t_._version) if isinstance(t_, torch.Tensor) else tuple(t_)      # in-place edits bump _version
-        if key != self._target_sent:
+        if self._target_watch.changed(t_):                  # re-assigned or edited in place since the last upload
             self._solver.set_target(drone_target=tuple(float(v) for v in torch.as_tensor(t_).reshape(-1)))
-            self._target_sent = key
         # blocking step: the out vector arrives in pinned host memory (zero-copy store), so the caller's
         # `xdes.to('cpu').tolist()` (drone.py:240) costs nothing more
         out = self._solver.step(self._solver.prepare_noise(noise, noise_layout))

@@ -20,7 +20,7 @@ import torch
 
 from .. import _native
 from ..core import NativeSolver
-from ..utils.pose import Pose
+from ..utils.pose import Pose, TensorWatch
 
 
 _U0_NEW = slice(_native.MPPI_OUT_U0_NEW, _native.MPPI_OUT_U0_NEW + 7)
@@ -37,7 +37,7 @@ class MPPI:
 
     def __init__(self, *, n_samples: int = 100, n_horizon: int = 32, dt: float = 0.01, sigma=0.1, lam: float = 0.1,
                  seed: int = 0, device=None, verbose: bool = True, cost_terms=(), torque_law: bool = False,
-                 torque_gains=(400.0, 40.0)):
+                 torque_gains=(400.0, 40.0), philox_rounds=None, fused=None, time_parallel=None):
         self.n_action = 7
         self.n_manipulator_dof = 7
         self.n_mobile_dof = 0
@@ -56,7 +56,8 @@ class MPPI:
         if self.torque_law:
             flags |= _native.OPT_TORQUE_LAW
         self._solver = NativeSolver(self.MODEL, n_samples=n_samples, n_horizon=n_horizon, dt=dt, lam=lam, sigma=sigma,
-                                    seed=seed, device=device, cost_flags=flags, torque_gains=torque_gains)
+                                    seed=seed, device=device, cost_flags=flags, torque_gains=torque_gains,
+                                    philox_rounds=philox_rounds, fused=fused, time_parallel=time_parallel)
         self.torque = np.zeros(7)
         self.device = self._solver.device
         if verbose:
@@ -67,7 +68,7 @@ class MPPI:
         self.target_pose = Pose()
         self.target_pose.pose = torch.tensor([0.1029, 0.4055, 1.6498])        # mppi.py:71
         self.target_pose.orientation = torch.tensor([-0.5, -0.5, 0.5, -0.5])  # mppi.py:72
-        self._target_key = None
+        self._target_watch = TensorWatch()
         self.ee_pose = Pose()
         # The measured state is ONE tuple (q, qdot, base xyz+quat, dtype) replaced atomically by update_joint() on the
         # subscriber thread and read once per step: a step never mixes two sensor messages, and the callback never
@@ -84,7 +85,9 @@ class MPPI:
     # ------------------------------------------------------------------ reference attribute surface
     @property
     def u_prev(self) -> torch.Tensor:
-        return self._solver.u_prev
+        """Nominal sequence [T][7] (warm start, not shifted: mppi.py:125,153).  A fresh clone, like the reference's
+        `u.clone()`: the solver's ping-pong buffers are overwritten two steps later."""
+        return self._solver.u_prev.clone()
 
     @u_prev.setter
     def u_prev(self, value):
@@ -92,7 +95,7 @@ class MPPI:
 
     @property
     def u(self) -> torch.Tensor:
-        return self._solver.u_prev[0]
+        return self._solver.u_prev[0].clone()
 
     @property
     def qdes(self) -> torch.Tensor:
@@ -105,7 +108,7 @@ class MPPI:
 
     @property
     def _qddot(self) -> torch.Tensor:
-        return self._solver._u[self._solver._cur ^ 1][0]
+        return self._solver._u[self._solver._cur ^ 1][0].clone()
 
     @property
     def _q64(self):
@@ -162,11 +165,9 @@ class MPPI:
 
     # ------------------------------------------------------------------ the control step
     def _sync_target(self):
-        key = self.target_pose.version_key()
-        if key != self._target_key:
+        if self._target_watch.changed(self.target_pose.pose, self.target_pose.orientation):
             tgt = self.target_pose.as_floats()
             self._solver.set_target(pos=tgt[:3], quat=tgt[3:])
-            self._target_key = key
 
     def compute_control_input(self, noise=None, noise_layout: str = "tkn", return_costs: bool = False):
         """mppi.py:122-169.  `noise`: optional injected noise, [T][K][nu] ("tkn") or the

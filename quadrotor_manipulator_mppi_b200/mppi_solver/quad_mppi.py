@@ -12,13 +12,14 @@ import torch
 
 from .. import _native
 from ..core import NativeSolver
+from ..utils.pose import TensorWatch
 
 
 class MPPI:
     MODEL = _native.MODEL_QUAD4
 
     def __init__(self, *, n_samples: int = 1000, n_timestep: int = 32, dt: float = 0.01, sigma=None,
-                 lam: float = 0.1, seed: int = 0, device=None, mass: float = 14.7):
+                 lam: float = 0.1, seed: int = 0, device=None, mass: float = 14.7, philox_rounds=None, fused=None):
         self.n_samples, self.n_timestep, self.dt, self.n_action = int(n_samples), int(n_timestep), float(dt), 4
         self.param_lambda = float(lam)
         self.mass = float(mass)
@@ -26,10 +27,11 @@ class MPPI:
             sigma = (30.0 * mass, 1.0, 1.0, 1.0)
         qp = (mass, 1.0 / 1.57, 1.0 / 3.93, 1.0 / 2.59, 0.0, -9.81)            # controller.cpp:488-490
         self._solver = NativeSolver(self.MODEL, n_samples=n_samples, n_horizon=n_timestep, dt=dt, lam=lam,
-                                    sigma=sigma, seed=seed, device=device, quad_params=qp)
+                                    sigma=sigma, seed=seed, device=device, quad_params=qp, philox_rounds=philox_rounds,
+                                    fused=fused)
         self.device = self._solver.device
         self.target = torch.tensor([1.0, 2.0, 3.4])
-        self._target_sent = None
+        self._target_watch = TensorWatch()
         self._state = np.zeros(12, np.float32)
         self._solver.set_state(self._state)
         hover = torch.zeros(self.n_timestep, 4)
@@ -38,7 +40,8 @@ class MPPI:
 
     @property
     def u_prev(self) -> torch.Tensor:
-        return self._solver.u_prev
+        """Nominal sequence (warm start, not shifted).  A fresh clone: the solver's ping-pong buffers are reused."""
+        return self._solver.u_prev.clone()
 
     @u_prev.setter
     def u_prev(self, value):
@@ -50,9 +53,7 @@ class MPPI:
     def compute_control_input(self, noise=None, noise_layout: str = "tkn"):
         """Returns the one-step-ahead state (p, rpy, v, w) as host tensors (blocking step)."""
         t_ = self.target
-        key = (id(t_), t_._version) if isinstance(t_, torch.Tensor) else tuple(t_)      # in-place edits bump _version
-        if key != self._target_sent:
+        if self._target_watch.changed(t_):                  # re-assigned or edited in place since the last upload
             self._solver.set_target(drone_target=tuple(float(v) for v in torch.as_tensor(t_).reshape(-1)))
-            self._target_sent = key
         out = torch.from_numpy(self._solver.step(self._solver.prepare_noise(noise, noise_layout))[0:12].copy())
         return out[0:3], out[3:6], out[6:9], out[9:12]

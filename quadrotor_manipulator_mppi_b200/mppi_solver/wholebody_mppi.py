@@ -13,7 +13,7 @@ import torch
 
 from .. import _native
 from ..core import NativeSolver
-from ..utils.pose import Pose
+from ..utils.pose import Pose, TensorWatch
 
 
 class MPPI:
@@ -21,7 +21,7 @@ class MPPI:
 
     def __init__(self, *, n_samples: int = 1000, n_horizon: int = 32, dt: float = 0.01, sigma=None,
                  lam: float = 0.1, seed: int = 0, device=None, mass: float = 14.7 + 5.5, k_offset: int = 0,
-                 torque_law: bool = False, torque_gains=(400.0, 40.0)):
+                 torque_law: bool = False, torque_gains=(400.0, 40.0), philox_rounds=None, fused=None):
         self.n_samples, self.n_horizon, self.dt, self.n_action = int(n_samples), int(n_horizon), float(dt), 11
         self._lambda = float(lam)
         self.mass = float(mass)
@@ -30,7 +30,8 @@ class MPPI:
         qp = (mass, 1.0 / 1.57, 1.0 / 3.93, 1.0 / 2.59, 0.0, -9.81)
         self._solver = NativeSolver(self.MODEL, n_samples=n_samples, n_horizon=n_horizon, dt=dt, lam=lam,
                                     sigma=sigma, seed=seed, device=device, quad_params=qp, k_offset=k_offset,
-                                    cost_flags=_native.OPT_TORQUE_LAW if torque_law else 0, torque_gains=torque_gains)
+                                    cost_flags=_native.OPT_TORQUE_LAW if torque_law else 0, torque_gains=torque_gains,
+                                    philox_rounds=philox_rounds, fused=fused)
         self.torque_law = bool(torque_law)
         self.torque = np.zeros(7)         # joint torques of the arm's computed-torque law (kinova.py:184) when enabled
         self.device = self._solver.device
@@ -38,7 +39,7 @@ class MPPI:
         self.target_pose.pose = torch.tensor([0.1029, 0.4055, 1.6498])
         self.target_pose.orientation = torch.tensor([-0.5, -0.5, 0.5, -0.5])
         self.drone_target = torch.tensor([1.0, 2.0, 3.4])
-        self._target_sent = None
+        self._target_watch = TensorWatch()
         self._state = np.zeros(26, np.float32)
         self._solver.set_state(self._state)
         hover = torch.zeros(self.n_horizon, 11)
@@ -47,7 +48,8 @@ class MPPI:
 
     @property
     def u_prev(self) -> torch.Tensor:
-        return self._solver.u_prev
+        """Nominal sequence (warm start, not shifted).  A fresh clone: the solver's ping-pong buffers are reused."""
+        return self._solver.u_prev.clone()
 
     @u_prev.setter
     def u_prev(self, value):
@@ -58,11 +60,9 @@ class MPPI:
 
     def _sync_target(self):
         dt_ = self.drone_target
-        key = self.target_pose.version_key() + ((id(dt_), dt_._version) if isinstance(dt_, torch.Tensor) else (tuple(dt_),))
-        if key != self._target_sent:
+        if self._target_watch.changed(self.target_pose.pose, self.target_pose.orientation, dt_):
             tgt = self.target_pose.as_floats() + tuple(float(v) for v in torch.as_tensor(dt_).reshape(-1))
             self._solver.set_target(pos=tgt[:3], quat=tgt[3:7], drone_target=tgt[7:])
-            self._target_sent = key
 
     def compute_control_input(self, noise=None, noise_layout: str = "tkn"):
         """Returns (qdes[7], vdes[7], next_base_state[12]) as numpy arrays."""

@@ -96,10 +96,33 @@ class Pose:
         return p
 
     def version_key(self):
-        """Cheap change detector for the solver (tensor identity + in-place version counters)."""
-        return (id(self._pose), self._pose._version, id(self._orientation), self._orientation._version)
+        """(tensor, in-place version) pairs; compare with `TensorWatch`, which holds the tensors it last saw so that
+        CPython cannot hand a NEW tensor the address (and version 0) of the one that was uploaded."""
+        return (self._pose, self._pose._version, self._orientation, self._orientation._version)
 
     def as_floats(self):
         """(x, y, z, qx, qy, qz, qw) as Python floats -- what the solver uploads."""
         return tuple(float(v) for v in self._pose.detach().cpu().reshape(-1)) + \
             tuple(float(v) for v in self._orientation.detach().cpu().reshape(-1))
+
+
+class TensorWatch:
+    """Change detector for attributes the caller may re-assign or edit in place between steps (`target_pose.pose`,
+    `drone.target`): identity + torch's in-place version counter, with a STRONG reference to the tensor last seen --
+    an `id()`-based key can repeat when a freed tensor's address is reused, and the solver would then skip an upload
+    the reference (which re-reads its target every step, mppi.py:137, drone_mppi.py:141) never misses."""
+
+    def __init__(self):
+        self._seen = None
+
+    def changed(self, *values) -> bool:
+        cur = []
+        for v in values:
+            cur.append((v, v._version) if isinstance(v, torch.Tensor) else (None, tuple(float(x) for x in v)))
+        prev, self._seen = self._seen, cur
+        if prev is None or len(prev) != len(cur):
+            return True
+        for (a, av), (b, bv) in zip(prev, cur):
+            if a is not b or av != bv:
+                return True
+        return False

@@ -46,12 +46,18 @@ def _seat_arm(m, g):
 
 
 # ------------------------------------------------------------------ arm vs the reference's golden vectors
+# Both kernel layouts are held to the reference's vectors: "time_parallel" = one warp per sample, horizon steps on the
+# lanes (the default at these sizes), "thread_per_sample" = the rollout kernel + weighting kernel pair.
+LAYOUTS = [("time_parallel", 1), ("thread_per_sample", 0)]
+
+
+@pytest.mark.parametrize("layout,tp", LAYOUTS)
 @pytest.mark.parametrize("name", ["arm_K64_T32.npz", "arm_K48_T12_tilt.npz", "arm_K64_T32_f64state.npz",
                                   "arm_K1024_T30.npz"])
-def test_arm_against_reference_golden(name, oracle):
+def test_arm_against_reference_golden(name, layout, tp, oracle):
     g = load_golden(name)
     K, T = int(g["K"]), int(g["T"])
-    m = _arm(K, T)
+    m = _arm(K, T, time_parallel=tp)
     _seat_arm(m, g)
     for i in range(len(g["seeds"])):
         noise = fixture_noise(g, i, 7)
@@ -74,6 +80,7 @@ def test_arm_against_reference_golden(name, oracle):
         assert np.abs(qdes - g[f"qdes_{i}"]).max() < 2e-6
         assert np.abs(vdes - g[f"vdes_{i}"]).max() < 2e-5 * max(1.0, np.abs(g[f"vdes_{i}"]).max())
         assert abs(m.last_stats["rho"] - S.min()) == 0.0
+        assert m._solver.last_path == ("time_parallel" if tp else "two_kernels")
 
 
 @pytest.mark.parametrize("name", ["arm_K64_T32.npz", "arm_K1024_T30.npz"])
@@ -118,11 +125,12 @@ def test_arm_optional_cost_terms_against_reference_golden(label, terms, oracle):
 
 
 # ------------------------------------------------------------------ drone vs golden
+@pytest.mark.parametrize("layout,tp", LAYOUTS)
 @pytest.mark.parametrize("name", ["drone_K64_T32.npz", "drone_K1024_T30.npz"])
-def test_drone_against_reference_golden(name):
+def test_drone_against_reference_golden(name, layout, tp):
     g = load_golden(name)
     K, T = int(g["K"]), int(g["T"])
-    m = _drone(K, T)
+    m = _drone(K, T, time_parallel=tp)
     for i in range(len(g["seeds"])):
         noise = fixture_noise(g, i, 3)
         m.set_state(g["x0"] if i == 0 else g[f"x0_{i}"], g["v0"] if i == 0 else g[f"v0_{i}"])
@@ -133,6 +141,7 @@ def test_drone_against_reference_golden(name):
         assert np.abs(x.cpu().numpy() - g[f"x_{i}"]).max() < 1e-6
         assert np.abs(v.cpu().numpy() - g[f"v_{i}"]).max() < 1e-5
         assert m.stats()["ess"] == pytest.approx(1.0, abs=1e-3)          # weights collapse
+        assert m._solver.last_path == ("time_parallel" if tp else "two_kernels")
 
 
 # ------------------------------------------------------------------ unpinned models vs the oracle

@@ -28,16 +28,22 @@ def _one(res, *needles):
 
 def test_register_budgets_of_the_hot_kernels():
     res = _resources()
-    # fused rollout, Philox, baked FK: 4 blocks of 128 threads per SM need <= 128 registers; no stack (no spills, no local arrays)
-    for model in (1, 3):                                        # ARM7, WB11
-        regs, stack = _one(res, f"rollout_cost_kernelILi{model}ELi0ELb1ELb0E")
-        assert regs <= 128 and stack == 0
-    for model in (0, 2):                                        # DRONE3, QUAD4
-        regs, stack = _one(res, f"rollout_cost_kernelILi{model}ELi0ELb0ELb0E")
-        assert regs <= 128 and stack == 0
+    for rounds in (10, 7):                                      # Philox round count (MPPI_OPTION_PHILOX_ROUNDS)
+        # fused rollout, Philox, baked FK: 4 blocks of 128 threads per SM need <= 128 registers; no stack (no spills, no local arrays)
+        for model in (1, 3):                                    # ARM7, WB11
+            regs, stack = _one(res, f"rollout_cost_kernelILi{model}ELi0ELb1ELb0ELi{rounds}E")
+            assert regs <= 128 and stack == 0
+            # the single-launch step inherits the rollout's 4 blocks / SM (its co-residency limit is 592 blocks = 75776 samples)
+            assert _one(res, f"step_fused_kernelILi{model}ELb1ELb0ELi{rounds}E")[0] <= 128
+        for model in (0, 2):                                    # DRONE3, QUAD4
+            regs, stack = _one(res, f"rollout_cost_kernelILi{model}ELi0ELb0ELb0ELi{rounds}E")
+            assert regs <= 128 and stack == 0
+            assert _one(res, f"step_fused_kernelILi{model}ELb0ELb0ELi{rounds}E")[0] <= 128
+        # Philox weighting pass: blocks of up to 1024 threads
+        for model in range(4):
+            assert _one(res, f"weight_philox_kernelILi{model}ELi{rounds}E")[0] <= 64
+        # time-parallel warp-per-sample step, one horizon step per lane: >= 5 blocks of 128 threads per SM
+        assert _one(res, f"step_tp_kernelILi1ELi0ELb1ELi1ELi{rounds}E")[0] <= 96
     # streaming weighting pass: 3 blocks of 32*nu threads per SM
     assert _one(res, "weighted_noise_kernelILi3ELi4E")[0] <= 62          # nu = 11: 352 threads
     assert _one(res, "weighted_noise_kernelILi1ELi4E")[0] <= 97          # nu = 7: 224 threads
-    # Philox weighting pass: blocks of up to 1024 threads
-    for model in range(4):
-        assert _one(res, f"weight_philox_kernelILi{model}E")[0] <= 64

@@ -62,6 +62,9 @@ def main():
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "probe.json"))
     ap.add_argument("--reps", type=int, default=30)
     ap.add_argument("--only", default=None, help="comma-separated model filter")
+    ap.add_argument("--rounds", type=int, default=None)
+    ap.add_argument("--fused", type=int, default=None)
+    ap.add_argument("--tp", type=int, default=None)
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     stream = torch.cuda.current_stream(dev)
@@ -72,7 +75,8 @@ def main():
         qp = (14.7 + 5.5, 1 / 1.57, 1 / 3.93, 1 / 2.59, 0.0, -9.81) if model == "wb" else None
 
         def make(lam_):
-            s = NativeSolver(IDS[model], n_samples=K, n_horizon=T, seed=0, device=dev, quad_params=qp, lam=lam_)
+            s = NativeSolver(IDS[model], n_samples=K, n_horizon=T, seed=0, device=dev, quad_params=qp, lam=lam_,
+                             philox_rounds=a.rounds, fused=a.fused, time_parallel=a.tp)
             s.set_state(synthetic_state(model))
             s.u_prev = torch.from_numpy(nominal_controls(model, T))
             return s
@@ -102,7 +106,8 @@ def main():
             s.finalize()
         row = {"model": model, "K": K, "T": T, "lam": lam_v, "dense": lam == "dense", "step_ms": step_ms,
                "rollout_ms": float(np.median(t_r)), "weight_ms": float(np.median(t_w)),
-               "ess": float(o[_native.MPPI_OUT_ESS]), "nonzero_weights": nz}
+               "ess": float(o[_native.MPPI_OUT_ESS]), "nonzero_weights": nz, "path": s.last_path,
+               "rounds": s.get_option(_native.OPTION_PHILOX_ROUNDS)}
         rows.append(row)
         print(row, flush=True)
         s.close()
