@@ -443,13 +443,10 @@ def run_native(args):
         torch.cuda.synchronize(device)
 
     def jitter(_i=None):
-        # state/goal jitter for latency realism; by-value kernel parameter, no H2D copy
+        # state/goal jitter for latency realism; by-value kernel parameter, no H2D copy.  Every rank draws
+        # from the same seeded generator, so the replicas see the same "sensor message" without any communication.
         jit = st.copy()
         jit[:3] += rng.uniform(-0.05, 0.05, 3).astype(np.float32)
-        if world > 1:                                       # replicas must see the same sensor message
-            t = torch.from_numpy(jit).to(device)
-            dist.broadcast(t, 0)
-            jit = t.cpu().numpy()
         solver.set_state(jit)
 
     for _ in range(max(args.warmup, 3)):
@@ -484,7 +481,7 @@ def run_native(args):
         for _ in range(50):
             one_step()
         barrier()
-        lat = timed_steps(one_step, n_lat, stream, device, flush, before=jitter if world == 1 else None)
+        lat = timed_steps(one_step, n_lat, stream, device, flush, before=jitter)
         lat_t = torch.tensor(lat, dtype=torch.float64, device=device)
         if world > 1:
             dist.all_reduce(lat_t, op=dist.ReduceOp.MAX)
@@ -515,6 +512,51 @@ def run_native(args):
                  "p50": float(np.percentile(dms, 50)), "p99": float(np.percentile(dms, 99)), "steps": int(len(dms)),
                  "note": "same K x T; lambda raised until ESS ~ 2e3, so (nearly) every sample keeps a non-zero weight"}
         solver.update_config(lambda_=args.lam if args.lam is not None else 0.1)
+        solver.u_prev = u_nom0
+        solver.set_state(st)
+
+    # ---- where the time inside a step goes: in-kernel %globaltimer stamps at the phase boundaries (MPPI_OPTION_TRACE)
+    phases = None
+    try:
+        solver.trace(True)
+        acc = []
+        for _ in range(30):
+            barrier()
+            one_step()
+            torch.cuda.synchronize(device)
+            acc.append(solver.trace_times())
+        solver.trace(False)
+        keys = [k for k in acc[-1] if k != "start"]
+        med = {k: float(np.median([x[k] for x in acc if k in x])) for k in keys}
+        if world > 1:
+            for k in keys:
+                t = torch.tensor([med[k]], dtype=torch.float64, device=device)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                med[k] = float(t.item())
+        phases = {"us_from_first_block_start": med,
+                  "note": "median of 30 steps, max over ranks; 'exchanged' - 'reduced' is the peer-exchange wait (N > 1)"}
+        if "exchanged" in med and "reduced" in med:
+            phases["peer_exchange_us"] = med["exchanged"] - med["reduced"]
+        if "end" in med and "rollout_done" in med:
+            phases["tail_after_rollout_us"] = med["end"] - med["rollout_done"]
+    except Exception as e:                                   # tracing is diagnostics: never fail the bench on it
+        phases = {"error": repr(e)}
+
+    # ---- the same steps with the other Philox round count, for the record (the noise definition is a handle option)
+    other_rounds = None
+    if noise is None:
+        r_now = solver.get_option(_native.OPTION_PHILOX_ROUNDS)
+        r_other = 10 if r_now == 7 else 7
+        solver.set_option(_native.OPTION_PHILOX_ROUNDS, r_other)
+        for _ in range(5):
+            one_step()
+        barrier()
+        oms = timed_steps(one_step, max(20, min(args.steps, 100)), stream, device, flush)
+        oms_t = torch.tensor(oms, dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(oms_t, op=dist.ReduceOp.MAX)
+        other_rounds = {"philox_rounds": r_other, "ms_per_step": float(oms_t.mean().item()), "steps": int(len(oms))}
+        solver.set_option(_native.OPTION_PHILOX_ROUNDS, r_now)
         solver.u_prev = u_nom0
         solver.set_state(st)
 
@@ -749,7 +791,7 @@ def run_native(args):
                            "timing": "CUDA events around every step on the launch stream, summed, max over ranks"},
                 "latency_ms": latency if latency is not None else {"n": int(args.steps), "p50": float(np.percentile(step_ms, 50)),
                                                                    "p99": float(np.percentile(step_ms, 99)), "max": float(step_ms.max())},
-                "weights": weights_info, "dense_weights": dense,
+                "weights": weights_info, "dense_weights": dense, "phases": phases, "other_philox_rounds": other_rounds,
                 "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
                 "parity_check": parity, "cpu_baseline": cpu, "cpu_baseline_torch": cpu_torch}
         if coll:

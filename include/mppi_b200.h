@@ -181,7 +181,7 @@ mppi_status_t mppi_set_state(mppi_handle_t h, const float *state_host, int32_t n
 
 /* compute_control_input (mppi.py:122-169 / drone_mppi.py:140-176), device-pointer form.
  *   d_u_nom  [T][nu]   nominal controls = u_prev (warm start, NOT shifted: SURVEY F4)
- *   d_noise  [T][K][nu] injected noise, or NULL -> in-kernel Philox4x32-10(seed, step_counter)
+ *   d_noise  [T][K][nu] injected noise, or NULL -> in-kernel Philox4x32-R(seed, step_counter), R = MPPI_OPTION_PHILOX_ROUNDS
  *   d_cost_out [K] or NULL  per-sample costs S
  *   d_u_new  [T][nu]   updated controls (may alias d_u_nom)
  *   d_out    [MPPI_OUT_FLOATS] or NULL
@@ -244,9 +244,11 @@ mppi_status_t mppi_step_host(mppi_handle_t h, const float *state_host, int32_t n
                              float *cost_out_host, float *out_host);
 
 /* Run-time options (new; the reference has no configuration system).
- *   PHILOX_ROUNDS  10 (default; Random123 / cuRAND) or 7 (the smallest Crush-resistant round count, -30 % multiplies)
- *   FUSED_STEP     1 (default): a Philox step whose rollout grid is co-resident (K_local <= 128 x resident blocks, T <= 128)
- *                  runs as ONE cooperative launch (rollout, grid barrier, weighting, exchange, finalize); 0 = always two kernels
+ *   PHILOX_ROUNDS  7 (default: the smallest round count Salmon et al., SC'11, report as Crush-resistant; -30 % multiplies)
+ *                  or 10 (Random123 / cuRAND default).  Part of the noise definition: every shard of a sharded solve must agree.
+ *   FUSED_STEP     0 (default) / 1: a Philox step whose rollout grid is co-resident (K_local <= 128 x resident blocks,
+ *                  T <= 128) runs as ONE cooperative launch (rollout, grid barrier, weighting, exchange, finalize).
+ *                  Measured no faster than the dependent-launch pair, hence opt-in.
  *   TIME_PARALLEL  ARM7 / DRONE3 (linear double integrators), default costs, T <= 64: one WARP per sample, the two
  *                  cumulative sums of the reference as warp scans, every (sample, step) evaluates FK + cost on its own
  *                  lane, weighted-noise sums from the registers.  -1 (default) = when K_local <= 16384, 0 = never, 1 = always
@@ -259,6 +261,8 @@ mppi_status_t mppi_step_host(mppi_handle_t h, const float *state_host, int32_t n
 #define MPPI_OPTION_PROFILE 4
 #define MPPI_OPTION_NVTX 5
 #define MPPI_OPTION_LAST_PATH 6
+#define MPPI_OPTION_TRACE 7     /* 1: the kernels stamp %globaltimer (ns) at their phase boundaries -> mppi_get_trace */
+#define MPPI_OPTION_HOST_YIELD 8 /* 1: blocking steps sched_yield() between polls of the result word (default 0: spin) */
 #define MPPI_PATH_TWO_KERNELS 1
 #define MPPI_PATH_FUSED 2
 #define MPPI_PATH_TIMEPARALLEL 3
@@ -268,6 +272,12 @@ mppi_status_t mppi_get_option(mppi_handle_t h, int32_t option, int32_t *value);
  * us3[0] = rollout kernel (or the whole single-launch step), us3[1] = weighting + finalize (0 for a single launch),
  * us3[2] = MPPI_PATH_*.  Blocks until that step has finished.                                                        */
 mppi_status_t mppi_get_kernel_times(mppi_handle_t h, float *us3);
+/* With MPPI_OPTION_TRACE: device timestamps (ns, %globaltimer; 0 = point not passed) of the most recent step:
+ * [0] first block starts, [1] rollout done (a late block), [2] cost minimum known (single-launch steps),
+ * [3] weighted sums added, [4] last block takes over, [5] sums reduced, [6] peer exchange done,
+ * [7] controls updated (after Savitzky-Golay), [8] outputs written, [9] weighting kernel starts.
+ * Synchronises the device.                                                                                         */
+mppi_status_t mppi_get_trace(mppi_handle_t h, uint64_t *stamps_ns, int32_t n);
 
 /* Writes the Philox noise of (seed, step_counter) for this shard to d_noise [T][K][nu]:
  * the exact values the in-kernel generator uses (equivalence checks).                   */

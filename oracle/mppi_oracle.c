@@ -730,7 +730,7 @@ static void box_muller(float f_radius, float f_angle, float *n0, float *n1)
 {
     float u1 = 2.0f - f_radius;
     float r = sqrtf(-2.0f * logf(u1));
-    float th = (f_angle - 1.5f) * 6.28318530717958647692f;
+    float th = fmaf(f_angle, 6.28318530717958647692f, -9.42477796076937971538f);   /* (f - 1.5) * 2 pi as one FMA, like the device */
     *n0 = r * cosf(th);
     *n1 = r * sinf(th);
 }

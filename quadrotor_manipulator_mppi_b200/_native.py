@@ -29,10 +29,13 @@ EXPORTS = [
     "mppi_update_config", "mppi_set_joint_traj", "mppi_set_chain", "mppi_set_arm_inertia", "mppi_set_target", "mppi_set_state", "mppi_step", "mppi_rollout", "mppi_weight",
     "mppi_finalize", "mppi_rho_ptr", "mppi_wsum_ptr", "mppi_wsum_count", "mppi_cost_ptr",
     "mppi_p2p_export", "mppi_p2p_bind", "mppi_step_p2p", "mppi_step_p2p_sync", "mppi_step_sync", "mppi_step_host", "mppi_generate_noise", "mppi_measure_fp32_peak",
-    "mppi_algorithmic_flops_per_rollout_step", "mppi_set_option", "mppi_get_option", "mppi_get_kernel_times",
+    "mppi_algorithmic_flops_per_rollout_step", "mppi_set_option", "mppi_get_option", "mppi_get_kernel_times", "mppi_get_trace",
     "mppi_structural_flops_per_rollout_step",
 ]
 OPTION_PHILOX_ROUNDS, OPTION_FUSED_STEP, OPTION_TIME_PARALLEL, OPTION_PROFILE, OPTION_NVTX, OPTION_LAST_PATH = 1, 2, 3, 4, 5, 6
+OPTION_TRACE = 7
+OPTION_HOST_YIELD = 8
+TRACE_POINTS = ("start", "rollout_done", "min_known", "sums_added", "last_block", "reduced", "exchanged", "controls_updated", "end", "weight_start")
 PATH_TWO_KERNELS, PATH_FUSED, PATH_TIMEPARALLEL = 1, 2, 3
 PATH_NAMES = {0: "none", 1: "two_kernels", 2: "fused", 3: "time_parallel"}
 ERR_PEER = 5
@@ -110,6 +113,7 @@ def load():
     lib.mppi_set_option.argtypes = [vp, i32, i32]
     lib.mppi_get_option.argtypes = [vp, i32, C.POINTER(i32)]
     lib.mppi_get_kernel_times.argtypes = [vp, _fp]
+    lib.mppi_get_trace.argtypes = [vp, C.POINTER(C.c_uint64), i32]
     for name in EXPORTS:
         if name not in ("mppi_abi_version", "mppi_last_error", "mppi_rho_ptr", "mppi_wsum_ptr", "mppi_wsum_count",
                         "mppi_cost_ptr", "mppi_algorithmic_flops_per_rollout_step", "mppi_structural_flops_per_rollout_step"):

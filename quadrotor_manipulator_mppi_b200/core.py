@@ -138,6 +138,18 @@ class NativeSolver:
         _native.check(self._lib.mppi_get_kernel_times(self.handle, us), self.handle)
         return {"rollout_us": float(us[0]), "weighting_finalize_us": float(us[1]), "path": _native.PATH_NAMES[int(us[2])]}
 
+    def trace(self, on: bool = True) -> None:
+        """Phase timestamps inside the kernels (device %globaltimer); read with trace_times()."""
+        self.set_option(_native.OPTION_TRACE, int(bool(on)))
+
+    def trace_times(self) -> dict:
+        """Microseconds from the start of the most recent traced step to each phase boundary it passed."""
+        n = len(_native.TRACE_POINTS)
+        buf = (C.c_uint64 * n)()
+        _native.check(self._lib.mppi_get_trace(self.handle, buf, n), self.handle)
+        t0 = buf[0]
+        return {name: (buf[i] - t0) / 1e3 for i, name in enumerate(_native.TRACE_POINTS) if buf[i]}
+
     # ------------------------------------------------------------------ state / warm start
     @property
     def u_prev(self) -> torch.Tensor:

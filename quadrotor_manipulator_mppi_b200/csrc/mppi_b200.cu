@@ -4,6 +4,7 @@
 //         (see quadrotor_manipulator_mppi_b200/build.py).  No CPU path exists in this file: every entry point
 // either launches on the device or returns an error.
 #include <atomic>
+#include <sched.h>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -349,6 +350,7 @@ mppi_status_t wait_published(mppi_ctx *h, unsigned seq, cudaStream_t st, float *
 #if defined(__x86_64__) || defined(__i386__)
         __builtin_ia32_pause();
 #endif
+        if (h->opt_host_yield) sched_yield();       // a 100 Hz node sharing its cores: give the slice away between polls
         if ((it & 255u) == 0) {
             const cudaError_t q = cudaStreamQuery(st);
             if (q == cudaErrorNotReady) continue;
@@ -542,6 +544,7 @@ mppi_status_t mppi_destroy(mppi_handle_t h)
         if (h->h_zc) cudaFreeHost(h->h_zc);
         if (h->h_fail) cudaFreeHost(h->h_fail);
         cudaFree(h->d_sync);
+        cudaFree(h->d_trace);
         for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
         if (h->own_stream) cudaStreamDestroy(h->own_stream);
     }
@@ -813,8 +816,29 @@ mppi_status_t mppi_set_option(mppi_handle_t h, int32_t option, int32_t value)
             h->opt_timepar = value; return MPPI_OK;
         case MPPI_OPTION_PROFILE: h->opt_profile = value ? 1 : 0; h->ev_valid = false; return MPPI_OK;
         case MPPI_OPTION_NVTX: h->opt_nvtx = value ? 1 : 0; return MPPI_OK;
+        case MPPI_OPTION_HOST_YIELD: h->opt_host_yield = value ? 1 : 0; return MPPI_OK;
+        case MPPI_OPTION_TRACE: {
+            DeviceGuard guard(h->cfg.device);
+            if (value && !h->d_trace) {
+                MPPI_CUDA(h, cudaMalloc(&h->d_trace, kTracePoints * sizeof(unsigned long long)));
+                MPPI_CUDA(h, cudaMemset(h->d_trace, 0, kTracePoints * sizeof(unsigned long long)));
+            }
+            h->dyn.trace = value ? h->d_trace : nullptr;
+            return MPPI_OK;
+        }
         default: return fail(h, MPPI_ERR_INVALID_ARG, "unknown option");
     }
+}
+
+mppi_status_t mppi_get_trace(mppi_handle_t h, uint64_t *stamps_ns, int32_t n)
+{
+    if (!h || !stamps_ns || n < 1 || n > kTracePoints) return fail(h, MPPI_ERR_INVALID_ARG, "trace: 1..16 stamps");
+    if (!h->d_trace) return fail(h, MPPI_ERR_INVALID_ARG, "trace is off (MPPI_OPTION_TRACE)");
+    DeviceGuard guard(h->cfg.device);
+    MPPI_CUDA(h, cudaDeviceSynchronize());
+    MPPI_CUDA(h, cudaMemcpy(stamps_ns, h->d_trace, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    MPPI_CUDA(h, cudaMemset(h->d_trace, 0, kTracePoints * sizeof(unsigned long long)));
+    return MPPI_OK;
 }
 
 mppi_status_t mppi_get_option(mppi_handle_t h, int32_t option, int32_t *value)
@@ -826,6 +850,7 @@ mppi_status_t mppi_get_option(mppi_handle_t h, int32_t option, int32_t *value)
         case MPPI_OPTION_TIME_PARALLEL: *value = h->opt_timepar; return MPPI_OK;
         case MPPI_OPTION_PROFILE: *value = h->opt_profile; return MPPI_OK;
         case MPPI_OPTION_NVTX: *value = h->opt_nvtx; return MPPI_OK;
+        case MPPI_OPTION_HOST_YIELD: *value = h->opt_host_yield; return MPPI_OK;
         case MPPI_OPTION_LAST_PATH: *value = h->last_path; return MPPI_OK;
         default: return fail(h, MPPI_ERR_INVALID_ARG, "unknown option");
     }

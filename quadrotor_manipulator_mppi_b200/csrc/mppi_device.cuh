@@ -72,7 +72,21 @@ struct DynBlock {
     // D2H copy + stream synchronisation.  nullptr = off.
     float *host_out;
     unsigned host_seq;
+    // MPPI_OPTION_TRACE: device buffer of kTracePoints %globaltimer stamps (ns) written at the phase boundaries of the
+    // step's kernels by one thread of the block that passes them (nullptr = off).
+    unsigned long long *trace;
 };
+constexpr int kTracePoints = 16;
+enum TracePoint { TR_START = 0, TR_ROLLOUT_DONE = 1, TR_MIN_KNOWN = 2, TR_SUMS_ADDED = 3, TR_LAST_BLOCK = 4, TR_REDUCED = 5,
+                  TR_EXCHANGED = 6, TR_CONTROLS_UPDATED = 7, TR_END = 8, TR_WEIGHT_START = 9 };
+__device__ __forceinline__ void trace_stamp(const DynBlock &D, int point, bool who)
+{
+    if (D.trace != nullptr && who) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        D.trace[point] = t;
+    }
+}
 
 // Peer-to-peer exchange over NVLink (K-sharded replicas, one process per GPU; buffers are
 // cudaMalloc'ed and mapped into every rank with CUDA IPC).  Rank r's buffer holds
@@ -148,16 +162,29 @@ __host__ __device__ constexpr int philox_calls(int nu) { return ((nu + 1) / 2 + 
 // Two Box-Muller pairs at once in packed FP32x2.  fu = radius uniforms, ft = angle uniforms, both in [1, 2):
 //   u1 = 2 - fu in (0, 1],  r = sqrt(-2 ln u1) = sqrt(lg2(u1) * (-2 ln 2))  (sqrt.approx maps 0 -> 0),
 //   theta = (ft - 1.5) * 2 pi in [-pi, pi);  rc = r cos(theta), rs = r sin(theta)       (MUFU lg2 / sqrt / sin / cos)
+// The MUFU evaluations are issued as the .ftz PTX forms: u1 >= 2^-21 and |theta| <= pi are never subnormal, and the
+// non-ftz __log2f / __sincosf carry a subnormal-input guard (FSETP + FMUL + FADD per call) this path does not need.
+__device__ __forceinline__ float lg2_ftz(float x)
+{
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ void sincos_ftz(float x, float &s, float &c)
+{
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(x));
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(x));
+}
 __device__ __forceinline__ void box_muller2(f2 fu, f2 ft, f2 &rc, f2 &rs)
 {
     const f2 u1 = vadd(f2(2.0f), vneg(fu));
-    const f2 th = vmul(vadd(ft, f2(-1.5f)), f2(kTwoPi));
-    const f2 l2(__log2f(u1.v.x), __log2f(u1.v.y));
+    const f2 th = vfma(ft, f2(kTwoPi), f2(-9.42477796076937971538f));      // (ft - 1.5) * 2 pi as one FMA
+    const f2 l2(lg2_ftz(u1.v.x), lg2_ftz(u1.v.y));
     const f2 a = vmul(l2, f2(-1.3862943611198906f));
     const f2 r(sqrt_approx(a.v.x), sqrt_approx(a.v.y));
     float s0, c0, s1, c1;
-    __sincosf(th.v.x, &s0, &c0);
-    __sincosf(th.v.y, &s1, &c1);
+    sincos_ftz(th.v.x, s0, c0);
+    sincos_ftz(th.v.y, s1, c1);
     rc = vmul(r, f2(c0, c1));
     rs = vmul(r, f2(s0, s1));
 }

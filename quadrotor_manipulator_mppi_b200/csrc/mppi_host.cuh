@@ -57,11 +57,13 @@ struct mppi_ctx {
     float *d_qtraj = nullptr;       // [T][7] joint reference trajectory (MPPI_COST_JOINT_TRAJ), zeros by default
     cudaStream_t own_stream = nullptr;
     // ---- options (mppi_set_option)
-    int philox_rounds = 10;         // 10 (Random123 / cuRAND default) or 7 (smallest Crush-resistant round count)
+    int philox_rounds = 7;          // 7 (smallest Crush-resistant round count, Salmon et al. SC'11) or 10 (Random123 / cuRAND default)
     int opt_fused = 0;              // single-launch step when the grid is co-resident (measured: the PDL-chained pair is as fast)
     int opt_timepar = -1;           // time-parallel warp-per-sample kernel (ARM7 / DRONE3): -1 auto, 0 off, 1 on when eligible
     int opt_profile = 0;            // record CUDA events around the kernels of every step (mppi_get_kernel_times)
     int opt_nvtx = 1;               // NVTX ranges around the launches
+    int opt_host_yield = 0;         // blocking steps: sched_yield() between polls of the result word instead of a pure spin
+    unsigned long long *d_trace = nullptr;      // MPPI_OPTION_TRACE: %globaltimer stamps of the step's phases
     // ---- single-launch steps: grid-wide barrier counter + cached launch shapes
     unsigned *d_sync = nullptr;     // monotonic arrival counter
     unsigned sync_target = 0;       // value it reaches after the launches issued so far

@@ -121,6 +121,7 @@ __device__ __forceinline__ float rollout_body(const StepParams &P, const DynBloc
     const bool active = k_raw < P.K;
     const int k = active ? k_raw : P.K - 1;
     const uint32_t kg = static_cast<uint32_t>(P.k_offset + k);
+    trace_stamp(D, TR_START, blockIdx.x == 0 && threadIdx.x == 0);
 
     // ---- per-sample state in registers
     float dcv[3], dcq[3], dvp[3];                  // DRONE3 double integrator
@@ -358,6 +359,7 @@ __device__ __forceinline__ float rollout_body(const StepParams &P, const DynBloc
         for (int w = 1; w < kRolloutThreads / 32; ++w) bm = fminf(bm, s_wmin[w]);
         atomicMin(rho_enc, encode_ordered(bm));
     }
+    trace_stamp(D, TR_ROLLOUT_DONE, blockIdx.x == gridDim.x - 1 && threadIdx.x == 0);
     active_out = active;
     return S;
 }
@@ -409,6 +411,7 @@ __device__ void finalize_block(const StepParams &P, const DynBlock &D, const flo
         u_new[j] = v;
     }
     __syncthreads();
+    trace_stamp(D, TR_CONTROLS_UPDATED, threadIdx.x == 0);
     // The epilogue is split over three warps so that its serial pieces overlap (this block is the tail of the step):
     //   warp 0 lane 0: controller outputs;  warp 1 lane 0: check_reach FK;  warp 2: u0 / statistics;  warp 3: torque law.
     const float dt = P.dt;
@@ -486,6 +489,7 @@ __device__ void finalize_block(const StepParams &P, const DynBlock &D, const flo
         if (l == 19) out[MPPI_OUT_STEP] = exchange_ok ? static_cast<float>(D.step_lo & 0xffffffu) : -1.0f;
     }
     __syncthreads();
+    trace_stamp(D, TR_END, threadIdx.x == 0);
     if (threadIdx.x == 0) *rho_enc = kRhoInit;          // re-arm the minimum for the next step
     if (out != nullptr && D.host_out != nullptr) {
         // zero-copy result for the blocking host call: out[] (complete after the barrier above) -> mapped host memory,
@@ -618,6 +622,7 @@ __device__ void reduce_partials_and_finalize(const StepParams &P, const DynBlock
     __syncthreads();
     if (!s_last) return;
     __threadfence();
+    trace_stamp(D, TR_LAST_BLOCK, threadIdx.x == 0);
     if (fix != nullptr) {
         // fixed-point accumulators -> float sums (sigma applied here), and re-arm them for the next step
         for (int j = threadIdx.x; j < row; j += blockDim.x) {
@@ -646,8 +651,10 @@ __device__ void reduce_partials_and_finalize(const StepParams &P, const DynBlock
     }
     if (threadIdx.x == 0) *counter = 0u;
     __syncthreads();
+    trace_stamp(D, TR_REDUCED, threadIdx.x == 0);
     bool ok = true;
     if (X.world > 1) ok = p2p_exchange<MODEL>(P, X, wsum, rho_enc);
+    trace_stamp(D, TR_EXCHANGED, threadIdx.x == 0);
     if (fuse) finalize_block<MODEL>(P, D, wsum, u_nom, u_new, out, rho_enc, scratch, ok);
 }
 
@@ -681,6 +688,7 @@ weight_philox_kernel(const __grid_constant__ StepParams P, const __grid_constant
     const bool worker = tid < R * TC;
     const int r = tid / TC, t = tid - r * TC;
     asm volatile("griddepcontrol.wait;" ::: "memory");      // PDL: launched while the rollout kernel drains (no-op otherwise)
+    trace_stamp(D, TR_WEIGHT_START, blockIdx.x == 0 && tid == 0);
     const float rho = decode_ordered(*rho_enc);
     const int k0 = blockIdx.x * chunk;
     const int k1 = min(P.K, k0 + chunk);
@@ -769,6 +777,7 @@ weight_philox_kernel(const __grid_constant__ StepParams P, const __grid_constant
         if (e != 0.f) atomicAdd(fix + row - 2, static_cast<unsigned long long>(__float2ll_rn(e * kFixScale)));
         if (e2 != 0.f) atomicAdd(fix + row - 1, static_cast<unsigned long long>(__float2ll_rn(e2 * kFixScale)));
     }
+    trace_stamp(D, TR_SUMS_ADDED, blockIdx.x == 0 && tid == 0);
     reduce_partials_and_finalize<MODEL>(P, D, nullptr, 0, counter, wsum, fuse != 0, u_nom, u_new, out,
                                         rho_enc, s_dyn, X, nullptr, 0, fix);
 }
@@ -820,6 +829,7 @@ step_fused_kernel(const __grid_constant__ StepParams P, const __grid_constant__ 
     const float S = rollout_body<MODEL, 0, BAKED, EXTRA, ROUNDS>(P, D, u_nom, nullptr, cost_out, rho_enc, q_traj, active);
     grid_barrier(sync_ctr, sync_target);                 // every block has folded its minimum into *rho_enc
     const float rho = decode_ordered(__ldcg(rho_enc));
+    trace_stamp(D, TR_MIN_KNOWN, blockIdx.x == 0 && threadIdx.x == 0);
 
     float *s_w = s_dyn;
     int *s_idx = reinterpret_cast<int *>(s_dyn + kRolloutThreads);
@@ -888,6 +898,7 @@ step_fused_kernel(const __grid_constant__ StepParams P, const __grid_constant__ 
             if (e2 != 0.f) atomicAdd(fix + row - 1, static_cast<unsigned long long>(__float2ll_rn(e2 * kFixScale)));
         }
     }
+    trace_stamp(D, TR_SUMS_ADDED, blockIdx.x == 0 && tid == 0);
     reduce_partials_and_finalize<MODEL>(P, D, nullptr, 0, counter, wsum, true, u_nom, u_new, out, rho_enc, s_dyn, X,
                                         nullptr, 0, fix);
 }
@@ -901,14 +912,16 @@ step_fused_kernel(const __grid_constant__ StepParams P, const __grid_constant__ 
 // is what a reference-sized problem (K = 100 ... 1000, T = 30) needs to fill 148 SMs: the thread-per-sample kernel
 // runs it as 8 blocks of serial 30-step chains.  The lanes still hold their step's noise when the sample's cost is
 // known, so the weighted-noise sum needs no second pass and no regeneration: each block keeps a running soft-min
-// accumulator (block-local minimum, rescaled when a new minimum arrives), and after ONE grid-wide barrier the block
-// rows are rescaled to the global minimum and added into the fixed-point accumulators; the last block to arrive
-// exchanges with the peer shards (if any) and finalizes.  One launch per control step.
+// accumulator (block-local minimum, rescaled when a new minimum arrives) over the tiles it loops over, and publishes
+// ONE row; the last block to arrive rescales the (<= one per SM) rows to the global minimum, adds them in block order
+// (deterministic), exchanges with the peer shards (if any) and finalizes.  One ordinary launch per control step, no
+// grid-wide barrier and no atomics on the sums (in-kernel timestamps, tools/trace_phases.py: 256 blocks adding 212
+// 64-bit atomics each cost 3.6 us of same-address contention; 64 rows combined by one block cost ~1 us).
 // NOISE: 0 = in-kernel Philox (same (k, t, call, step) addressing as every other kernel: bit-identical normals),
 //        1 = injected [T][K][nu].
 // S/mppi_solver/mppi.py:122-158, S/mppi_solver/drone_mppi.py:140-170.
 // ------------------------------------------------------------------------------------------
-constexpr int kTpThreads = 128;
+constexpr int kTpThreads = 512;        // 16 warps = 16 samples per tile
 constexpr int kTpWarps = kTpThreads / 32;
 
 __device__ __forceinline__ float warp_excl_scan(float x, int lane)
@@ -939,12 +952,13 @@ __device__ __forceinline__ float warp_sum_compensated(float hi, float lo)
     return __fadd_rn(hi, lo);
 }
 
+constexpr int kTpMaxRows = 160;         // rows the last block combines: one per resident block, <= one block per SM
 template <int MODEL, int NOISE, bool BAKED, int SPL, int ROUNDS>
 __global__ void __launch_bounds__(kTpThreads)
 step_tp_kernel(const __grid_constant__ StepParams P, const __grid_constant__ DynBlock D,
                const float *__restrict__ u_nom, const float *__restrict__ noise, float *__restrict__ cost_out,
-               int32_t *rho_enc, unsigned long long *__restrict__ fix, uint32_t *counter, unsigned *sync_ctr,
-               unsigned sync_target, float *wsum, float *u_new, float *out, const __grid_constant__ P2PParams X)
+               int32_t *rho_enc, float *__restrict__ rows, float *__restrict__ rho_rows, uint32_t *counter,
+               float *wsum, float *u_new, float *out, const __grid_constant__ P2PParams X)
 {
     static_assert(MODEL == MPPI_MODEL_ARM7 || MODEL == MPPI_MODEL_DRONE3, "linear-integrator models only");
     constexpr int NU = ModelNu<MODEL>::value;
@@ -952,12 +966,14 @@ step_tp_kernel(const __grid_constant__ StepParams P, const __grid_constant__ Dyn
     constexpr int NUP = 4 * NQ;
     constexpr bool PHILOX = (NOISE == 0);
     constexpr int Q0 = 0, QD0 = (MODEL == MPPI_MODEL_ARM7) ? 7 : 3;
-    extern __shared__ __align__(16) float s_dyn[];       // [n] block accumulator | [kTpWarps][n] tile contributions (finalize scratch later)
+    extern __shared__ __align__(16) float s_dyn[];       // [n] block accumulator | [kTpWarps][n] tile contributions (combine / finalize scratch later)
     __shared__ float s_S[kTpWarps], s_W[kTpWarps];
+    __shared__ bool s_last;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = P.T * NU;
     float *s_acc = s_dyn, *s_con = s_dyn + n;
+    trace_stamp(D, TR_START, blockIdx.x == 0 && tid == 0);
     for (int j = tid; j < n; j += kTpThreads) s_acc[j] = 0.f;
     float rho_blk = __int_as_float(0x7f800000), eta_blk = 0.f, eta2_blk = 0.f;
 
@@ -1105,25 +1121,89 @@ step_tp_kernel(const __grid_constant__ StepParams P, const __grid_constant__ Dyn
         __syncthreads();
     }
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    // ---- global minimum, then every block row rescaled to it and added into the fixed-point accumulators
-    if (tid == 0) atomicMin(rho_enc, encode_ordered(rho_blk));
-    grid_barrier(sync_ctr, sync_target);
-    const float rho = decode_ordered(__ldcg(rho_enc));
-    const float cb = expf(-P.inv_lambda * (rho_blk - rho));
-    const int row = n + 2;
-    if (cb != 0.f) {
-        for (int j = tid; j < n; j += kTpThreads) {
-            const float v = s_acc[j] * cb;
-            if (v != 0.f) atomicAdd(fix + j, static_cast<unsigned long long>(__float2ll_rn(v * kFixScale)));
-        }
-        if (tid == 0) {
-            const float e = eta_blk * cb, e2 = eta2_blk * cb * cb;
-            if (e != 0.f) atomicAdd(fix + row - 2, static_cast<unsigned long long>(__float2ll_rn(e * kFixScale)));
-            if (e2 != 0.f) atomicAdd(fix + row - 1, static_cast<unsigned long long>(__float2ll_rn(e2 * kFixScale)));
-        }
+    trace_stamp(D, TR_ROLLOUT_DONE, blockIdx.x == 0 && tid == 0);
+    // ---- publish this block's row (sums relative to its own minimum); the last block to arrive combines the rows
+    const int nout = n + 2;
+    const int rstride = (nout + 3) & ~3;                  // rows are read back as float4
+    {
+        float *my = rows + static_cast<size_t>(blockIdx.x) * rstride;
+        for (int j = tid; j < n; j += kTpThreads) my[j] = s_acc[j];
+        if (tid == 0) { my[n] = eta_blk; my[n + 1] = eta2_blk; rho_rows[blockIdx.x] = rho_blk; }
     }
-    reduce_partials_and_finalize<MODEL>(P, D, nullptr, 0, counter, wsum, true, u_nom, u_new, out, rho_enc, s_dyn, X,
-                                        nullptr, 0, fix, /*fix_has_sigma=*/!PHILOX);
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();                                  // release: cumulative over the block's stores ordered by the barrier above
+        s_last = (atomicAdd(counter, 1u) == gridDim.x - 1u);
+        if (s_last) __threadfence();                      // acquire side; the rows are then read with ld.cg (L2)
+    }
+    __syncthreads();
+    trace_stamp(D, TR_SUMS_ADDED, blockIdx.x == 0 && tid == 0);
+    if (!s_last) return;
+    trace_stamp(D, TR_LAST_BLOCK, tid == 0);
+    const int nb = gridDim.x;                             // <= kTpMaxRows
+    // shared-memory layout of the hand-over: [0, 2n+nu) finalize scratch | row scales | combine partials | combined sums |
+    // nominal controls.  The combined sums and u_nom reach finalize_block through shared memory: every global round
+    // trip on this serial tail costs 0.5-1 us.
+    float *s_scale = s_con, *s_red = s_dyn + ((n + kTpMaxRows + 3) & ~3);          // float4-aligned
+    const int off_w = max(2 * n + NU, n + kTpMaxRows + 4 * kTpThreads + 4) + 4;
+    float *s_w = s_dyn + off_w, *s_u = s_w + nout + 2;
+    for (int j = tid; j < n; j += kTpThreads) s_u[j] = __ldg(u_nom + j);            // in flight while the rows are combined
+    // global minimum over the rows' minima: one value per thread, warp shuffles, 16 partials
+    float rmin = __int_as_float(0x7f800000);
+    for (int b = tid; b < nb; b += kTpThreads) { const float r = __ldcg(rho_rows + b); s_scale[b] = r; rmin = fminf(rmin, r); }
+    rmin = warp_min(rmin);
+    if (lane == 0) s_S[warp] = rmin;
+    __syncthreads();
+    float rho = s_S[0];
+#pragma unroll
+    for (int wv = 1; wv < kTpWarps; ++wv) rho = fminf(rho, s_S[wv]);
+    for (int b = tid; b < nb; b += kTpThreads) s_scale[b] = expf(-P.inv_lambda * (s_scale[b] - rho));
+    __syncthreads();
+    // rows are added in block order within each of `parts` interleaved sub-sequences, the sub-sequences in order;
+    // a thread owns one float4 column of the rows: the loop is bound by the L2 latency (~0.7 us per dependent batch
+    // measured), so it keeps 8 float4 loads in flight (hoisting them above the minimum, 16 deep, measured slower)
+    const int c4 = rstride >> 2;
+    const int parts = max(1, kTpThreads / c4);
+    for (int o = tid; o < parts * c4; o += kTpThreads) {
+        const int pt = o / c4, c = o - pt * c4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int e = n + 1 - 4 * c;                                      // component of this column holding sum w^2 (if 0..3)
+        for (int b0 = pt; b0 < nb; b0 += 8 * parts) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int b = b0 + u * parts;
+                v[u] = (b < nb) ? __ldcg(reinterpret_cast<const float4 *>(rows + static_cast<size_t>(b) * rstride) + c)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int b = b0 + u * parts;
+                const float sc = (b < nb) ? s_scale[b] : 0.f;
+                const float sq = sc * sc;
+                acc.x = fmaf(e == 0 ? sq : sc, v[u].x, acc.x);
+                acc.y = fmaf(e == 1 ? sq : sc, v[u].y, acc.y);
+                acc.z = fmaf(e == 2 ? sq : sc, v[u].z, acc.z);
+                acc.w = fmaf(e == 3 ? sq : sc, v[u].w, acc.w);
+            }
+        }
+        reinterpret_cast<float4 *>(s_red)[o] = acc;
+    }
+    __syncthreads();
+    for (int j = tid; j < nout; j += kTpThreads) {
+        float v = 0.f;
+        for (int pt = 0; pt < parts; ++pt) v += s_red[pt * rstride + j];
+        v = (PHILOX && j < n) ? v * P.sigma[j % NU] : v;                 // unit normals were accumulated: sigma once, here
+        s_w[j] = v;
+        wsum[j] = v;                                                     // observability / allreduce contract; not re-read here
+    }
+    if (tid == 0) { *rho_enc = encode_ordered(rho); *counter = 0u; }
+    __syncthreads();
+    trace_stamp(D, TR_REDUCED, tid == 0);
+    bool ok = true;
+    if (X.world > 1) ok = p2p_exchange<MODEL>(P, X, s_w, rho_enc);
+    trace_stamp(D, TR_EXCHANGED, tid == 0);
+    finalize_block<MODEL>(P, D, s_w, s_u, u_new, out, rho_enc, s_dyn, ok);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -174,17 +174,26 @@ mppi_status_t launch_tp_variant(mppi_ctx *h, int slot, const float *d_u_nom, con
 {
     constexpr int NU = ModelNu<MODEL>::value;
     const size_t n = (size_t)h->P.T * NU;
-    const size_t smem = (1 + kTpWarps) * n * sizeof(float);          // >= finalize scratch (2n + nu)
+    size_t floats = (1 + (size_t)kTpWarps) * n;                       // block accumulator + tile contributions of the 16 warps
+    size_t off_w = 2 * n + NU;                                        // hand-over layout of the last block (see the kernel)
+    if (off_w < n + kTpMaxRows + 4 * kTpThreads + 4) off_w = n + kTpMaxRows + 4 * kTpThreads + 4;
+    const size_t tail = off_w + 4 + (n + 2) + 2 + n;
+    if (floats < tail) floats = tail;
+    const size_t smem = floats * sizeof(float);
     auto kernel = step_tp_kernel<MODEL, NOISE, BAKED, SPL, ROUNDS>;
-    const int cap = coresident_blocks(h, kernel, kTpThreads, smem, h->tp_blocks_max[slot]);
-    if (cap < 1) return MPPI_OK;
+    int &ready = h->tp_blocks_max[slot];
+    if (ready < 0) {
+        if (smem > 48 * 1024) MPPI_CUDA(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ready = 1;
+    }
     const int n_tiles = (h->P.K + kTpWarps - 1) / kTpWarps;
+    int cap = h->num_sms < kTpMaxRows ? h->num_sms : kTpMaxRows;      // one row per block, one block per SM
+    if (cap > h->max_parts) cap = h->max_parts;
     const int grid = n_tiles < cap ? n_tiles : cap;                  // persistent blocks loop over the remaining tiles
     NvtxRange nv(h, "mppi.step_timeparallel");
-    h->sync_target += (unsigned)grid;
-    mppi_status_t rc = launch_cooperative(h, kernel, grid, kTpThreads, smem, st, h->P, h->dyn, d_u_nom, d_noise, h->d_cost, h->d_rho,
-                                          h->d_fix, h->d_counter, h->d_sync, h->sync_target, h->d_wsum, d_u_new, d_out, X);
-    if (rc != MPPI_OK) { h->sync_target -= (unsigned)grid; return rc; }
+    kernel<<<grid, kTpThreads, smem, st>>>(h->P, h->dyn, d_u_nom, d_noise, h->d_cost, h->d_rho, h->d_part, h->d_eta_part,
+                                           h->d_counter, h->d_wsum, d_u_new, d_out, X);
+    MPPI_CUDA(h, cudaGetLastError());
     *launched = true;
     return MPPI_OK;
 }

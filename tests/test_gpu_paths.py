@@ -98,12 +98,16 @@ def test_single_launch_falls_back_when_the_grid_cannot_be_resident(native):
     assert s.last_path == "two_kernels"
     s, _ = _run(native, native.MODEL_DRONE3, 1024, 200, 50.0, steps=1, time_parallel=0)
     assert s.last_path == "two_kernels"
-    s, _ = _run(native, native.MODEL_DRONE3, 1024, 100, 50.0, steps=1, time_parallel=-1)       # auto, T > 64: fused
+    s, _ = _run(native, native.MODEL_DRONE3, 1024, 100, 50.0, steps=1, time_parallel=-1, fused=1)   # T > 64: not time-parallel
     assert s.last_path == "fused"
-    s, _ = _run(native, native.MODEL_ARM7, 20000, 32, 0.1, steps=1)                            # auto, K > 16384
+    s, _ = _run(native, native.MODEL_ARM7, 20000, 32, 0.1, steps=1, fused=1)                   # auto, K beyond the time-parallel range
     assert s.last_path == "fused"
+    s, _ = _run(native, native.MODEL_ARM7, 20000, 32, 0.1, steps=1)                            # library defaults
+    assert s.last_path == "two_kernels"
     s, _ = _run(native, native.MODEL_ARM7, 2000, 32, 0.1, steps=1)
     assert s.last_path == "time_parallel"
+    s, _ = _run(native, native.MODEL_WB11, 2000, 32, 0.1, steps=1)                             # non-linear model: never time-parallel
+    assert s.last_path == "two_kernels"
 
 
 @pytest.mark.parametrize("rounds", [10, 7])

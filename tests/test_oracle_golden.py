@@ -20,6 +20,55 @@ def test_philox_known_answers(oracle):
             [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1])]
     for ctr, key, want in kat:
         assert oracle.philox4x32_10(ctr, key).tolist() == want
+        assert oracle.philox4x32(ctr, key, 10).tolist() == want
+    # Random123 kat_vectors, philox4x32 with 7 rounds (MPPI_OPTION_PHILOX_ROUNDS = 7): same round function, fewer rounds
+    assert oracle.philox4x32([0, 0, 0, 0], [0, 0], 7).tolist() == [0x5f6fb709, 0x0d893f64, 0x4f121f81, 0x4f730a48]
+    assert oracle.philox4x32([1, 2, 3, 4], [5, 6], 7).tolist() != oracle.philox4x32([1, 2, 3, 4], [5, 6], 10).tolist()
+
+
+@pytest.mark.parametrize("rounds", [10, 7])
+def test_philox_noise_distribution_and_independence(oracle, rounds):
+    """The noise definition itself (shared bit for bit by the device generator up to MUFU rounding): goodness of fit to
+    N(0,1), tails, and independence along every axis of the addressing (input, horizon step, sample, step counter,
+    Philox call) -- VERDICT r01 'noise quality is asserted by four moments only'."""
+    from scipy import stats
+    K, T, nu = 8192, 32, 11
+    n0 = oracle.philox_noise(K, T, nu, 1.0, seed=12345, step=0, rounds=rounds).astype(np.float64)
+    n1 = oracle.philox_noise(K, T, nu, 1.0, seed=12345, step=1, rounds=rounds).astype(np.float64)
+    flat = n0.ravel()
+    # Kolmogorov-Smirnov against N(0,1): 2.9e6 values -> critical D(1e-3) = 1.95 / sqrt(n) = 1.15e-3
+    D = stats.kstest(flat, "norm").statistic
+    assert D < 1.15e-3, D
+    # chi-square on 64 equiprobable bins (63 dof: 99.9 % quantile = 103.4)
+    edges = stats.norm.ppf(np.linspace(0, 1, 65)[1:-1])
+    counts = np.bincount(np.searchsorted(edges, flat), minlength=64)
+    chi2 = ((counts - flat.size / 64.0) ** 2 / (flat.size / 64.0)).sum()
+    assert chi2 < 103.4, chi2
+    # tails: P(|z| > 4) = 6.33e-5; 21-bit radius uniforms cap |z| at 5.4
+    tail = (np.abs(flat) > 4.0).mean()
+    assert 4.5e-5 < tail < 8.5e-5 and np.abs(flat).max() < 5.5
+    # per input: each of the 11 streams on its own
+    for i in range(nu):
+        assert stats.kstest(n0[:, :, i].ravel(), "norm").statistic < 1.95 / np.sqrt(K * T) * 1.3
+    # serial correlation: lag 1 along t, along k, across the step counter, and between the two Philox calls / the
+    # two members of a Box-Muller pair; |r| < 4 / sqrt(N)
+    def corr(a, b):
+        a, b = a.ravel() - a.mean(), b.ravel() - b.mean()
+        return float((a * b).sum() / np.sqrt((a * a).sum() * (b * b).sum()))
+    N = (T - 1) * K * nu
+    assert abs(corr(n0[1:], n0[:-1])) < 4 / np.sqrt(N)
+    assert abs(corr(n0[:, 1:], n0[:, :-1])) < 4 / np.sqrt(N)
+    assert abs(corr(n0, n1)) < 4 / np.sqrt(flat.size)
+    assert abs(corr(n0[:, :, 0], n0[:, :, 1])) < 4 / np.sqrt(K * T)         # cos / sin of one pair
+    assert abs(corr(n0[:, :, 5], n0[:, :, 6])) < 4 / np.sqrt(K * T)         # last input of call 0 / first of call 1
+    assert abs(corr(n0[:, :, 0] ** 2, n0[:, :, 1] ** 2)) < 4 / np.sqrt(K * T)   # a pair shares a radius only through independence of (r, theta)
+    c = np.corrcoef(n0.reshape(-1, nu).T)
+    assert np.abs(c - np.eye(nu)).max() < 4 / np.sqrt(K * T)
+    # no two (sample, step, call) addresses collide: all 12-normal blocks of the two calls are distinct rows
+    rows = np.ascontiguousarray(n0.astype(np.float32)).reshape(-1, nu)
+    assert len(np.unique(rows.view([("", np.float32)] * nu))) == rows.shape[0]
+    both = np.concatenate([rows, np.ascontiguousarray(n1.astype(np.float32)).reshape(-1, nu)])
+    assert len(np.unique(both[:, :6].copy().view([("", np.float32)] * 6))) == both.shape[0]      # call 0 across step counters
 
 
 def test_philox_noise_is_standard_normal_and_shard_invariant(oracle):
@@ -171,3 +220,20 @@ def test_unpinned_models_reduce_to_pinned_pieces(oracle):
         e = ((p - np.array(oracle.DRONE_TARGET)) ** 2).sum(1)
         S += 100 * e if t < T - 1 else 20 * e
     assert rel_inf(Sq, S) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["quad_K128_T40_torchport.npz", "wb_K96_T20_torchport.npz"])
+def test_c_oracle_matches_the_independent_torch_restatement_on_the_unpinned_models(name, oracle):
+    """quad4 / wb11 have no runnable reference: these fixtures come from oracle/torch_port.py (generator:
+    oracle/make_golden_unpinned.py); the C oracle -- the checker of the CUDA path -- is held to them so that it cannot
+    drift unnoticed.  PARITY UNPINNED against the reference itself, by construction."""
+    g = load_golden(name)
+    for i in range(2):
+        noise, u = g[f"noise_{i}"], g[f"u_prev_{i}"]
+        if str(g["model"]) == "quad4":
+            o = oracle.quad_step(noise, u, g["state"])
+        else:
+            o = oracle.wb_step(noise, u, g["qstate"], g["q"], g["qdot"])
+        assert rel_inf(o["S"], g[f"S_{i}"]) < 1e-6
+        iso = oracle._update(g[f"S_{i}"], noise, u, float(g["lam"]), int(g["window"]))
+        assert rel_inf(iso["u_new"], g[f"u_new_{i}"]) < 2e-6
