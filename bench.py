@@ -486,9 +486,19 @@ def run_native(args):
         if world > 1:
             dist.all_reduce(lat_t, op=dist.ReduceOp.MAX)
         lat = lat_t.cpu().numpy()
+        if world > 1:
+            # every one of the n_lat + warm-up steps went through the exchange and u_prev carries over from step to step:
+            # a single stale or torn row in any step would leave the replicas' control sequences different for good
+            u_now = solver.u_prev.clone()
+            gu_ = [torch.empty_like(u_now) for _ in range(world)]
+            dist.all_gather(gu_, u_now)
+            replicas_identical_after_loop = bool(all(torch.equal(gu_[0], g) for g in gu_)) and bool(torch.isfinite(u_now).all())
         latency = {"n": int(n_lat), "warmup": 50, "p50": float(np.percentile(lat, 50)), "p90": float(np.percentile(lat, 90)),
                    "p99": float(np.percentile(lat, 99)), "max": float(lat.max()), "mean": float(lat.mean()),
                    "host_wall_ms_per_step_incl_flush": wall / args.steps * 1e3}
+
+    if latency is not None and world > 1:
+        latency["replicas_bit_identical_after_these_steps"] = replicas_identical_after_loop
 
     # ---- the same K x T with weights that do NOT collapse (ESS >= 1e3): the weighting pass regenerates all of the noise
     dense = None
@@ -596,6 +606,8 @@ def run_native(args):
 
         # ---- parity self-check (outside every timed region): N ranks == 1 rank, both exchanges
         checks = {}
+        if latency is not None:
+            checks["replicas_bit_identical_after_latency_loop"] = replicas_identical_after_loop
         # (a) no peer-exchange timeout during the timed steps: blocking step raises on the sticky failure word
         try:
             o_blk = stepper.step(noise, state=st)
@@ -603,46 +615,56 @@ def run_native(args):
         except _native.MppiError as e:
             checks["exchange_timeouts"] = 1
             checks["exchange_error"] = str(e)
-        # (b) one step from identical inputs through p2p, NCCL and (rank 0) a single full-K solver
+        # (b) one step from identical inputs through p2p, NCCL and (rank 0) a single full-K solver -- with the reference's
+        # lambda (weights may collapse to one sample: then the update is that sample's noise whatever the exchange does)
+        # AND with the dense-weights lambda (every shard contributes to every entry of the sums)
         SC = 1000003
-        res = {}
-        for name, stp, slv in (("used", stepper, solver), ("nccl", stepper_n, solver_n)):
-            slv.set_state(st)
-            slv.u_prev = u_nom0
-            slv.step_counter = SC
-            o = stp.step(noise, state=st)
-            res[name] = (slv.u_prev.clone(), torch.from_numpy(np.array(o, copy=True)).to(device), slv.costs.clone())
-        u_used, o_used, S_used = res["used"]
-        u_nccl, o_nccl, _ = res["nccl"]
-        gu = [torch.empty_like(u_used) for _ in range(world)]
-        go = [torch.empty_like(o_used) for _ in range(world)]
-        dist.all_gather(gu, u_used)
-        dist.all_gather(go, o_used)
-        checks["ranks_bit_identical_u_new"] = bool(all(torch.equal(gu[0], g) for g in gu))
-        checks["ranks_bit_identical_out"] = bool(all(torch.equal(go[0], g) for g in go))
-        checks["out_step_nonnegative"] = bool(all(float(g[_native.MPPI_OUT_STEP]) >= 0 for g in go))
-        un = u_nccl.double()
-        checks["p2p_vs_nccl_u_new_rel"] = float(((u_used.double() - un).abs().max() / un.abs().max().clamp_min(1e-30)).item())
-        # costs of every shard -> rank 0 (ragged shards: pad to the largest)
-        kmax = (K + world - 1) // world
-        pad = torch.full((kmax,), float("nan"), device=device)
-        pad[:K_loc] = S_used
-        gs = [torch.empty_like(pad) for _ in range(world)]
-        dist.all_gather(gs, pad)
-        if rank == 0:
-            full = make_solver(k_local=K, k_offset=0)
-            full.set_state(st)
-            full.u_prev = u_nom0
-            full.step(noise if noise is None else None, step_counter=SC)
-            S_all = torch.cat([gs[r][:shard_range(K, world, r)[1]] for r in range(world)])
-            checks["sharded_costs_bitwise_equal_single_rank"] = bool(torch.equal(S_all, full.costs))
-            uf = full.u_prev.double()
-            checks["sharded_vs_single_rank_u_new_rel"] = float(((u_used.double() - uf).abs().max() / uf.abs().max().clamp_min(1e-30)).item())
-            full.close()
-        ok_local = (checks["exchange_timeouts"] == 0 and checks["ranks_bit_identical_u_new"] and checks["ranks_bit_identical_out"]
-                    and checks["out_step_nonnegative"] and checks["p2p_vs_nccl_u_new_rel"] <= 1e-6
-                    and checks.get("sharded_costs_bitwise_equal_single_rank", True)
-                    and checks.get("sharded_vs_single_rank_u_new_rel", 0.0) <= 1e-5)
+        lam_ref = args.lam if args.lam is not None else 0.1
+        lam_dense = dense["lambda"] if dense else 50.0
+        ok_local = checks["exchange_timeouts"] == 0 and checks.get("replicas_bit_identical_after_latency_loop", True)
+        for tag, lam_c in (("", lam_ref), ("dense_", lam_dense)):
+            res = {}
+            for name, stp, slv in (("used", stepper, solver), ("nccl", stepper_n, solver_n)):
+                slv.update_config(lambda_=lam_c)
+                slv.set_state(st)
+                slv.u_prev = u_nom0
+                slv.step_counter = SC
+                o = stp.step(noise, state=st)
+                res[name] = (slv.u_prev.clone(), torch.from_numpy(np.array(o, copy=True)).to(device), slv.costs.clone())
+            u_used, o_used, S_used = res["used"]
+            u_nccl, o_nccl, _ = res["nccl"]
+            gu = [torch.empty_like(u_used) for _ in range(world)]
+            go = [torch.empty_like(o_used) for _ in range(world)]
+            dist.all_gather(gu, u_used)
+            dist.all_gather(go, o_used)
+            checks[tag + "ranks_bit_identical_u_new"] = bool(all(torch.equal(gu[0], g) for g in gu))
+            checks[tag + "ranks_bit_identical_out"] = bool(all(torch.equal(go[0], g) for g in go))
+            checks[tag + "out_step_nonnegative"] = bool(all(float(g[_native.MPPI_OUT_STEP]) >= 0 for g in go))
+            checks[tag + "ess"] = float(go[0][_native.MPPI_OUT_ESS])
+            un = u_nccl.double()
+            checks[tag + "p2p_vs_nccl_u_new_rel"] = float(((u_used.double() - un).abs().max() / un.abs().max().clamp_min(1e-30)).item())
+            # costs of every shard -> rank 0 (ragged shards: pad to the largest)
+            kmax = (K + world - 1) // world
+            pad = torch.full((kmax,), float("nan"), device=device)
+            pad[:K_loc] = S_used
+            gs = [torch.empty_like(pad) for _ in range(world)]
+            dist.all_gather(gs, pad)
+            if rank == 0:
+                full = make_solver(k_local=K, k_offset=0, lam=lam_c)
+                full.set_state(st)
+                full.u_prev = u_nom0
+                full.step(None, step_counter=SC)
+                S_all = torch.cat([gs[r][:shard_range(K, world, r)[1]] for r in range(world)])
+                checks[tag + "sharded_costs_bitwise_equal_single_rank"] = bool(torch.equal(S_all, full.costs))
+                uf = full.u_prev.double()
+                checks[tag + "sharded_vs_single_rank_u_new_rel"] = float(((u_used.double() - uf).abs().max() / uf.abs().max().clamp_min(1e-30)).item())
+                full.close()
+            ok_local = (ok_local and checks[tag + "ranks_bit_identical_u_new"] and checks[tag + "ranks_bit_identical_out"]
+                        and checks[tag + "out_step_nonnegative"] and checks[tag + "p2p_vs_nccl_u_new_rel"] <= 1e-6
+                        and checks.get(tag + "sharded_costs_bitwise_equal_single_rank", True)
+                        and checks.get(tag + "sharded_vs_single_rank_u_new_rel", 0.0) <= 1e-5)
+        for slv in (solver, solver_n):
+            slv.update_config(lambda_=lam_ref)
         okt = torch.tensor([1 if ok_local else 0], dtype=torch.int32, device=device)
         dist.all_reduce(okt, op=dist.ReduceOp.MIN)
         checks["ok"] = bool(int(okt.item()) == 1)

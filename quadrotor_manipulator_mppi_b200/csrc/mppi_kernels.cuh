@@ -544,50 +544,56 @@ template <int MODEL>
 __device__ bool p2p_exchange(const StepParams &P, const P2PParams &X, float *wsum, int32_t *rho_enc)
 {
     constexpr int NU = ModelNu<MODEL>::value;
-    __shared__ float s_scale[kMaxRanks];
+    __shared__ float s_scale[kMaxRanks], s_rho[kMaxRanks];
     __shared__ int s_ok;
     const int row = P.T * NU + 2;
     const int parity = static_cast<int>(X.epoch & 1u);
     const int tid = threadIdx.x;
     if (tid == 0) s_ok = 1;
-    // ---- publish (own slot included, so the combine loop is uniform)
+    // ---- publish (own slot included, so the combine loop is uniform): plain stores into every peer's inbox ...
+    const float my_rho = __int_as_float(*rho_enc);
     for (int dst = 0; dst < X.world; ++dst) {
         float *slot = p2p_inbox(X.base[dst], X.world, X.rowp, parity, X.rank);
         for (int j = tid; j < row; j += blockDim.x) slot[j] = wsum[j];
-        if (tid == 0) slot[row] = __int_as_float(*rho_enc);
+        if (tid == 0) slot[row] = my_rho;
     }
-    __threadfence_system();
+    // ... ordered before the flags by the block barrier + ONE system-scope release per peer (release is cumulative over
+    // the stores the barrier made visible to the releasing thread; a separate all-thread __threadfence_system() before
+    // it costs a second NVLink round trip)
     __syncthreads();
     if (tid < X.world) st_release_sys(p2p_flags(X.base[tid]) + X.rank * kFlagStrideInts, static_cast<int>(X.epoch));
-    // ---- wait for every source
+    // ---- wait for every source; the thread that acquired source r's flag also fetches r's cost minimum
+    float *mine = X.base[X.rank];
     if (tid < X.world) {
-        const int *flag = p2p_flags(X.base[X.rank]) + tid * kFlagStrideInts;
+        const int *flag = p2p_flags(mine) + tid * kFlagStrideInts;
         const long long t0 = clock64();
+        bool ok = true;
         while (static_cast<int>(ld_acquire_sys(flag) - static_cast<int>(X.epoch)) < 0) {
-            __nanosleep(64);
-            if (clock64() - t0 > 4000000000LL) { s_ok = 0; break; }     // ~2 s: give up instead of hanging
+            __nanosleep(32);
+            if (clock64() - t0 > 4000000000LL) { ok = false; break; }     // ~2 s: give up instead of hanging
         }
+        if (!ok) s_ok = 0;
+        s_rho[tid] = decode_ordered(__float_as_int(ld_relaxed_sys(p2p_inbox(mine, X.world, X.rowp, parity, tid) + row)));
     }
     __syncthreads();
-    // ---- combine in rank order
-    float *mine = X.base[X.rank];
-    if (tid == 0) {
-        float rho = __int_as_float(0x7f800000);
-        for (int r = 0; r < X.world; ++r)
-            rho = fminf(rho, decode_ordered(__float_as_int(ld_relaxed_sys(p2p_inbox(mine, X.world, X.rowp, parity, r) + row))));
-        for (int r = 0; r < X.world; ++r) {
-            const float rr = decode_ordered(__float_as_int(ld_relaxed_sys(p2p_inbox(mine, X.world, X.rowp, parity, r) + row)));
-            s_scale[r] = expf(-P.inv_lambda * (rr - rho));
-        }
-        *rho_enc = encode_ordered(rho);
-    }
+    // ---- combine in rank order (every rank: same order, same values -> replicas stay bit-identical)
+    float rho = s_rho[0];
+    for (int r = 1; r < X.world; ++r) rho = fminf(rho, s_rho[r]);
+    if (tid < X.world) s_scale[tid] = expf(-P.inv_lambda * (s_rho[tid] - rho));
+    if (tid == 0) *rho_enc = encode_ordered(rho);
     __syncthreads();
     for (int j = tid; j < row; j += blockDim.x) {
+        float v[kMaxRanks];
+#pragma unroll
+        for (int r = 0; r < kMaxRanks; ++r)       // all rows' loads in flight (L2; ordered after the acquires by the barrier)
+            v[r] = (r < X.world) ? __ldcg(p2p_inbox(mine, X.world, X.rowp, parity, r) + j) : 0.f;
         float acc = 0.f;
-        for (int r = 0; r < X.world; ++r) {
-            const float c = s_scale[r];
-            const float v = ld_relaxed_sys(p2p_inbox(mine, X.world, X.rowp, parity, r) + j);
-            acc = fmaf((j == row - 1) ? c * c : c, v, acc);      // last entry is sum w^2
+#pragma unroll
+        for (int r = 0; r < kMaxRanks; ++r) {
+            if (r < X.world) {
+                const float c = s_scale[r];
+                acc = fmaf((j == row - 1) ? c * c : c, v[r], acc);      // last entry is sum w^2
+            }
         }
         wsum[j] = acc;
     }
