@@ -629,13 +629,22 @@ __device__ void reduce_partials_and_finalize(const StepParams &P, const DynBlock
     if (!s_last) return;
     __threadfence();
     trace_stamp(D, TR_LAST_BLOCK, threadIdx.x == 0);
+    // When this block also finalizes, the sums and the nominal controls reach finalize_block through shared memory
+    // (behind its own scratch): re-reading what was just stored to global costs an L2 round trip (~0.7 us) each on
+    // this serial tail.  The global copy is still written (allreduce contract, observability).
+    const int n_ctl = P.T * NU;
+    float *s_w = scratch + ((2 * n_ctl + NU + 3) & ~3), *s_u = s_w + ((row + 3) & ~3);
+    if (fuse)
+        for (int j = threadIdx.x; j < n_ctl; j += blockDim.x) s_u[j] = __ldg(u_nom + j);
     if (fix != nullptr) {
         // fixed-point accumulators -> float sums (sigma applied here), and re-arm them for the next step
         for (int j = threadIdx.x; j < row; j += blockDim.x) {
             const long long q = static_cast<long long>(__ldcg(fix + j));
             fix[j] = 0ull;
             const float scale = (j < row - 2 && !fix_has_sigma) ? P.sigma[j % NU] * (1.0f / kFixScale) : (1.0f / kFixScale);
-            wsum[j] = static_cast<float>(q) * scale;
+            const float v = static_cast<float>(q) * scale;
+            wsum[j] = v;
+            if (fuse) s_w[j] = v;
         }
     } else
     for (int j = threadIdx.x; j < row; j += blockDim.x) {
@@ -654,14 +663,19 @@ __device__ void reduce_partials_and_finalize(const StepParams &P, const DynBlock
             for (int e = 0; e < n_eta; ++e) acc += __ldcg(eta_part + 2 * e + (j - (row - 2)));
         }
         wsum[j] = acc;
+        if (fuse) s_w[j] = acc;
     }
     if (threadIdx.x == 0) *counter = 0u;
     __syncthreads();
     trace_stamp(D, TR_REDUCED, threadIdx.x == 0);
     bool ok = true;
-    if (X.world > 1) ok = p2p_exchange<MODEL>(P, X, wsum, rho_enc);
+    if (!fuse) {
+        if (X.world > 1) ok = p2p_exchange<MODEL>(P, X, wsum, rho_enc);
+        return;
+    }
+    if (X.world > 1) ok = p2p_exchange<MODEL>(P, X, s_w, rho_enc);
     trace_stamp(D, TR_EXCHANGED, threadIdx.x == 0);
-    if (fuse) finalize_block<MODEL>(P, D, wsum, u_nom, u_new, out, rho_enc, scratch, ok);
+    finalize_block<MODEL>(P, D, s_w, s_u, u_new, out, rho_enc, scratch, ok);
 }
 
 // ------------------------------------------------------------------------------------------

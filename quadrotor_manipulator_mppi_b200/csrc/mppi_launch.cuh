@@ -129,7 +129,7 @@ mppi_status_t launch_fused_variant(mppi_ctx *h, int slot, const float *d_u_nom, 
     const int R = kRolloutThreads / T;
     size_t floats = (size_t)2 * kRolloutThreads + (size_t)R * T * NUP;            // weights, indices, reduction
     if (floats < (size_t)T * NU + 4) floats = (size_t)T * NU + 4;                  // staged nominal sequence
-    if (floats < (size_t)2 * T * NU + NU) floats = (size_t)2 * T * NU + NU;        // finalize scratch
+    if (floats < (size_t)4 * T * NU + NU + 16) floats = (size_t)4 * T * NU + NU + 16;   // finalize scratch + smem hand-over of sums and u_nom
     const size_t smem = floats * sizeof(float);
     auto kernel = step_fused_kernel<MODEL, BAKED, EXTRA, ROUNDS>;
     if (grid > coresident_blocks(h, kernel, kRolloutThreads, smem, h->fused_blocks_max[slot])) return MPPI_OK;
@@ -233,7 +233,7 @@ mppi_status_t launch_weight(mppi_ctx *h, const float *d_noise, bool fuse, const 
 {
     constexpr int NU = ModelNu<MODEL>::value;
     const int K = h->P.K, T = h->P.T;
-    const size_t fin_floats = (size_t)2 * T * NU + NU;
+    const size_t fin_floats = (size_t)4 * T * NU + NU + 16;      // finalize scratch (2n + nu) + the sums and u_nom handed over in smem
     if (!d_noise) {
         const int TC = T;                       // one thread per horizon step (all Philox calls of the step), R sample sub-ranges
         int R = 512 / TC;

@@ -68,3 +68,56 @@ def test_two_gpu_matches_single_gpu(tmp_path, exchange):
     S = np.concatenate([np.load(tmp_path / f"S_{r}.npy") for r in range(world)])
     # costs of the 3rd step depend on u after two updates; those agree to ~1e-6, so S agrees closely
     assert np.abs(S - full.costs.cpu().numpy()).max() / np.abs(S).max() < 1e-4
+
+
+def _dead_peer_worker(rank, world, port, out_dir):
+    import sys
+    sys.path.insert(0, ROOT)
+    import time
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from quadrotor_manipulator_mppi_b200 import _native
+        from quadrotor_manipulator_mppi_b200.sharded import make_sharded_solver
+        st = make_sharded_solver(_native.MODEL_DRONE3, 2048, 16, device=torch.device("cuda", rank), seed=3, exchange="p2p")
+        assert st.exchange == "p2p"
+        state = np.array([0, 0, 2.1, 0, 0, 0], np.float32)
+        st.step(state=state)                                    # one healthy step on both ranks
+        u_before = st.u_prev.clone()
+        dist.barrier()
+        result = "no-error"
+        if rank == 0:
+            # rank 1 never makes this call: the exchange gives up after ~2 s, the step must NOT be applied and the
+            # blocking call must raise (a dead peer may not make the replicas apply garbage silently)
+            t0 = time.perf_counter()
+            try:
+                st.step(state=state)
+            except _native.MppiError as e:
+                result = "raised:" + str(e)
+            waited = time.perf_counter() - t0
+            unchanged = bool(torch.equal(st.solver.u_prev, u_before) or torch.equal(st.solver._u[st.solver._cur ^ 1], u_before))
+            try:                                                # sticky: later steps keep failing until the peers re-bind
+                st.solver.step_p2p_async()
+                sticky = False
+            except _native.MppiError:
+                sticky = True
+            with open(os.path.join(out_dir, "dead_peer.txt"), "w") as f:
+                f.write(f"{result}\n{waited:.2f}\n{unchanged}\n{sticky}\n")
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_dead_peer_is_reported_not_applied(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_dead_peer_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    result, waited, unchanged, sticky = open(tmp_path / "dead_peer.txt").read().split("\n")[:4]
+    assert result.startswith("raised:") and "peer" in result
+    assert 0.5 < float(waited) < 20.0
+    assert unchanged == "True" and sticky == "True"
