@@ -40,6 +40,7 @@ MODELS = {
     "quad": dict(nu=4, K=65536, T=100, desc="rigid-body quadrotor MPPI nu=4 (BASELINE.json configs[2])"),
 }
 Q_HOME = [1.57, 1.7, 0.0, 4.4, 0.0, 4.71, 0.0]     # kinova.py:135
+PHILOX_ROUNDS = 7                                  # the library default (MPPI_OPTION_PHILOX_ROUNDS); the CPU legs generate the same noise
 
 
 def parse_args():
@@ -99,7 +100,7 @@ def oracle_step_fn(model: str, K: int, T: int):
     counter = [0]
 
     def step():
-        noise = orc.philox_noise(K, T, nu, sigma, seed=0, step=counter[0])
+        noise = orc.philox_noise(K, T, nu, sigma, seed=0, step=counter[0], rounds=PHILOX_ROUNDS)
         counter[0] += 1
         if model == "wb":
             return orc.wb_step(noise, u, st[:12], st[12:19], st[19:26])

@@ -671,7 +671,8 @@ mppi_status_t mppi_p2p_export(mppi_handle_t h, int32_t world, void *ipc_handle_o
     static_assert(sizeof(cudaIpcMemHandle_t) == MPPI_IPC_HANDLE_BYTES, "IPC handle size");
     DeviceGuard guard(h->cfg.device);
     const int rowp = (h->P.T * h->nu + 4 + 3) & ~3;
-    const size_t bytes = ((size_t)kMaxRanks * kFlagStrideInts + (size_t)2 * world * rowp) * sizeof(float);
+    // inbox: [2 parities][world sources][rowp] 64-bit {value, epoch} words behind a (legacy, unused) flag area
+    const size_t bytes = (size_t)kMaxRanks * kFlagStrideInts * sizeof(float) + (size_t)2 * world * rowp * sizeof(unsigned long long);
     if (h->p2p_buf) { cudaFree(h->p2p_buf); h->p2p_buf = nullptr; }
     MPPI_CUDA(h, cudaMalloc(&h->p2p_buf, bytes));
     MPPI_CUDA(h, cudaMemset(h->p2p_buf, 0, bytes));
