@@ -251,7 +251,8 @@ mppi_status_t mppi_step_host(mppi_handle_t h, const float *state_host, int32_t n
  *                  Measured no faster than the dependent-launch pair, hence opt-in.
  *   TIME_PARALLEL  ARM7 / DRONE3 (linear double integrators), default costs, T <= 64: one WARP per sample, the two
  *                  cumulative sums of the reference as warp scans, every (sample, step) evaluates FK + cost on its own
- *                  lane, weighted-noise sums from the registers.  -1 (default) = when K_local <= 16384, 0 = never, 1 = always
+ *                  lane, weighted-noise sums from the registers.  -1 (default) = when K_local <= 8192 (arm) / 4096 (drone),
+ *                  0 = never, 1 = whenever eligible
  *   PROFILE        1: CUDA events around the kernels of every step -> mppi_get_kernel_times (SURVEY section 5 tracing hook)
  *   NVTX           1 (default): NVTX ranges "mppi.*" around the launches
  *   LAST_PATH      (read-only) MPPI_PATH_* taken by the most recent step                                              */

@@ -167,7 +167,9 @@ mppi_status_t launch_fused(mppi_ctx *h, const float *d_u_nom, float *d_u_new, fl
 }
 
 // Time-parallel warp-per-sample step (step_tp_kernel): ARM7 / DRONE3, default cost terms, T <= 64.
-constexpr int kTpAutoMaxSamples = 16384;       // "auto": beyond this the thread-per-sample kernels fill the machine on their own
+// "auto": beyond these the thread-per-sample kernels fill the machine on their own (profiles/r02/sweep_1gpu.md: the arm
+// ties at K = 16384, the much cheaper point-mass step at ~8192)
+constexpr int kTpAutoMaxSamplesArm = 8192, kTpAutoMaxSamplesDrone = 4096;
 template <int MODEL, int NOISE, bool BAKED, int SPL, int ROUNDS>
 mppi_status_t launch_tp_variant(mppi_ctx *h, int slot, const float *d_u_nom, const float *d_noise, float *d_u_new, float *d_out,
                                 cudaStream_t st, const P2PParams &X, bool *launched)
@@ -205,7 +207,7 @@ mppi_status_t launch_tp(mppi_ctx *h, const float *d_u_nom, const float *d_noise,
     *launched = false;
     if constexpr (MODEL == MPPI_MODEL_ARM7 || MODEL == MPPI_MODEL_DRONE3) {
         if (h->opt_timepar == 0 || h->P.T > 64 || (h->P.cost_flags & MPPI_COST_MASK) != 0 || h->P.K > (1 << 20)) return MPPI_OK;
-        if (h->opt_timepar < 0 && h->P.K > kTpAutoMaxSamples) return MPPI_OK;
+        if (h->opt_timepar < 0 && h->P.K > (MODEL == MPPI_MODEL_ARM7 ? kTpAutoMaxSamplesArm : kTpAutoMaxSamplesDrone)) return MPPI_OK;
         constexpr bool ARM = (MODEL == MPPI_MODEL_ARM7);
         const bool baked = ARM && h->baked_fk;
         const bool r7 = h->philox_rounds == 7 && !d_noise;
