@@ -305,6 +305,27 @@ __device__ __forceinline__ void sincos_pi(V x, V &s, V &c)
     c = vxor(cr, flip);
 }
 
+// sin / cos on the MUFU unit for the two UNPINNED models (QUAD4, WB11): reduce by 2 pi (Cody-Waite, 2 terms) to [-pi, pi],
+// then sin.approx / cos.approx (max abs error 2^-20.9 ~ 5e-7 on that range against 1.4e-7 for sincos_pi).  The FMA pipe is
+// what bounds the rollout kernel and the XU pipe is two-thirds idle: ten polynomial evaluations per whole-body step are
+// 150 of its ~600 FMA-pipe cycles.  The pinned models (ARM7, DRONE3) keep the polynomial: their costs are held to 2e-6
+// of the reference's and the soft-min amplifies cost errors by 1/lambda.
+template <class V>
+__device__ __forceinline__ void sincos_mufu(V x, V &s, V &c)
+{
+    const V k = vadd(vfma(x, V(kInvTwoPi), V(12582912.0f)), V(-12582912.0f));      // rint(x / 2 pi)
+    V r = vfma(k, V(-6.28318548202514648f), x);
+    r = vfma(k, V(1.74845553146951715e-7f), r);
+    s = vmap(r, [](float a) { float y; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(a)); return y; });
+    c = vmap(r, [](float a) { float y; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(a)); return y; });
+}
+template <bool FAST, class V>
+__device__ __forceinline__ void sincos_sel(V x, V &s, V &c)
+{
+    if constexpr (FAST) sincos_mufu(x, s, c);
+    else sincos_pi(x, s, c);
+}
+
 // Branch-free atan2 / asin for the pose cost.  Accuracy (max abs error vs double): atan2 1.5e-7 plus the
 // 2-ulp MUFU quotient, asin 1.6e-7; rcp / sqrt are the MUFU approximations (<= 2 ulp).  The reference's
 // own float32 atan2/asin carry ~1e-7; these terms enter the cost multiplied by 30 against a float32

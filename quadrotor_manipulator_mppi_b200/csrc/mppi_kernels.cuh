@@ -73,6 +73,7 @@ __device__ __forceinline__ float rollout_body(const StepParams &P, const DynBloc
     constexpr int QOFF = (MODEL == MPPI_MODEL_WB11) ? 12 : 0;    // arm q in the state vector
 
     constexpr bool PHILOX = (NOISE == 0);
+    constexpr bool FAST_TRIG = (MODEL == MPPI_MODEL_QUAD4 || MODEL == MPPI_MODEL_WB11);       // MUFU sin/cos: unpinned models only
     extern __shared__ __align__(16) float s_unom[];              // [T][NU] | (NOISE == 2) noise tiles [kNoiseStages][128][NU]
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ __align__(8) uint64_t s_full[kNoiseStages];
@@ -241,9 +242,9 @@ __device__ __forceinline__ float rollout_body(const StepParams &P, const DynBloc
         }
         if constexpr (MODEL == MPPI_MODEL_QUAD4) {
             f2 s2, c2;
-            sincos_pi(f2(qs.rpy[0], qs.rpy[1]), s2, c2);
+            sincos_sel<FAST_TRIG>(f2(qs.rpy[0], qs.rpy[1]), s2, c2);
             qs.sphi = s2.v.x; qs.cphi = c2.v.x; qs.sth = s2.v.y; qs.cth = c2.v.y;
-            sincos_pi(qs.rpy[2], qs.spsi, qs.cpsi);
+            sincos_sel<FAST_TRIG>(qs.rpy[2], qs.spsi, qs.cpsi);
         }
         if constexpr (HAS_ARM) {
             // arm accelerations in the joint pairing: chunk c1 = ARM0/4 holds joints 0..3, the next one joints 4..6
@@ -293,17 +294,17 @@ __device__ __forceinline__ float rollout_body(const StepParams &P, const DynBloc
             f2 s2, c2;
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
-                sincos_pi(qp[i], s2, c2);
+                sincos_sel<FAST_TRIG>(qp[i], s2, c2);
                 sq[pairA(i)] = s2.v.x; cq[pairA(i)] = c2.v.x; sq[pairB(i)] = s2.v.y; cq[pairB(i)] = c2.v.y;
             }
             Pose3 Tp;
             if constexpr (MODEL == MPPI_MODEL_ARM7) {
-                sincos_pi(qp[3].v.x, sq[5], cq[5]);
+                sincos_sel<FAST_TRIG>(qp[3].v.x, sq[5], cq[5]);
                 Tp = base0;
             } else {
-                sincos_pi(f2(qp[3].v.x, qs.rpy[0]), s2, c2);
+                sincos_sel<FAST_TRIG>(f2(qp[3].v.x, qs.rpy[0]), s2, c2);
                 sq[5] = s2.v.x; cq[5] = c2.v.x; qs.sphi = s2.v.y; qs.cphi = c2.v.y;
-                sincos_pi(f2(qs.rpy[1], qs.rpy[2]), s2, c2);
+                sincos_sel<FAST_TRIG>(f2(qs.rpy[1], qs.rpy[2]), s2, c2);
                 qs.sth = s2.v.x; qs.cth = c2.v.x; qs.spsi = s2.v.y; qs.cpsi = c2.v.y;
                 // moving base T(p_t, rpy_t) (S/robot/transformation_matrix.py:148-187)
                 pose3_rpy(Tp, qs.sphi, qs.cphi, qs.sth, qs.cth, qs.spsi, qs.cpsi);
@@ -366,8 +367,11 @@ __device__ __forceinline__ float rollout_body(const StepParams &P, const DynBloc
 
 // 4 blocks/SM (<= 128 registers): measured best -- with a 72-register cap (7 blocks/SM) ptxas cannot interleave the
 // Philox multiplies with the FK arithmetic and the FMA pipe stalls more (0.421 -> 0.393 ms on the bench case).
+#ifndef MPPI_WB_MINB
+#define MPPI_WB_MINB MPPI_ROLLOUT_MINB
+#endif
 template <int MODEL, int NOISE, bool BAKED, bool EXTRA, int ROUNDS>
-__global__ void __launch_bounds__(kRolloutThreads, MPPI_ROLLOUT_MINB)
+__global__ void __launch_bounds__(kRolloutThreads, (MODEL == MPPI_MODEL_WB11 && NOISE == 0 && !EXTRA) ? MPPI_WB_MINB : MPPI_ROLLOUT_MINB)
 rollout_cost_kernel(const __grid_constant__ StepParams P, const __grid_constant__ DynBlock D,
                     const float *__restrict__ u_nom, const float *__restrict__ noise,
                     float *__restrict__ cost_out, int32_t *__restrict__ rho_enc,
