@@ -150,7 +150,9 @@ int32_t mppi_abi_version(void);
  * from the absolute root to the end link, in order: type (0 fixed, 1 revolute/continuous,
  * 2 prismatic -- robot/transformation_matrix.py:38-55), origin xyz[3], origin rpy[3], axis[3].
  * The library folds it to  C0 J1(q1) C1 ... Jn(qn) Cn  with Ji = Rz(qi) or Trans(0,0,qi); the
- * chain must have exactly 7 actuated joints (the arm models' inputs).
+ * chain may have 1 to 7 actuated joints (the arm models carry 7 inputs: the slots beyond the chain's
+ * joints become null joints whose controls are sampled but cannot influence the cost; more than 7 is
+ * MPPI_ERR_UNSUPPORTED; the torque law needs exactly 7).
  * mppi_create() pre-loads the j2s7s300 chain of aerial_manipulator_gpu.urdf.            */
 mppi_status_t mppi_set_chain(mppi_handle_t h, int32_t n_chain_joints, const int32_t *types,
                              const float *xyz, const float *rpy, const float *axis);

@@ -245,12 +245,26 @@ mppi_status_t set_chain_impl(mppi_ctx *h, int n, const int32_t *types, const flo
     for (int i = 0; i < 16; ++i) dev = std::fmax(dev, std::fabs(C.m[i] - I.m[i]));
     ch.n = nrev;
     ch.last_identity = dev < 1e-12;
+    if (nrev < 1) return fail(h, MPPI_ERR_INVALID_ARG, "the chain has no actuated joint");
+    if (nrev > 7) return fail(h, MPPI_ERR_UNSUPPORTED, "the arm kernels carry 7 joint inputs: chains with more than 7 actuated joints are not supported");
+    if (nrev < 7) {
+        // Shorter arms (urdfparser.py:122-163 handles any joint count): the remaining input slots become NULL joints --
+        // identity transforms the FK skips.  Their controls are still sampled (nu is a compile-time constant of the arm
+        // kernels) but cannot influence the cost; the torque law needs all seven links and is refused below.
+        if (h->P.cost_flags & MPPI_OPT_TORQUE_LAW)
+            return fail(h, MPPI_ERR_UNSUPPORTED, "the torque law is built for 7 actuated joints");
+        for (int j = nrev; j < 7; ++j) {
+            ch.null_mask |= 1 << j;
+            for (int i = 0; i < 9; ++i) ch.R[j + 1][i] = (i % 4 == 0) ? 1.0f : 0.0f;
+            for (int i = 0; i < 3; ++i) ch.t[j + 1][i] = 0.0f;
+        }
+        ch.last_identity = 1;       // R[7] is an identity pad; the true end transform R[nrev] is applied after the last real joint
+    }
     bool baked = (nrev == FkKinova::kJoints) && ch.prismatic == 0;
     for (int j = 0; baked && j <= nrev; ++j) {
         for (int i = 0; i < 9; ++i) baked = baked && std::fabs(ch.R[j][i] - FkKinova::R[j][i]) < 1e-6f;
         for (int i = 0; i < 3; ++i) baked = baked && std::fabs(ch.t[j][i] - FkKinova::t[j][i]) < 1e-6f;
     }
-    if (nrev != 7) return fail(h, MPPI_ERR_UNSUPPORTED, "the arm kernels are built for 7 actuated joints");   // handle unchanged
     h->baked_fk = baked;
     ch.baked = baked ? 1 : 0;
     h->P.chain = ch;

@@ -26,6 +26,7 @@ struct ChainDev {
     int last_identity;   // Cn == I (true for the j2s7s300_link_7 end link)
     int baked;           // equals the compile-time FkKinova tables (fk_tables_gen.cuh)
     int prismatic;       // bit j: joint j slides along its (folded) z axis instead of rotating about it
+    int null_mask;       // bit j: input slot j is not a joint of this (shorter) chain: no motion
 };
 
 // Rigid-body parameters of the seven arm links in the folded link frames + the gains of the computed-torque law
@@ -481,6 +482,7 @@ __device__ __forceinline__ void pose3_fk_chain(const ChainDev &ch, const float *
 {
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
+        if ((ch.null_mask >> j) & 1) continue;      // padding slot of a chain with fewer than NJ actuated joints (uniform branch)
         if ((ch.prismatic >> j) & 1) {     // S/robot/transformation_matrix.py:38-55: translate by q along the joint axis (uniform branch)
             T.pxy = vfma(T.c2, f2(qv[j]), T.pxy);
             T.pz = fmaf(T.r2, qv[j], T.pz);

@@ -560,10 +560,47 @@ def test_generic_chain_against_oracle(which, oracle, native):
     assert out[native.MPPI_OUT_REACH] == pytest.approx(reach, abs=2e-5)
     # and the baked chain really is a different answer (the test would be vacuous otherwise)
     assert rel_inf(want, oracle.arm_costs(noise, np.zeros((T, 7), np.float32), q, qd, base)) > 1e-3
-    with pytest.raises(native.MppiError):        # unknown joint types and wrong joint counts are rejected
+    with pytest.raises(native.MppiError):        # unknown joint types and chains with more than 7 actuated joints are rejected
         s.set_chain([0, 3, 1, 1, 1, 1, 1, 1], ch.xyz[:8], ch.rpy[:8], ch.axis[:8])
     with pytest.raises(native.MppiError):
-        s.set_chain([0, 1, 1, 1, 1, 1, 1, 0], ch.xyz[:8], ch.rpy[:8], ch.axis[:8])
+        s.set_chain([0, 1, 1, 1, 1, 1, 1, 1, 1], np.vstack([ch.xyz[:8], ch.xyz[7:8]]), np.vstack([ch.rpy[:8], ch.rpy[7:8]]),
+                    np.vstack([ch.axis[:8], ch.axis[7:8]]))
+    with pytest.raises(native.MppiError):
+        s.set_chain([0, 0, 0], ch.xyz[:3], ch.rpy[:3], ch.axis[:3])          # no actuated joint at all
+
+
+@pytest.mark.parametrize("n_act", [6, 4, 1])
+def test_shorter_chains_run_with_null_joint_slots(n_act, oracle, native):
+    """urdfparser.py:122-163 handles any joint count; the arm kernels carry 7 inputs, so a chain with fewer actuated
+    joints leaves the remaining input slots as null joints: sampled, but without influence on the cost."""
+    from quadrotor_manipulator_mppi_b200.core import NativeSolver
+    base_ch = oracle.KINOVA_CHAIN
+    n = 1 + n_act                                  # joint_base (fixed) + the first n_act revolute joints: end link = link_<n_act>
+    ch = oracle.Chain(base_ch.jtype[:n], base_ch.qidx[:n], base_ch.xyz[:n], base_ch.rpy[:n], base_ch.axis[:n])
+    K, T = 320, 18
+    for tp in (0, 1):                              # thread-per-sample pair and the time-parallel kernel (generic FK in both)
+        s = NativeSolver(native.MODEL_ARM7, n_samples=K, n_horizon=T, time_parallel=tp)
+        s.set_chain(ch.jtype, ch.xyz, ch.rpy, ch.axis)
+        q = np.array([1.2, 2.0, -0.4, 4.0, 0.7, 4.2, -1.0], np.float32)
+        qd = np.array([0.05, -0.1, 0.02, 0.3, -0.2, 0.1, -0.05], np.float32)
+        base = np.array([0.3, -0.2, 1.7, 0.0499792, -0.0998334, 0.1494381, 0.9824485], np.float32)
+        s.set_state(np.concatenate([q, qd, base]))
+        noise = _rand_noise(T, K, (0.1,) * 7, 40 + n_act)
+        out = s.step(s.prepare_noise(noise)).copy()
+        S = s.costs.cpu().numpy()
+        want = oracle.arm_costs(noise, np.zeros((T, 7), np.float32), q, qd, base, chain=ch)
+        assert rel_inf(S, want) < 5e-6
+        # the null slots' noise cannot matter: zeroing it leaves every cost unchanged
+        noise2 = noise.copy()
+        noise2[:, :, n_act:] = 0.0
+        s.u_prev = torch.zeros(T, 7)
+        s.step(s.prepare_noise(noise2))
+        assert torch.equal(s.costs.cpu(), torch.from_numpy(S))
+        Tw = oracle.xyzquat_to_matrix(base).astype(np.float64) @ oracle.fk(out[0:7], ch).astype(np.float64)
+        assert out[native.MPPI_OUT_REACH] == pytest.approx(np.abs(Tw[:3, 3] - np.asarray(oracle.ARM_TARGET_POS)).sum(), abs=2e-5)
+    with pytest.raises(native.MppiError):           # the torque law needs all seven links
+        t = NativeSolver(native.MODEL_ARM7, n_samples=64, n_horizon=16, cost_flags=native.OPT_TORQUE_LAW)
+        t.set_chain(ch.jtype, ch.xyz, ch.rpy, ch.axis)
 
 
 def test_update_config_and_targets_take_effect(oracle, native):
