@@ -210,7 +210,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "rollout_steps_per_s", "value": value, "unit": "rollout-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot / args.steps * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{spec['desc']}, K={K}, T={T}", "noise": "philox", "sample_K": Ks},
+            "config": {"workload": f"{spec['desc']}, K={K}, T={T}", "noise": "philox", "philox_rounds": PHILOX_ROUNDS, "sample_K": Ks,
+                       "l2": "CPU arm: host caches, no flush", "timing": "time.perf_counter around every step, rank 0 only"},
             "cpu_baseline": {"value": value, "unit": "rollout-steps/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "rollout-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "latency_ms": {"p50": float(np.percentile(times, 50) * 1e3), "p99": float(np.percentile(times, 99) * 1e3)},
@@ -660,6 +661,7 @@ def run_native(args):
                 uf = full.u_prev.double()
                 checks[tag + "sharded_vs_single_rank_u_new_rel"] = float(((u_used.double() - uf).abs().max() / uf.abs().max().clamp_min(1e-30)).item())
                 full.close()
+            barrier()            # the other ranks must not enter the next exchange (bounded ~2 s wait) while rank 0 is still busy here
             ok_local = (ok_local and checks[tag + "ranks_bit_identical_u_new"] and checks[tag + "ranks_bit_identical_out"]
                         and checks[tag + "out_step_nonnegative"] and checks[tag + "p2p_vs_nccl_u_new_rel"] <= 1e-6
                         and checks.get(tag + "sharded_costs_bitwise_equal_single_rank", True)
