@@ -90,24 +90,19 @@ __device__ __forceinline__ void trace_stamp(const DynBlock &D, int point, bool w
 }
 
 // Peer-to-peer exchange over NVLink (K-sharded replicas, one process per GPU; buffers are
-// cudaMalloc'ed and mapped into every rank with CUDA IPC).  Rank r's buffer holds
-//   flags [kMaxRanks] (128-byte stride): flags[s] = last epoch published by source rank s
-//   inbox [2 parity][world][rowp] floats: slot (parity, s) = row published by source rank s
+// cudaMalloc'ed and mapped into every rank with CUDA IPC).  Rank r's buffer holds, behind a 1 KB reserved header,
+//   inbox [2 parity][world][rowp] 64-bit words {value, epoch}: slot (parity, s, j) = element j of the row published
+//   by source rank s at an epoch of that parity (low-latency protocol, see p2p_exchange in mppi_kernels.cuh).
 // world == 1 disables the exchange.
 constexpr int kMaxRanks = 8;
-constexpr int kFlagStrideInts = 32;
+constexpr int kFlagStrideInts = 32;          // header size in units of kMaxRanks * 4 bytes
 struct P2PParams {
     int world, rank;
-    unsigned epoch;              // starts at 1, +1 per control step, same on every rank
-    int rowp;                    // floats per inbox row (T*nu + 4, padded to a multiple of 4)
+    unsigned epoch;              // starts at 1, +1 per control step, same on every rank; the tag of every published element
+    int rowp;                    // elements per inbox row (T*nu + 4, padded to a multiple of 4)
     float *base[kMaxRanks];      // base[r] = rank r's exchange buffer as mapped in THIS process
     unsigned *fail_flag;         // mapped host word: set to the epoch at which a peer never published (sticky)
 };
-__host__ __device__ __forceinline__ int *p2p_flags(float *base) { return reinterpret_cast<int *>(base); }
-__host__ __device__ __forceinline__ float *p2p_inbox(float *base, int world, int rowp, int parity, int src)
-{
-    return base + kMaxRanks * kFlagStrideInts + (static_cast<size_t>(parity) * world + src) * rowp;
-}
 
 template <int MODEL> struct ModelNu;
 template <> struct ModelNu<MPPI_MODEL_DRONE3> { static constexpr int value = 3; };

@@ -568,16 +568,15 @@ __device__ bool p2p_exchange(const StepParams &P, const P2PParams &X, float *wsu
     // replicas stay bit-identical).
     float *mine = X.base[X.rank];
     const long long t0 = clock64();
-    auto take = [&](int r, int j) -> float {
-        const unsigned long long *slot = p2p_ll_slot(mine, X.world, X.rowp, parity, r) + j;
+    if (tid < X.world) {
+        const unsigned long long *slot = p2p_ll_slot(mine, X.world, X.rowp, parity, tid) + row;
         unsigned long long w = ld_ll(slot);
         while (static_cast<unsigned>(w >> 32) != X.epoch) {
             if (clock64() - t0 > 4000000000LL) { s_ok = 0; break; }     // ~2 s: a peer is gone; give up instead of hanging
             w = ld_ll(slot);
         }
-        return __uint_as_float(static_cast<unsigned>(w));
-    };
-    if (tid < X.world) s_rho[tid] = take(tid, row);
+        s_rho[tid] = __uint_as_float(static_cast<unsigned>(w));
+    }
     __syncthreads();
     float rho = s_rho[0];
     for (int r = 1; r < X.world; ++r) rho = fminf(rho, s_rho[r]);

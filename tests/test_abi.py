@@ -115,3 +115,25 @@ def test_c_example_runs_on_the_gpu(tmp_path):
     assert len(lines) == 5 and "tau[1]=" in lines[-1]
     tau1 = float(lines[0].split("tau[1]=")[1])
     assert 5.0 < abs(tau1) < 40.0              # gravity load on the shoulder joint at the home pose
+
+
+def test_a_stale_library_is_never_loaded_silently(tmp_path, monkeypatch):
+    """the .so travels to the GPU box; it may only be used if it was built from the sources on disk.
+    build.py stores a content hash of csrc/ + include/ next to the library and rebuilds on any mismatch."""
+    from quadrotor_manipulator_mppi_b200 import build
+    build.build()
+    assert not build.needs_build()
+    assert open(build.HASH).read().strip() == build.source_hash()
+    srcs = [os.path.basename(p) for p in build.sources()]
+    for must in ("mppi_b200.cu", "mppi_model_unit.cu", "mppi_kernels.cuh", "mppi_device.cuh", "mppi_dynamics.cuh", "arm_inertia_gen.cuh",
+                 "fk_tables_gen.cuh", "mppi_launch.cuh", "mppi_host.cuh", "mppi_vec.cuh", "mppi_b200.h"):
+        assert must in srcs, must
+    good = open(build.HASH).read()
+    try:
+        with open(build.HASH, "w") as f:
+            f.write("0" * 64 + "\n")                 # as if a header had been edited after the build
+        assert build.needs_build()
+    finally:
+        with open(build.HASH, "w") as f:
+            f.write(good)
+    assert not build.needs_build()
