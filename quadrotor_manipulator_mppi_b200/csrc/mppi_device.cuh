@@ -140,17 +140,22 @@ __device__ __forceinline__ uint4 philox4x32(uint4 c, const uint32_t *rk)
 // [21 i, 21 i + 21) of the little-endian 128-bit word, placed in the top of a float mantissa: f in [1, 2)
 // with 2^-21 steps (radius up to sqrt(2*21*ln 2) = 5.4 sigma, angle step 3e-6 rad).
 constexpr uint32_t kU21 = 0x1FFFFFu;
+__device__ __forceinline__ float mantissa_field(uint32_t x)          // (x & (kU21 << 2)) | 0x3f800000 as ONE LOP3 (LUT 0xEA = (a & b) | c)
+{
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(x), "r"(kU21 << 2), "r"(0x3f800000u));
+    return __uint_as_float(d);
+}
 __device__ __forceinline__ void philox_uniforms6(uint4 r, float f[6])
 {
-    const uint32_t u0 = r.x & kU21;
-    const uint32_t u1 = __funnelshift_r(r.x, r.y, 21) & kU21;
-    const uint32_t u2 = (r.y >> 10) & kU21;
-    const uint32_t u3 = __funnelshift_r(r.y, r.z, 31) & kU21;
-    const uint32_t u4 = __funnelshift_r(r.z, r.w, 20) & kU21;
-    const uint32_t u5 = (r.w >> 9) & kU21;
-    f[0] = __uint_as_float(0x3f800000u | (u0 << 2)); f[1] = __uint_as_float(0x3f800000u | (u1 << 2));
-    f[2] = __uint_as_float(0x3f800000u | (u2 << 2)); f[3] = __uint_as_float(0x3f800000u | (u3 << 2));
-    f[4] = __uint_as_float(0x3f800000u | (u4 << 2)); f[5] = __uint_as_float(0x3f800000u | (u5 << 2));
+    // the 21-bit field is shifted straight to mantissa bits [2, 23), then masked and given its exponent in one LOP3:
+    // one shift (or funnel shift) + one LOP3 per uniform
+    f[0] = mantissa_field(r.x << 2);                                // bits [  0,  21)
+    f[1] = mantissa_field(__funnelshift_r(r.x, r.y, 19));           // bits [ 21,  42)
+    f[2] = mantissa_field(r.y >> 8);                                // bits [ 42,  63)
+    f[3] = mantissa_field(__funnelshift_r(r.y, r.z, 29));           // bits [ 63,  84)
+    f[4] = mantissa_field(__funnelshift_r(r.z, r.w, 18));           // bits [ 84, 105)
+    f[5] = mantissa_field(r.w >> 7);                                // bits [105, 126)
 }
 // Number of Philox calls per (sample, step): pairs = ceil(nu / 2), three pairs per call.
 __host__ __device__ constexpr int philox_calls(int nu) { return ((nu + 1) / 2 + 2) / 3; }
