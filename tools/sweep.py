@@ -32,6 +32,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=None)
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--medium", action="store_true", help="K in {1k, 16k, 256k, 4M} x T in {16, 64, 256}: the multi-GPU grid")
     ap.add_argument("--philox-rounds", type=int, default=None)
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -44,8 +45,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     out_path = a.out or os.path.join(ROOT, "profiles", "r02", f"sweep_{world}gpu.json")
     ids = {"wb": _native.MODEL_WB11, "arm": _native.MODEL_ARM7, "drone": _native.MODEL_DRONE3, "quad": _native.MODEL_QUAD4}
-    Ks = [1 << e for e in ((10, 14, 18) if a.quick else (10, 12, 14, 16, 18, 20, 22))]
-    Ts = (16, 64) if a.quick else (16, 32, 64, 128, 256)
+    Ks = [1 << e for e in ((10, 14, 18) if a.quick else (10, 14, 18, 22) if a.medium else (10, 12, 14, 16, 18, 20, 22))]
+    Ts = (16, 64) if a.quick else (16, 64, 256) if a.medium else (16, 32, 64, 128, 256)
     stream = torch.cuda.current_stream(dev)
     rows = []
 
