@@ -224,7 +224,7 @@ def run_reference(args):
 class ClockSampler:
     """Samples SM clock / throttle reasons through NVML while the timed region runs."""
 
-    def __init__(self, index: int, period_s: float = 0.02):
+    def __init__(self, index: int, period_s: float = 0.004):
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
         self._thread = None
