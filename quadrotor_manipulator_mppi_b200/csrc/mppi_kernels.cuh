@@ -940,7 +940,7 @@ step_fused_kernel(const __grid_constant__ StepParams P, const __grid_constant__ 
 // ------------------------------------------------------------------------------------------
 // Time-parallel control step for the models whose dynamics are a LINEAR double integrator (ARM7, DRONE3 -- the two
 // controllers the reference runs): ONE WARP PER SAMPLE, lane l owns the SPL consecutive horizon steps
-// [l*SPL, (l+1)*SPL).  The reference integrates with two cumulative sums over the horizon
+// [l*SPL, (l+1)*SPL) (SPL = 1, 2 or 4: T <= 128).  The reference integrates with two cumulative sums over the horizon
 // (S/sampling/standard_normal_noise.py:37-48, S/mppi_solver/drone_mppi.py:47-54); here they are two warp scans, after
 // which every (sample, step) pair evaluates its FK + cost independently -- K*T-way instead of K-way parallelism, which
 // is what a reference-sized problem (K = 100 ... 1000, T = 30) needs to fill 148 SMs: the thread-per-sample kernel
@@ -1030,7 +1030,7 @@ step_tp_kernel(const __grid_constant__ StepParams P, const __grid_constant__ Dyn
         const uint32_t kg = static_cast<uint32_t>(P.k_offset + k);
 
         // ---- noise and controls of this lane's steps: a = u_nom + eps  (mppi.py:130)
-        float nrm[SPL][NUP], a[SPL][NU];
+        float nrm[SPL][NUP];
 #pragma unroll
         for (int s = 0; s < SPL; ++s) {
             const int t = lane * SPL + s;
@@ -1050,21 +1050,28 @@ step_tp_kernel(const __grid_constant__ StepParams P, const __grid_constant__ Dyn
 #pragma unroll
                 for (int i = 0; i < NUP; ++i) nrm[s][i] = (i < NU) ? __ldg(row + i) : 0.f;
             }
+            if (!valid) {
 #pragma unroll
-            for (int i = 0; i < NU; ++i) {
-                const float eps = PHILOX ? __fmul_rn(P.sigma[i], nrm[s][i]) : nrm[s][i];
-                a[s][i] = valid ? __fadd_rn(__ldg(u_nom + tc * NU + i), eps) : 0.f;
-                if (!valid) nrm[s][i] = 0.f;
+                for (int i = 0; i < NUP; ++i) nrm[s][i] = 0.f;
             }
         }
         // ---- double integrator as two scans over the horizon (standard_normal_noise.py:37-48 / drone_mppi.py:47-54)
         float qs[SPL][NU];                                // position-like state after each of this lane's steps
 #pragma unroll
         for (int i = 0; i < NU; ++i) {
+            // controls of this lane's steps for input i, rebuilt from the normals (only the normals are kept across the
+            // cost evaluation: registers scale with SPL)
+            float a_i[SPL];
+#pragma unroll
+            for (int s = 0; s < SPL; ++s) {
+                const int t = lane * SPL + s;
+                const float eps = PHILOX ? __fmul_rn(P.sigma[i], nrm[s][i]) : nrm[s][i];
+                a_i[s] = (t < P.T) ? __fadd_rn(__ldg(u_nom + t * NU + i), eps) : 0.f;
+            }
             float lcv[SPL];
             float c = 0.f;
 #pragma unroll
-            for (int s = 0; s < SPL; ++s) { c = fmaf(a[s][i], P.dt, c); lcv[s] = c; }
+            for (int s = 0; s < SPL; ++s) { c = fmaf(a_i[s], P.dt, c); lcv[s] = c; }
             const float ex_v = warp_excl_scan(c, lane);   // sum a dt over all earlier lanes
             const float v0 = D.state[QD0 + i];
             float lcq[SPL];
@@ -1072,7 +1079,7 @@ step_tp_kernel(const __grid_constant__ StepParams P, const __grid_constant__ Dyn
 #pragma unroll
             for (int s = 0; s < SPL; ++s) {
                 const float vprev = ((s == 0) ? ex_v : ex_v + lcv[s - 1]) + v0;
-                cq += fmaf(vprev, P.dt, (0.5f * a[s][i]) * P.dt2);
+                cq += fmaf(vprev, P.dt, (0.5f * a_i[s]) * P.dt2);
                 lcq[s] = cq;
             }
             const float ex_q = warp_excl_scan(cq, lane);

@@ -200,31 +200,40 @@ mppi_status_t launch_tp_variant(mppi_ctx *h, int slot, const float *d_u_nom, con
     return MPPI_OK;
 }
 
+template <int MODEL, int NOISE, bool BAKED, int ROUNDS>
+mppi_status_t launch_tp_spl(mppi_ctx *h, int slot, int spl, const float *d_u_nom, const float *d_noise, float *d_u_new, float *d_out,
+                            cudaStream_t st, const P2PParams &X, bool *launched)
+{
+    switch (spl) {
+        case 1: return launch_tp_variant<MODEL, NOISE, BAKED, 1, ROUNDS>(h, slot, d_u_nom, d_noise, d_u_new, d_out, st, X, launched);
+        case 2: return launch_tp_variant<MODEL, NOISE, BAKED, 2, ROUNDS>(h, slot, d_u_nom, d_noise, d_u_new, d_out, st, X, launched);
+        default: return launch_tp_variant<MODEL, NOISE, BAKED, 4, ROUNDS>(h, slot, d_u_nom, d_noise, d_u_new, d_out, st, X, launched);
+    }
+}
+
 template <int MODEL>
 mppi_status_t launch_tp(mppi_ctx *h, const float *d_u_nom, const float *d_noise, float *d_u_new, float *d_out, cudaStream_t st,
                         const P2PParams &X, bool *launched)
 {
     *launched = false;
     if constexpr (MODEL == MPPI_MODEL_ARM7 || MODEL == MPPI_MODEL_DRONE3) {
-        if (h->opt_timepar == 0 || h->P.T > 64 || (h->P.cost_flags & MPPI_COST_MASK) != 0 || h->P.K > (1 << 20)) return MPPI_OK;
+        if (h->opt_timepar == 0 || h->P.T > 128 || (h->P.cost_flags & MPPI_COST_MASK) != 0 || h->P.K > (1 << 20)) return MPPI_OK;
         if (h->opt_timepar < 0 && h->P.K > (MODEL == MPPI_MODEL_ARM7 ? kTpAutoMaxSamplesArm : kTpAutoMaxSamplesDrone)) return MPPI_OK;
         constexpr bool ARM = (MODEL == MPPI_MODEL_ARM7);
         const bool baked = ARM && h->baked_fk;
         const bool r7 = h->philox_rounds == 7 && !d_noise;
-        const int spl = h->P.T <= 32 ? 1 : 2;
-        const int slot = (baked ? 1 : 0) + (d_noise ? 2 : 0) + (spl == 2 ? 4 : 0) + (r7 ? 8 : 0);
-#define MPPI_TP_CASE(N, B, S, R) return launch_tp_variant<MODEL, N, B, S, R>(h, slot, d_u_nom, d_noise, d_u_new, d_out, st, X, launched)
+        const int spl = h->P.T <= 32 ? 1 : h->P.T <= 64 ? 2 : 4;       // horizon steps per lane
+        const int slot = (baked ? 1 : 0) + (d_noise ? 2 : 0) + (r7 ? 4 : 0) + 8 * (spl == 1 ? 0 : spl == 2 ? 1 : 2);
         if (d_noise) {
-            if (baked) { if (spl == 1) MPPI_TP_CASE(1, ARM, 1, 10); else MPPI_TP_CASE(1, ARM, 2, 10); }
-            else       { if (spl == 1) MPPI_TP_CASE(1, false, 1, 10); else MPPI_TP_CASE(1, false, 2, 10); }
-        } else if (r7) {
-            if (baked) { if (spl == 1) MPPI_TP_CASE(0, ARM, 1, 7); else MPPI_TP_CASE(0, ARM, 2, 7); }
-            else       { if (spl == 1) MPPI_TP_CASE(0, false, 1, 7); else MPPI_TP_CASE(0, false, 2, 7); }
-        } else {
-            if (baked) { if (spl == 1) MPPI_TP_CASE(0, ARM, 1, 10); else MPPI_TP_CASE(0, ARM, 2, 10); }
-            else       { if (spl == 1) MPPI_TP_CASE(0, false, 1, 10); else MPPI_TP_CASE(0, false, 2, 10); }
+            if (baked) return launch_tp_spl<MODEL, 1, ARM, 10>(h, slot, spl, d_u_nom, d_noise, d_u_new, d_out, st, X, launched);
+            return launch_tp_spl<MODEL, 1, false, 10>(h, slot, spl, d_u_nom, d_noise, d_u_new, d_out, st, X, launched);
         }
-#undef MPPI_TP_CASE
+        if (r7) {
+            if (baked) return launch_tp_spl<MODEL, 0, ARM, 7>(h, slot, spl, d_u_nom, d_noise, d_u_new, d_out, st, X, launched);
+            return launch_tp_spl<MODEL, 0, false, 7>(h, slot, spl, d_u_nom, d_noise, d_u_new, d_out, st, X, launched);
+        }
+        if (baked) return launch_tp_spl<MODEL, 0, ARM, 10>(h, slot, spl, d_u_nom, d_noise, d_u_new, d_out, st, X, launched);
+        return launch_tp_spl<MODEL, 0, false, 10>(h, slot, spl, d_u_nom, d_noise, d_u_new, d_out, st, X, launched);
     }
     return MPPI_OK;
 }
