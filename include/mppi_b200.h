@@ -251,7 +251,7 @@ mppi_status_t mppi_step_host(mppi_handle_t h, const float *state_host, int32_t n
  *   FUSED_STEP     0 (default) / 1: a Philox step whose rollout grid is co-resident (K_local <= 128 x resident blocks,
  *                  T <= 128) runs as ONE cooperative launch (rollout, grid barrier, weighting, exchange, finalize).
  *                  Measured no faster than the dependent-launch pair, hence opt-in.
- *   TIME_PARALLEL  ARM7 / DRONE3 (linear double integrators), default costs, T <= 128: one WARP per sample, the two
+ *   TIME_PARALLEL  ARM7 / DRONE3 (linear double integrators), default costs (any horizon up to 256): one WARP per sample, the two
  *                  cumulative sums of the reference as warp scans, every (sample, step) evaluates FK + cost on its own
  *                  lane, weighted-noise sums from the registers.  -1 (default) = when K_local <= 8192 (arm) / 4096 (drone),
  *                  0 = never, 1 = whenever eligible

@@ -68,7 +68,7 @@ struct mppi_ctx {
     unsigned *d_sync = nullptr;     // monotonic arrival counter
     unsigned sync_target = 0;       // value it reaches after the launches issued so far
     int fused_blocks_max[8] = {-1, -1, -1, -1, -1, -1, -1, -1};   // co-resident capacity of step_fused_kernel per (baked, extra, rounds) variant
-    int tp_blocks_max[24] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
+    int tp_blocks_max[32] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
     int last_path = 0;              // MPPI_PATH_* of the most recent step
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     bool ev_valid = false;

@@ -940,7 +940,7 @@ step_fused_kernel(const __grid_constant__ StepParams P, const __grid_constant__ 
 // ------------------------------------------------------------------------------------------
 // Time-parallel control step for the models whose dynamics are a LINEAR double integrator (ARM7, DRONE3 -- the two
 // controllers the reference runs): ONE WARP PER SAMPLE, lane l owns the SPL consecutive horizon steps
-// [l*SPL, (l+1)*SPL) (SPL = 1, 2 or 4: T <= 128).  The reference integrates with two cumulative sums over the horizon
+// [l*SPL, (l+1)*SPL) (SPL = 1, 2, 4 or 8: T <= 256).  The reference integrates with two cumulative sums over the horizon
 // (S/sampling/standard_normal_noise.py:37-48, S/mppi_solver/drone_mppi.py:47-54); here they are two warp scans, after
 // which every (sample, step) pair evaluates its FK + cost independently -- K*T-way instead of K-way parallelism, which
 // is what a reference-sized problem (K = 100 ... 1000, T = 30) needs to fill 148 SMs: the thread-per-sample kernel
@@ -955,8 +955,9 @@ step_fused_kernel(const __grid_constant__ StepParams P, const __grid_constant__ 
 //        1 = injected [T][K][nu].
 // S/mppi_solver/mppi.py:122-158, S/mppi_solver/drone_mppi.py:140-170.
 // ------------------------------------------------------------------------------------------
-constexpr int kTpThreads = 512;        // 16 warps = 16 samples per tile
-constexpr int kTpWarps = kTpThreads / 32;
+// Block shape by steps per lane: 512 threads (16 samples per tile) up to four steps per lane; eight steps per lane
+// (T <= 256) keep 8 x 15 values per thread across the cost evaluation and run as 256-thread blocks (<= 255 registers).
+__host__ __device__ constexpr int tp_threads(int spl) { return spl <= 4 ? 512 : 256; }
 
 __device__ __forceinline__ float warp_excl_scan(float x, int lane)
 {
@@ -988,7 +989,7 @@ __device__ __forceinline__ float warp_sum_compensated(float hi, float lo)
 
 constexpr int kTpMaxRows = 160;         // rows the last block combines: one per resident block, <= one block per SM
 template <int MODEL, int NOISE, bool BAKED, int SPL, int ROUNDS>
-__global__ void __launch_bounds__(kTpThreads)
+__global__ void __launch_bounds__(tp_threads(SPL))
 step_tp_kernel(const __grid_constant__ StepParams P, const __grid_constant__ DynBlock D,
                const float *__restrict__ u_nom, const float *__restrict__ noise, float *__restrict__ cost_out,
                int32_t *rho_enc, float *__restrict__ rows, float *__restrict__ rho_rows, uint32_t *counter,
@@ -999,6 +1000,7 @@ step_tp_kernel(const __grid_constant__ StepParams P, const __grid_constant__ Dyn
     constexpr int NQ = (NU + 3) / 4;
     constexpr int NUP = 4 * NQ;
     constexpr bool PHILOX = (NOISE == 0);
+    constexpr int kTpThreads = tp_threads(SPL), kTpWarps = kTpThreads / 32;
     constexpr int Q0 = 0, QD0 = (MODEL == MPPI_MODEL_ARM7) ? 7 : 3;
     extern __shared__ __align__(16) float s_dyn[];       // [n] block accumulator | [kTpWarps][n] tile contributions (combine / finalize scratch later)
     __shared__ float s_S[kTpWarps], s_W[kTpWarps];
@@ -1186,7 +1188,7 @@ step_tp_kernel(const __grid_constant__ StepParams P, const __grid_constant__ Dyn
     // nominal controls.  The combined sums and u_nom reach finalize_block through shared memory: every global round
     // trip on this serial tail costs 0.5-1 us.
     float *s_scale = s_con, *s_red = s_dyn + ((n + kTpMaxRows + 3) & ~3);          // float4-aligned
-    const int off_w = max(2 * n + NU, n + kTpMaxRows + 4 * kTpThreads + 4) + 4;
+    const int off_w = max(2 * n + NU, n + kTpMaxRows + 4 + max(4 * kTpThreads, rstride)) + 4;      // s_red holds parts * rstride floats
     float *s_w = s_dyn + off_w, *s_u = s_w + nout + 2;
     for (int j = tid; j < n; j += kTpThreads) s_u[j] = __ldg(u_nom + j);            // in flight while the rows are combined
     // global minimum over the rows' minima: one value per thread, warp shuffles, 16 partials

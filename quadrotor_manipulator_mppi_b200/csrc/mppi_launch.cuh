@@ -169,16 +169,19 @@ mppi_status_t launch_fused(mppi_ctx *h, const float *d_u_nom, float *d_u_new, fl
 // Time-parallel warp-per-sample step (step_tp_kernel): ARM7 / DRONE3, default cost terms, T <= 64.
 // "auto": beyond these the thread-per-sample kernels fill the machine on their own (profiles/r02/sweep_1gpu.md: the arm
 // ties at K = 16384, the much cheaper point-mass step at ~8192)
-constexpr int kTpAutoMaxSamplesArm = 8192, kTpAutoMaxSamplesDrone = 4096;
+constexpr int kTpAutoMaxSamplesArm = 8192, kTpAutoMaxSamplesDrone = 4096, kTpAutoMaxSamplesDroneLong = 2048;
 template <int MODEL, int NOISE, bool BAKED, int SPL, int ROUNDS>
 mppi_status_t launch_tp_variant(mppi_ctx *h, int slot, const float *d_u_nom, const float *d_noise, float *d_u_new, float *d_out,
                                 cudaStream_t st, const P2PParams &X, bool *launched)
 {
     constexpr int NU = ModelNu<MODEL>::value;
+    constexpr int THREADS = tp_threads(SPL), WARPS = THREADS / 32;
     const size_t n = (size_t)h->P.T * NU;
-    size_t floats = (1 + (size_t)kTpWarps) * n;                       // block accumulator + tile contributions of the 16 warps
+    size_t floats = (1 + (size_t)WARPS) * n;                          // block accumulator + tile contributions of the block's warps
     size_t off_w = 2 * n + NU;                                        // hand-over layout of the last block (see the kernel)
-    if (off_w < n + kTpMaxRows + 4 * kTpThreads + 4) off_w = n + kTpMaxRows + 4 * kTpThreads + 4;
+    const size_t rstride = (n + 2 + 3) & ~(size_t)3;
+    const size_t red = rstride > (size_t)4 * THREADS ? rstride : (size_t)4 * THREADS;      // combine partials: parts * rstride floats
+    if (off_w < n + kTpMaxRows + 4 + red) off_w = n + kTpMaxRows + 4 + red;
     const size_t tail = off_w + 4 + (n + 2) + 2 + n;
     if (floats < tail) floats = tail;
     const size_t smem = floats * sizeof(float);
@@ -188,13 +191,13 @@ mppi_status_t launch_tp_variant(mppi_ctx *h, int slot, const float *d_u_nom, con
         if (smem > 48 * 1024) MPPI_CUDA(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ready = 1;
     }
-    const int n_tiles = (h->P.K + kTpWarps - 1) / kTpWarps;
+    const int n_tiles = (h->P.K + WARPS - 1) / WARPS;
     int cap = h->num_sms < kTpMaxRows ? h->num_sms : kTpMaxRows;      // one row per block, one block per SM
     if (cap > h->max_parts) cap = h->max_parts;
     const int grid = n_tiles < cap ? n_tiles : cap;                  // persistent blocks loop over the remaining tiles
     NvtxRange nv(h, "mppi.step_timeparallel");
-    kernel<<<grid, kTpThreads, smem, st>>>(h->P, h->dyn, d_u_nom, d_noise, h->d_cost, h->d_rho, h->d_part, h->d_eta_part,
-                                           h->d_counter, h->d_wsum, d_u_new, d_out, X);
+    kernel<<<grid, THREADS, smem, st>>>(h->P, h->dyn, d_u_nom, d_noise, h->d_cost, h->d_rho, h->d_part, h->d_eta_part,
+                                        h->d_counter, h->d_wsum, d_u_new, d_out, X);
     MPPI_CUDA(h, cudaGetLastError());
     *launched = true;
     return MPPI_OK;
@@ -207,7 +210,8 @@ mppi_status_t launch_tp_spl(mppi_ctx *h, int slot, int spl, const float *d_u_nom
     switch (spl) {
         case 1: return launch_tp_variant<MODEL, NOISE, BAKED, 1, ROUNDS>(h, slot, d_u_nom, d_noise, d_u_new, d_out, st, X, launched);
         case 2: return launch_tp_variant<MODEL, NOISE, BAKED, 2, ROUNDS>(h, slot, d_u_nom, d_noise, d_u_new, d_out, st, X, launched);
-        default: return launch_tp_variant<MODEL, NOISE, BAKED, 4, ROUNDS>(h, slot, d_u_nom, d_noise, d_u_new, d_out, st, X, launched);
+        case 4: return launch_tp_variant<MODEL, NOISE, BAKED, 4, ROUNDS>(h, slot, d_u_nom, d_noise, d_u_new, d_out, st, X, launched);
+        default: return launch_tp_variant<MODEL, NOISE, BAKED, 8, ROUNDS>(h, slot, d_u_nom, d_noise, d_u_new, d_out, st, X, launched);
     }
 }
 
@@ -217,13 +221,16 @@ mppi_status_t launch_tp(mppi_ctx *h, const float *d_u_nom, const float *d_noise,
 {
     *launched = false;
     if constexpr (MODEL == MPPI_MODEL_ARM7 || MODEL == MPPI_MODEL_DRONE3) {
-        if (h->opt_timepar == 0 || h->P.T > 128 || (h->P.cost_flags & MPPI_COST_MASK) != 0 || h->P.K > (1 << 20)) return MPPI_OK;
-        if (h->opt_timepar < 0 && h->P.K > (MODEL == MPPI_MODEL_ARM7 ? kTpAutoMaxSamplesArm : kTpAutoMaxSamplesDrone)) return MPPI_OK;
+        constexpr bool ARM_MODEL = (MODEL == MPPI_MODEL_ARM7);
+        if (h->opt_timepar == 0 || h->P.T > 256 || (h->P.cost_flags & MPPI_COST_MASK) != 0 || h->P.K > (1 << 20)) return MPPI_OK;
+        // measured, T = 256 (8 steps per lane): the arm still wins at K = 8192 (115 vs 117 us), the point mass only up to ~2048
+        const int auto_max = ARM_MODEL ? kTpAutoMaxSamplesArm : (h->P.T > 128 ? kTpAutoMaxSamplesDroneLong : kTpAutoMaxSamplesDrone);
+        if (h->opt_timepar < 0 && h->P.K > auto_max) return MPPI_OK;
         constexpr bool ARM = (MODEL == MPPI_MODEL_ARM7);
         const bool baked = ARM && h->baked_fk;
         const bool r7 = h->philox_rounds == 7 && !d_noise;
-        const int spl = h->P.T <= 32 ? 1 : h->P.T <= 64 ? 2 : 4;       // horizon steps per lane
-        const int slot = (baked ? 1 : 0) + (d_noise ? 2 : 0) + (r7 ? 4 : 0) + 8 * (spl == 1 ? 0 : spl == 2 ? 1 : 2);
+        const int spl = h->P.T <= 32 ? 1 : h->P.T <= 64 ? 2 : h->P.T <= 128 ? 4 : 8;       // horizon steps per lane
+        const int slot = (baked ? 1 : 0) + (d_noise ? 2 : 0) + (r7 ? 4 : 0) + 8 * (spl == 1 ? 0 : spl == 2 ? 1 : spl == 4 ? 2 : 3);
         if (d_noise) {
             if (baked) return launch_tp_spl<MODEL, 1, ARM, 10>(h, slot, spl, d_u_nom, d_noise, d_u_new, d_out, st, X, launched);
             return launch_tp_spl<MODEL, 1, false, 10>(h, slot, spl, d_u_nom, d_noise, d_u_new, d_out, st, X, launched);

@@ -93,7 +93,7 @@ def test_single_launch_step_equals_the_two_kernel_step(name, K, T, rounds, nativ
 
 
 def test_single_launch_falls_back_when_the_grid_cannot_be_resident(native):
-    """K beyond 128 x resident blocks (or T > 128) keeps the two-kernel path; both are the same step."""
+    """K beyond the resident rows (or T > 256) keeps the two-kernel path; both are the same step."""
     s, _ = _run(native, native.MODEL_WB11, 148 * 4 * 128 + 128, 16, 50.0, steps=1)
     assert s.last_path == "two_kernels"
     s, _ = _run(native, native.MODEL_DRONE3, 1024, 200, 50.0, steps=1, time_parallel=0)
@@ -102,8 +102,8 @@ def test_single_launch_falls_back_when_the_grid_cannot_be_resident(native):
     assert s.last_path == "fused"
     s, _ = _run(native, native.MODEL_DRONE3, 1024, 100, 50.0, steps=1)                          # T <= 128: four steps per lane
     assert s.last_path == "time_parallel"
-    s, _ = _run(native, native.MODEL_DRONE3, 1024, 129, 50.0, steps=1, time_parallel=1)         # T > 128: never time-parallel
-    assert s.last_path == "two_kernels"
+    s, _ = _run(native, native.MODEL_DRONE3, 1024, 129, 50.0, steps=1)                          # T <= 256: eight steps per lane
+    assert s.last_path == "time_parallel"
     s, _ = _run(native, native.MODEL_ARM7, 20000, 32, 0.1, steps=1, fused=1)                   # auto, K beyond the time-parallel range
     assert s.last_path == "fused"
     s, _ = _run(native, native.MODEL_ARM7, 20000, 32, 0.1, steps=1)                            # library defaults
@@ -116,7 +116,7 @@ def test_single_launch_falls_back_when_the_grid_cannot_be_resident(native):
 
 @pytest.mark.parametrize("rounds", [10, 7])
 @pytest.mark.parametrize("K,T", [(1, 8), (3, 33), (100, 32), (1000, 30), (1024, 30), (4099, 64), (40000, 20), (517, 65), (1000, 100),
-                                 (300, 128)])
+                                 (300, 128), (200, 129), (520, 256)])
 @pytest.mark.parametrize("name", ["arm", "drone"])
 def test_time_parallel_step_equals_the_thread_per_sample_step(name, K, T, rounds, native, oracle):
     model = _mid(native, name)
