@@ -53,8 +53,18 @@ constexpr int kNoiseStages = 4;
 // Models whose horizon step is a short dependent chain (point mass, rigid body: ~100 instructions behind one Philox
 // call) are latency-bound at any occupancy this path reaches; their noise is generated kNoiseBatch steps at a time so
 // the Philox / Box-Muller chains of several steps overlap (independent counters), then the steps run back to back.
+#ifndef MPPI_WB_NB
+#define MPPI_WB_NB 1
+#endif
+#ifndef MPPI_WB_PREFETCH
+#define MPPI_WB_PREFETCH 1
+#endif
+#ifndef MPPI_ARM_PREFETCH
+#define MPPI_ARM_PREFETCH 0
+#endif
 template <int MODEL, int NOISE> struct NoiseBatch {
-    static constexpr int value = (NOISE == 0 && (MODEL == MPPI_MODEL_DRONE3 || MODEL == MPPI_MODEL_QUAD4)) ? 4 : 1;
+    static constexpr int value = (NOISE == 0 && (MODEL == MPPI_MODEL_DRONE3 || MODEL == MPPI_MODEL_QUAD4)) ? 4
+                               : (NOISE == 0 && MODEL == MPPI_MODEL_WB11) ? MPPI_WB_NB : 1;
 };
 
 // The body of K2, shared by rollout_cost_kernel and the single-launch step_fused_kernel.  Returns the sample's cost
@@ -126,7 +136,7 @@ __device__ __forceinline__ float rollout_body(const StepParams &P, const DynBloc
 
     // ---- per-sample state in registers
     float dcv[3], dcq[3], dvp[3];                  // DRONE3 double integrator
-    f2 cum_v[4], cum_q[4], vprev[4];               // arm joints in pairs (pairA, pairB)
+    f2 cum_v[4], cum_q[4];                         // arm joints in pairs (pairA, pairB)
     f2 q0p[4], qd0p[4];                            // measured joint state in the same pairing (uniform)
     QuadState<float> qs;
     Pose3 base0;                                   // chain root pose composed with C0 (uniform, loop-invariant for ARM7)
@@ -140,7 +150,7 @@ __device__ __forceinline__ float rollout_body(const StepParams &P, const DynBloc
             const int ja = pairA(i), jb = pairB(i);
             q0p[i] = f2(D.state[QOFF + ja], jb >= 0 ? D.state[QOFF + jb] : 0.f);
             qd0p[i] = f2(D.state[QOFF + 7 + ja], jb >= 0 ? D.state[QOFF + 7 + jb] : 0.f);
-            cum_v[i] = f2(0.f); cum_q[i] = f2(0.f); vprev[i] = qd0p[i];
+            cum_v[i] = f2(0.f); cum_q[i] = f2(0.f);
         }
     }
     if constexpr (MODEL == MPPI_MODEL_ARM7) {
@@ -159,12 +169,8 @@ __device__ __forceinline__ float rollout_body(const StepParams &P, const DynBloc
     float term_d = 0.f;
 
     constexpr int NB = NoiseBatch<MODEL, NOISE>::value;
-    for (int t0 = 0; t0 < P.T; t0 += NB) {
-      f2 a02b[NB][NCH], a13b[NB][NCH];
-#pragma unroll
-      for (int jb = 0; jb < NB; ++jb) {
-        const int t = min(t0 + jb, P.T - 1);
-        f2 *a02 = a02b[jb], *a13 = a13b[jb];
+    // controls of horizon step t into the pair layout (a02, a13)
+    auto load_controls = [&](const int t, f2 *a02, f2 *a13) {
         // ---- controls of this step: v = u + noise  (S/mppi_solver/mppi.py:130).  Inputs 4c..4c+3 arrive
         // as the pairs (4c, 4c+2) and (4c+1, 4c+3).
         if constexpr (NOISE == 2) mbar_wait(&s_full[t % kNoiseStages], (t / kNoiseStages) & 1);
@@ -209,6 +215,22 @@ __device__ __forceinline__ float rollout_body(const StepParams &P, const DynBloc
                              noise + (static_cast<size_t>(t + kNoiseStages) * P.K + k0_blk) * NU, tile_bytes, &s_full[st]);
             }
         }
+    };
+    // whole body: the noise of step t + 1 is generated while step t runs (independent instruction streams in one
+    // basic block: the Box-Muller MUFU work overlaps the FK arithmetic inside every warp, not only across warps)
+    constexpr bool PREFETCH = PHILOX && NB == 1 && !EXTRA &&
+                              ((MODEL == MPPI_MODEL_WB11 && MPPI_WB_PREFETCH != 0) || (MODEL == MPPI_MODEL_ARM7 && MPPI_ARM_PREFETCH != 0));
+    f2 nx02[NCH], nx13[NCH];
+    if constexpr (PREFETCH) load_controls(0, nx02, nx13);
+    for (int t0 = 0; t0 < P.T; t0 += NB) {
+      f2 a02b[NB][NCH], a13b[NB][NCH];
+      if constexpr (PREFETCH) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) { a02b[0][c] = nx02[c]; a13b[0][c] = nx13[c]; }
+        load_controls(min(t0 + 1, P.T - 1), nx02, nx13);
+      } else {
+#pragma unroll
+        for (int jb = 0; jb < NB; ++jb) load_controls(min(t0 + jb, P.T - 1), a02b[jb], a13b[jb]);
       }
 #pragma unroll
       for (int jb = 0; jb < NB; ++jb) {
@@ -254,9 +276,9 @@ __device__ __forceinline__ float rollout_body(const StepParams &P, const DynBloc
             f2 qp[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const f2 dq = vfma(vprev[i], f2(P.dt), vmul(vmul(f2(0.5f), aj[i]), f2(P.dt2)));
+                const f2 vprev = vadd(cum_v[i], qd0p[i]);          // V_{t-1} (0 + qd0 at t = 0), rebuilt instead of carried
+                const f2 dq = vfma(vprev, f2(P.dt), vmul(vmul(f2(0.5f), aj[i]), f2(P.dt2)));
                 cum_v[i] = vfma(aj[i], f2(P.dt), cum_v[i]);
-                vprev[i] = vadd(cum_v[i], qd0p[i]);
                 cum_q[i] = vadd(cum_q[i], dq);
                 qp[i] = vadd(cum_q[i], q0p[i]);
             }
