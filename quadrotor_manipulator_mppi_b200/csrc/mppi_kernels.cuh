@@ -56,6 +56,15 @@ constexpr int kNoiseStages = 4;
 #ifndef MPPI_WB_NB
 #define MPPI_WB_NB 1
 #endif
+#ifndef MPPI_SMALL_NB
+#define MPPI_SMALL_NB 4
+#endif
+#ifndef MPPI_SMALL_NOBREAK
+#define MPPI_SMALL_NOBREAK 1
+#endif
+#ifndef MPPI_SMALL_PREFETCH
+#define MPPI_SMALL_PREFETCH 0
+#endif
 #ifndef MPPI_WB_PREFETCH
 #define MPPI_WB_PREFETCH 1
 #endif
@@ -63,7 +72,7 @@ constexpr int kNoiseStages = 4;
 #define MPPI_ARM_PREFETCH 0
 #endif
 template <int MODEL, int NOISE> struct NoiseBatch {
-    static constexpr int value = (NOISE == 0 && (MODEL == MPPI_MODEL_DRONE3 || MODEL == MPPI_MODEL_QUAD4)) ? 4
+    static constexpr int value = (NOISE == 0 && (MODEL == MPPI_MODEL_DRONE3 || MODEL == MPPI_MODEL_QUAD4)) ? MPPI_SMALL_NB
                                : (NOISE == 0 && MODEL == MPPI_MODEL_WB11) ? MPPI_WB_NB : 1;
 };
 
@@ -218,16 +227,24 @@ __device__ __forceinline__ float rollout_body(const StepParams &P, const DynBloc
     };
     // whole body: the noise of step t + 1 is generated while step t runs (independent instruction streams in one
     // basic block: the Box-Muller MUFU work overlaps the FK arithmetic inside every warp, not only across warps)
-    constexpr bool PREFETCH = PHILOX && NB == 1 && !EXTRA &&
-                              ((MODEL == MPPI_MODEL_WB11 && MPPI_WB_PREFETCH != 0) || (MODEL == MPPI_MODEL_ARM7 && MPPI_ARM_PREFETCH != 0));
-    f2 nx02[NCH], nx13[NCH];
-    if constexpr (PREFETCH) load_controls(0, nx02, nx13);
+    constexpr bool PREFETCH = PHILOX && !EXTRA &&
+                              ((MODEL == MPPI_MODEL_WB11 && MPPI_WB_PREFETCH != 0) || (MODEL == MPPI_MODEL_ARM7 && MPPI_ARM_PREFETCH != 0) ||
+                               ((MODEL == MPPI_MODEL_DRONE3 || MODEL == MPPI_MODEL_QUAD4) && MPPI_SMALL_PREFETCH != 0));
+    f2 nx02[NB][NCH], nx13[NB][NCH];
+    if constexpr (PREFETCH) {
+#pragma unroll
+        for (int jb = 0; jb < NB; ++jb) load_controls(min(jb, P.T - 1), nx02[jb], nx13[jb]);
+    }
     for (int t0 = 0; t0 < P.T; t0 += NB) {
       f2 a02b[NB][NCH], a13b[NB][NCH];
       if constexpr (PREFETCH) {
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) { a02b[0][c] = nx02[c]; a13b[0][c] = nx13[c]; }
-        load_controls(min(t0 + 1, P.T - 1), nx02, nx13);
+        for (int jb = 0; jb < NB; ++jb) {
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) { a02b[jb][c] = nx02[jb][c]; a13b[jb][c] = nx13[jb][c]; }
+        }
+#pragma unroll
+        for (int jb = 0; jb < NB; ++jb) load_controls(min(t0 + NB + jb, P.T - 1), nx02[jb], nx13[jb]);
       } else {
 #pragma unroll
         for (int jb = 0; jb < NB; ++jb) load_controls(min(t0 + jb, P.T - 1), a02b[jb], a13b[jb]);
@@ -235,7 +252,8 @@ __device__ __forceinline__ float rollout_body(const StepParams &P, const DynBloc
 #pragma unroll
       for (int jb = 0; jb < NB; ++jb) {
         const int t = t0 + jb;
-        if (NB > 1 && t >= P.T) break;
+        if (NB > 1 && !MPPI_SMALL_NOBREAK && t >= P.T) break;
+        const bool valid = (NB == 1) || t < P.T;       // past the horizon (ragged last batch): nothing is accumulated
         const f2 *a02 = a02b[jb], *a13 = a13b[jb];
         // scalar view: input i lives in (i & 1 ? a13 : a02)[i >> 2], lane (i >> 1) & 1
         auto input = [&](int i) -> float { return lane((i & 1) ? a13[i >> 2] : a02[i >> 2], (i >> 1) & 1); };
@@ -254,13 +272,13 @@ __device__ __forceinline__ float rollout_body(const StepParams &P, const DynBloc
                 const float e = (dcq[i] + D.state[i]) - D.drone_target[i];
                 sq = fmaf(e, e, sq);
             }
-            if (last) term_d = sq; else Sd += sq;
+            if (last) term_d = sq; else if (valid) Sd += sq;
         }
         if constexpr (HAS_QUAD) {
             quad_advance<false>(qs, input(0), input(1), input(2), input(3), P.dt, P.quad);   // sin/cos refreshed below
             const float ex = qs.p[0] - D.drone_target[0], ey = qs.p[1] - D.drone_target[1], ez = qs.p[2] - D.drone_target[2];
             const float sq = fmaf(ex, ex, fmaf(ey, ey, ez * ez));
-            if (last) term_d = sq; else Sd += sq;
+            if (last) term_d = sq; else if (valid) Sd += sq;
         }
         if constexpr (MODEL == MPPI_MODEL_QUAD4) {
             f2 s2, c2;
