@@ -306,19 +306,27 @@ __device__ __forceinline__ void sincos_pi(V x, V &s, V &c)
     c = vxor(cr, flip);
 }
 
-// sin / cos on the MUFU unit for the two UNPINNED models (QUAD4, WB11): reduce by 2 pi (Cody-Waite, 2 terms) to [-pi, pi],
-// then sin.approx / cos.approx (max abs error 2^-20.9 ~ 5e-7 on that range against 1.4e-7 for sincos_pi).  The FMA pipe is
-// what bounds the rollout kernel and the XU pipe is two-thirds idle: ten polynomial evaluations per whole-body step are
-// 150 of its ~600 FMA-pipe cycles.  The pinned models (ARM7, DRONE3) keep the polynomial: their costs are held to 2e-6
-// of the reference's and the soft-min amplifies cost errors by 1/lambda.
+// sin / cos on the MUFU unit for the two UNPINNED models (QUAD4, WB11): sin.approx / cos.approx (max abs error 2^-20.9 ~ 5e-7
+// on [-pi, pi] against 1.4e-7 for sincos_pi).  The FMA pipe / register operand bandwidth bound the rollout kernel and the
+// XU pipe overlaps them (tools/probe_pipes2.cu): ten polynomial evaluations per whole-body step were 150 of its ~600
+// FMA-pipe cycles.  NO range reduction here: the instruction's own x / 2 pi step loses |x| * 2^-23 turns, so the callers
+// keep their arguments within a turn or so -- the Euler angles are wrapped to [-pi, pi] by quad_advance every step, and the
+// joint angles are measured from whole_turns_removed(q0) (one reduction per rollout instead of one per horizon step).
+// The pinned models (ARM7, DRONE3) keep the polynomial: their costs are held to 2e-6 of the reference's and the soft-min
+// amplifies cost errors by 1/lambda.
 template <class V>
 __device__ __forceinline__ void sincos_mufu(V x, V &s, V &c)
 {
+    s = vmap(x, [](float a) { float y; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(a)); return y; });
+    c = vmap(x, [](float a) { float y; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(a)); return y; });
+}
+// x - 2 pi rint(x / 2 pi), two-term Cody-Waite: the trig argument base of a joint whose angle is q0 + (a small excursion)
+template <class V>
+__device__ __forceinline__ V whole_turns_removed(V x)
+{
     const V k = vadd(vfma(x, V(kInvTwoPi), V(12582912.0f)), V(-12582912.0f));      // rint(x / 2 pi)
     V r = vfma(k, V(-6.28318548202514648f), x);
-    r = vfma(k, V(1.74845553146951715e-7f), r);
-    s = vmap(r, [](float a) { float y; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(a)); return y; });
-    c = vmap(r, [](float a) { float y; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(a)); return y; });
+    return vfma(k, V(1.74845553146951715e-7f), r);
 }
 template <bool FAST, class V>
 __device__ __forceinline__ void sincos_sel(V x, V &s, V &c)
@@ -532,7 +540,9 @@ __device__ __forceinline__ V wrap_pi(V a)
     return vfma(V(-kTwoPi), k, a);
 }
 
-template <bool REFRESH = true, class V>
+// WRAP = false (the MUFU sin / cos of the unpinned models): the angles only ever enter through sin / cos, whose own
+// range step makes the per-step wrap redundant within a horizon; quad_load removes the whole turns of the measured angles.
+template <bool REFRESH = true, bool WRAP = true, class V>
 __device__ __forceinline__ void quad_advance(QuadState<V> &s, V F, V tx, V ty, V tz, float dt, const float *qp)
 {
     const float inv_m = rcp_approx(qp[0]), kd = qp[4], gz = qp[5];
@@ -551,9 +561,10 @@ __device__ __forceinline__ void quad_advance(QuadState<V> &s, V F, V tx, V ty, V
     const V ax = vmul(vfma(r02, F, vneg(vmul(V(kd), s.v[0]))), V(inv_m));
     const V ay = vmul(vfma(r12, F, vneg(vmul(V(kd), s.v[1]))), V(inv_m));
     const V az = vfma(vfma(r22, F, vneg(vmul(V(kd), s.v[2]))), V(inv_m), V(gz));
-    s.rpy[0] = wrap_pi(vfma(V(dt), dphi, s.rpy[0]));
-    s.rpy[1] = wrap_pi(vfma(V(dt), dth, s.rpy[1]));
-    s.rpy[2] = wrap_pi(vfma(V(dt), dpsi, s.rpy[2]));
+    s.rpy[0] = vfma(V(dt), dphi, s.rpy[0]);
+    s.rpy[1] = vfma(V(dt), dth, s.rpy[1]);
+    s.rpy[2] = vfma(V(dt), dpsi, s.rpy[2]);
+    if constexpr (WRAP) { s.rpy[0] = wrap_pi(s.rpy[0]); s.rpy[1] = wrap_pi(s.rpy[1]); s.rpy[2] = wrap_pi(s.rpy[2]); }
     s.v[0] = vfma(V(dt), ax, s.v[0]); s.v[1] = vfma(V(dt), ay, s.v[1]); s.v[2] = vfma(V(dt), az, s.v[2]);
     s.p[0] = vfma(V(dt), s.v[0], s.p[0]); s.p[1] = vfma(V(dt), s.v[1], s.p[1]); s.p[2] = vfma(V(dt), s.v[2], s.p[2]);
     if constexpr (REFRESH) {          // callers that batch the sin/cos of several angles pass REFRESH = false
@@ -567,7 +578,7 @@ template <class V>
 __device__ __forceinline__ void quad_load(QuadState<V> &s, const float *st)
 {
 #pragma unroll
-    for (int i = 0; i < 3; ++i) { s.p[i] = V(st[i]); s.rpy[i] = V(st[3 + i]); s.v[i] = V(st[6 + i]); s.w[i] = V(st[9 + i]); }
+    for (int i = 0; i < 3; ++i) { s.p[i] = V(st[i]); s.rpy[i] = wrap_pi(V(st[3 + i])); s.v[i] = V(st[6 + i]); s.w[i] = V(st[9 + i]); }
     sincos_pi(s.rpy[0], s.sphi, s.cphi);
     sincos_pi(s.rpy[1], s.sth, s.cth);
     sincos_pi(s.rpy[2], s.spsi, s.cpsi);

@@ -56,6 +56,12 @@ constexpr int kNoiseStages = 4;
 #ifndef MPPI_WB_NB
 #define MPPI_WB_NB 1
 #endif
+#ifndef MPPI_WB_UNROLL
+#define MPPI_WB_UNROLL 1
+#endif
+#ifndef MPPI_ARM_UNROLL
+#define MPPI_ARM_UNROLL 1
+#endif
 #ifndef MPPI_SMALL_NB
 #define MPPI_SMALL_NB 4
 #endif
@@ -147,6 +153,7 @@ __device__ __forceinline__ float rollout_body(const StepParams &P, const DynBloc
     float dcv[3], dcq[3], dvp[3];                  // DRONE3 double integrator
     f2 cum_v[4], cum_q[4];                         // arm joints in pairs (pairA, pairB)
     f2 q0p[4], qd0p[4];                            // measured joint state in the same pairing (uniform)
+    f2 q0t[4];                                     // FAST_TRIG: q0 less its whole turns, the base of the sin / cos arguments
     QuadState<float> qs;
     Pose3 base0;                                   // chain root pose composed with C0 (uniform, loop-invariant for ARM7)
     if constexpr (MODEL == MPPI_MODEL_DRONE3) {
@@ -160,6 +167,7 @@ __device__ __forceinline__ float rollout_body(const StepParams &P, const DynBloc
             q0p[i] = f2(D.state[QOFF + ja], jb >= 0 ? D.state[QOFF + jb] : 0.f);
             qd0p[i] = f2(D.state[QOFF + 7 + ja], jb >= 0 ? D.state[QOFF + 7 + jb] : 0.f);
             cum_v[i] = f2(0.f); cum_q[i] = f2(0.f);
+            q0t[i] = FAST_TRIG ? whole_turns_removed(q0p[i]) : q0p[i];
         }
     }
     if constexpr (MODEL == MPPI_MODEL_ARM7) {
@@ -235,6 +243,10 @@ __device__ __forceinline__ float rollout_body(const StepParams &P, const DynBloc
 #pragma unroll
         for (int jb = 0; jb < NB; ++jb) load_controls(min(jb, P.T - 1), nx02[jb], nx13[jb]);
     }
+    constexpr int UNROLL_T = (MODEL == MPPI_MODEL_WB11) ? MPPI_WB_UNROLL : (MODEL == MPPI_MODEL_ARM7) ? MPPI_ARM_UNROLL : 1;
+#if MPPI_WB_UNROLL > 1 || MPPI_ARM_UNROLL > 1
+#pragma unroll UNROLL_T
+#endif
     for (int t0 = 0; t0 < P.T; t0 += NB) {
       f2 a02b[NB][NCH], a13b[NB][NCH];
       if constexpr (PREFETCH) {
@@ -265,7 +277,7 @@ __device__ __forceinline__ float rollout_body(const StepParams &P, const DynBloc
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
                 const float ai = input(i);
-                const float dq = fmaf(dvp[i], P.dt, (0.5f * ai) * P.dt2);
+                const float dq = fmaf(dvp[i], P.dt, ai * (0.5f * P.dt2));      // (0.5 a) dt^2 exactly: halving is exact
                 dcv[i] = fmaf(ai, P.dt, dcv[i]);
                 dvp[i] = dcv[i] + D.state[3 + i];
                 dcq[i] += dq;
@@ -275,7 +287,7 @@ __device__ __forceinline__ float rollout_body(const StepParams &P, const DynBloc
             if (last) term_d = sq; else if (valid) Sd += sq;
         }
         if constexpr (HAS_QUAD) {
-            quad_advance<false>(qs, input(0), input(1), input(2), input(3), P.dt, P.quad);   // sin/cos refreshed below
+            quad_advance<false, !FAST_TRIG>(qs, input(0), input(1), input(2), input(3), P.dt, P.quad);   // sin/cos refreshed below
             const float ex = qs.p[0] - D.drone_target[0], ey = qs.p[1] - D.drone_target[1], ez = qs.p[2] - D.drone_target[2];
             const float sq = fmaf(ex, ex, fmaf(ey, ey, ez * ez));
             if (last) term_d = sq; else if (valid) Sd += sq;
@@ -291,14 +303,15 @@ __device__ __forceinline__ float rollout_body(const StepParams &P, const DynBloc
             constexpr int C1 = ARM0 / 4;
             const f2 aj[4] = {a02[C1], a13[C1], a02[C1 + 1], a13[C1 + 1]};
             // S/sampling/standard_normal_noise.py:32-50, two joints per instruction
-            f2 qp[4];
+            f2 qp[4], qt[4];                     // joint angles; the same less q0's whole turns (sin / cos arguments)
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const f2 vprev = vadd(cum_v[i], qd0p[i]);          // V_{t-1} (0 + qd0 at t = 0), rebuilt instead of carried
-                const f2 dq = vfma(vprev, f2(P.dt), vmul(vmul(f2(0.5f), aj[i]), f2(P.dt2)));
+                const f2 dq = vfma(vprev, f2(P.dt), vmul(aj[i], f2(0.5f * P.dt2)));   // (0.5 a) dt^2 exactly: halving is exact
                 cum_v[i] = vfma(aj[i], f2(P.dt), cum_v[i]);
                 cum_q[i] = vadd(cum_q[i], dq);
                 qp[i] = vadd(cum_q[i], q0p[i]);
+                qt[i] = FAST_TRIG ? vadd(cum_q[i], q0t[i]) : qp[i];
             }
             if constexpr (EXTRA) {
                 // covar_cost.py:20-25 (u^T Sigma^-1 v), action_cost.py:15-25, joint_space_cost.py:18-77; gamma^t discount
@@ -334,15 +347,15 @@ __device__ __forceinline__ float rollout_body(const StepParams &P, const DynBloc
             f2 s2, c2;
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
-                sincos_sel<FAST_TRIG>(qp[i], s2, c2);
+                sincos_sel<FAST_TRIG>(qt[i], s2, c2);
                 sq[pairA(i)] = s2.v.x; cq[pairA(i)] = c2.v.x; sq[pairB(i)] = s2.v.y; cq[pairB(i)] = c2.v.y;
             }
             Pose3 Tp;
             if constexpr (MODEL == MPPI_MODEL_ARM7) {
-                sincos_sel<FAST_TRIG>(qp[3].v.x, sq[5], cq[5]);
+                sincos_sel<FAST_TRIG>(qt[3].v.x, sq[5], cq[5]);
                 Tp = base0;
             } else {
-                sincos_sel<FAST_TRIG>(f2(qp[3].v.x, qs.rpy[0]), s2, c2);
+                sincos_sel<FAST_TRIG>(f2(qt[3].v.x, qs.rpy[0]), s2, c2);
                 sq[5] = s2.v.x; cq[5] = c2.v.x; qs.sphi = s2.v.y; qs.cphi = c2.v.y;
                 sincos_sel<FAST_TRIG>(f2(qs.rpy[1], qs.rpy[2]), s2, c2);
                 qs.sth = s2.v.x; qs.cth = c2.v.x; qs.spsi = s2.v.y; qs.cpsi = c2.v.y;
@@ -1121,7 +1134,7 @@ step_tp_kernel(const __grid_constant__ StepParams P, const __grid_constant__ Dyn
 #pragma unroll
             for (int s = 0; s < SPL; ++s) {
                 const float vprev = ((s == 0) ? ex_v : ex_v + lcv[s - 1]) + v0;
-                cq += fmaf(vprev, P.dt, (0.5f * a_i[s]) * P.dt2);
+                cq += fmaf(vprev, P.dt, a_i[s] * (0.5f * P.dt2));
                 lcq[s] = cq;
             }
             const float ex_q = warp_excl_scan(cq, lane);

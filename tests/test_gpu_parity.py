@@ -207,6 +207,53 @@ def test_unpinned_models_against_the_torch_restatement_fixtures(name, native):
         assert rel_inf(s.u_prev.cpu().numpy(), g[f"u_new_{i}"]) < TOL
 
 
+def test_wound_up_angles_keep_the_unpinned_models_on_the_oracle(native, oracle):
+    """The MUFU sin / cos of the unpinned models carry no per-step range reduction: joint angles are measured from
+    q0 less its whole turns and the Euler angles are wrapped once at load.  Continuous joints several turns away
+    from zero and Euler angles outside [-pi, pi] must therefore still give the oracle's costs (libm sinf / cosf of
+    the wound-up float angle)."""
+    from quadrotor_manipulator_mppi_b200.core import NativeSolver
+    K, T = 2048, 48
+    qp = (20.2, 1 / 1.57, 1 / 3.93, 1 / 2.59, 0.0, -9.81)
+    turns = np.array([3, -2, 5, 0, -7, 1, 4], np.float32)
+    for wound in (False, True):
+        s = NativeSolver(native.MODEL_WB11, n_samples=K, n_horizon=T, seed=5, quad_params=qp)
+        state = np.zeros(native.MODEL_STATE[native.MODEL_WB11], np.float32)
+        state[2] = 2.1
+        state[3:6] = [0.05, -0.03, 0.4]
+        state[12:19] = oracle.Q_HOME
+        if wound:
+            state[12:19] += np.float32(2 * np.pi) * turns
+            state[3:6] += np.float32(2 * np.pi) * np.array([1, -1, 2], np.float32)
+        s.set_state(state)
+        u0 = np.zeros((T, 11), np.float32)
+        u0[:, 0] = 20.2 * 9.81
+        s.u_prev = torch.from_numpy(u0)
+        s.step(None, step_counter=3)
+        S = s.costs.cpu().numpy()
+        noise = s.generate_noise(3).cpu().numpy()
+        want = oracle.wb_costs(noise, u0, state[:12], state[12:19], state[19:26])
+        rel = np.abs(S.astype(np.float64) - want) / np.abs(want)
+        # the wound-up float angles themselves carry 2 pi k * 2^-24 of rounding; both sides see the same floats
+        assert rel.max() < 1e-5, (wound, rel.max())
+        s.close()
+        sq = NativeSolver(native.MODEL_QUAD4, n_samples=K, n_horizon=T, seed=5)
+        st = np.zeros(native.MODEL_STATE[native.MODEL_QUAD4], np.float32)
+        st[2] = 2.1
+        st[3:6] = [0.05, -0.03, 0.4]
+        if wound:
+            st[3:6] += np.float32(2 * np.pi) * np.array([1, -1, 2], np.float32)
+        sq.set_state(st)
+        uq = np.zeros((T, 4), np.float32)
+        uq[:, 0] = 14.7 * 9.81
+        sq.u_prev = torch.from_numpy(uq)
+        sq.step(None, step_counter=3)
+        Sq = sq.costs.cpu().numpy()
+        wantq = oracle.quad_costs(sq.generate_noise(3).cpu().numpy(), uq, st)
+        assert (np.abs(Sq.astype(np.float64) - wantq) / np.abs(wantq)).max() < 1e-5, wound
+        sq.close()
+
+
 # ------------------------------------------------------------------ in-kernel Philox
 @pytest.mark.parametrize("rounds", [10, 7])
 def test_philox_noise_matches_oracle_and_is_self_consistent(rounds, oracle, native):

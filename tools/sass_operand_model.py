@@ -1,0 +1,148 @@
+#!/usr/bin/env python
+"""Register-operand-bandwidth model of a kernel's hot loop, from its SASS (no GPU needed).
+
+    python tools/sass_operand_model.py OBJECT_OR_SO 'rollout_cost_kernel<3, 0, true, false, 7>' [--loop N]
+
+tools/probe_pipes2.cu measured on B200 that an SM sub-partition delivers TWO 32-bit register source operands per lane
+per cycle: FFMA with a constant / uniform operand issues every cycle, a three-register FFMA every 1.5, FFMA2 with three
+distinct register pairs every 3 (not 2), and MUFU (8 cycles) overlaps the FMA pipe fully.  So the cost of a warp
+instruction is max(pipe cycles, register source words / 2), and the bound of a loop is the larger of its issue slots, its
+per-pipe cycle sums and its total register reads / 2.  Operands served by the reuse cache (`.reuse` set by the previous
+reader of the same register in the same operand slot) are free.
+
+The hot loop is the N-th largest backward branch region (default: the largest).
+"""
+import re
+import subprocess
+import sys
+from collections import Counter
+
+FMA_PIPE = {"FFMA": 1, "FMUL": 1, "FADD": 1, "FFMA2": 2, "FMUL2": 2, "FADD2": 2, "IMAD": 2, "IMAD.WIDE": 4, "IMAD.HI": 4,
+            "HFMA2": 1, "IMAD.MOV": 1, "IMAD.SHL": 1, "IMAD.IADD": 1, "FSWZADD": 1}
+ALU_PIPE = {"LOP3", "SHF", "IADD3", "MOV", "SEL", "FSEL", "FMNMX", "ISETP", "FSETP", "PRMT", "LEA", "IABS", "I2FP", "F2FP", "PLOP3",
+            "FCHK", "IADD", "CS2R", "VIADD", "UMOV", "FMNMX3", "LOP", "POPC", "FLO", "BREV", "VIMNMX", "IMNMX", "SGXT", "BMSK", "P2R", "R2P"}
+XU = {"MUFU": 8, "F2I": 4, "I2F": 4, "F2F": 4, "FRND": 4}
+
+
+def function_sass(path, pattern):
+    txt = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True).stdout
+    for blk in txt.split("Function : ")[1:]:
+        mangled = blk.split("\n", 1)[0].strip()
+        name = subprocess.run(["c++filt", mangled], capture_output=True, text=True).stdout.strip()
+        if pattern in name:
+            return name, blk
+    raise SystemExit(f"no function matching {pattern!r}")
+
+
+def parse(blk):
+    ins = []
+    for m in re.finditer(r"/\*([0-9a-f]{4,5})\*/\s+(.*?);", blk):
+        text = m.group(2).strip()
+        pred = None
+        if text.startswith("@"):
+            pred, text = text.split(None, 1)
+        ins.append((int(m.group(1), 16), pred, text))
+    return ins
+
+
+def opcode_key(op):
+    parts = op.split(".")
+    if parts[0] == "IMAD" and len(parts) > 1 and parts[1] in ("WIDE", "HI", "MOV", "SHL", "IADD"):
+        return parts[0] + "." + parts[1]
+    return parts[0]
+
+
+def source_words(text):
+    """[(slot, register number, words, sets_reuse)] of the register SOURCE operands."""
+    op, _, rest = text.partition(" ")
+    ops = [o.strip() for o in rest.split(",")]
+    if not ops or ops == [""]:
+        return []
+    key = opcode_key(op)
+    n_dst = 1
+    if key in ("ISETP", "FSETP", "PLOP3"):
+        n_dst = 2
+    if key in ("ST", "STS", "STG", "STL", "RED", "BAR", "BRA", "EXIT", "BSSY", "BSYNC", "ATOMS", "ATOMG", "MEMBAR", "NOP", "WARPSYNC", "SYNCS", "UTMALDG", "UBLKCP"):
+        n_dst = 0
+    srcs = ops[n_dst:]
+    out = []
+    for slot, o in enumerate(srcs):
+        m = re.search(r"(?<![UP\w])R(\d+)((?:\.\w+)*)", o)
+        if not m or re.match(r"^-?\|?RZ", o.lstrip("-~|")):
+            continue
+        mods = m.group(2)
+        words = 2 if ("F32x2" in mods or ".64" in mods or (key in ("FFMA2", "FMUL2", "FADD2") and ".F32" not in mods.replace(".F32x2", ""))) else 1
+        if key == "IMAD.WIDE" and slot == 2:
+            words = 2                      # 64-bit addend
+        if "[" in o:                      # address register of a memory operand
+            words = 2 if ".64" in o else 1
+        out.append((slot, int(m.group(1)), words, ".reuse" in mods))
+    return out
+
+
+def main():
+    path, pattern = sys.argv[1], sys.argv[2]
+    nth = int(sys.argv[sys.argv.index("--loop") + 1]) if "--loop" in sys.argv else 0
+    name, blk = function_sass(path, pattern)
+    ins = parse(blk)
+    loops = []
+    for addr, pred, text in ins:
+        m = re.match(r"BRA(?:\.\w+)*\s+(?:P\d,\s*)?0x([0-9a-f]+)", text)
+        if m and int(m.group(1), 16) < addr:
+            loops.append((addr - int(m.group(1), 16), int(m.group(1), 16), addr))
+    loops.sort(reverse=True)
+    _, lo, hi = loops[nth]
+    body = [(a, p, t) for a, p, t in ins if lo <= a <= hi]
+    issue = len(body)
+    pipe = Counter()
+    reads = 0
+    reads_by = Counter()
+    cost_max = 0.0
+    counts = Counter()
+    reuse = {}                             # slot -> register kept in the reuse cache by the previous instruction
+    unknown = Counter()
+    for a, p, t in body:
+        op = t.split(" ", 1)[0]
+        key = opcode_key(op)
+        counts[key] += 1
+        srcs = source_words(t)
+        w = 0
+        new_reuse = {}
+        for slot, reg, words, sets in srcs:
+            if reuse.get(slot) != reg:
+                w += words
+            if sets:
+                new_reuse[slot] = reg
+        reuse = new_reuse
+        reads += w
+        if key in FMA_PIPE:
+            pc = FMA_PIPE[key]
+            pipe["fma"] += pc
+            reads_by["fma"] += w
+        elif key in XU:
+            pc = XU[key]
+            pipe["xu"] += pc
+            reads_by["xu"] += w
+            pc = 1
+        elif key in ALU_PIPE:
+            pc = 2 if key != "MOV" else 1
+            pipe["alu"] += 2
+            reads_by["alu"] += w
+        else:
+            pc = 1
+            pipe["other"] += 1
+            reads_by["other"] += w
+            unknown[key] += 1
+        cost_max += max(pc if key in FMA_PIPE else 1, w / 2.0)
+    print(name[:100])
+    print(f"loop 0x{lo:x}..0x{hi:x}: {issue} instructions")
+    print("opcode counts:", dict(counts.most_common(16)))
+    print("other-pipe opcodes:", dict(unknown))
+    print(f"pipe cycles per iteration: fma {pipe['fma']}, alu {pipe['alu']} (half-rate pipe), xu {pipe['xu']}")
+    print(f"register source words per iteration: {reads}  -> {reads / 2:.0f} cycles at 2 words/lane/cycle   by pipe: {dict(reads_by)}")
+    print(f"sum over instructions of max(FMA-pipe cycles or 1 issue slot, words/2): {cost_max:.0f} cycles")
+    print(f"lower bounds per warp-iteration per scheduler: issue {issue}, fma pipe {pipe['fma']}, xu {pipe['xu']}, operand bandwidth {reads / 2:.0f}")
+
+
+if __name__ == "__main__":
+    main()
