@@ -322,6 +322,22 @@ def dense_lambda(costs, target_ess: float = 2000.0) -> float:
     return hi
 
 
+def _operand_model(om, K_loc, T, k_ms, sm_mhz, sms=148):
+    """Predicted kernel time from the static register-operand model of the hot loop (tools/sass_operand_model.py, committed
+    in profiles/ncu_metrics.json): every warp instruction costs max(1 issue slot, its FMA-pipe cycles, its register source
+    words / 2) on its scheduler; warps of 32 samples are spread over 4 schedulers per SM."""
+    if not om or "serial_cost_cycles_per_warp_step" not in om or not sm_mhz:
+        return None
+    warp_steps_per_scheduler = (K_loc / 32.0) * T / (4 * sms)
+    pred_ms = om["serial_cost_cycles_per_warp_step"] * warp_steps_per_scheduler / (sm_mhz * 1e3)
+    bound_ms = max(om["issue_slots"], om["fma_pipe_cycles"], om["xu_pipe_cycles"], om["register_source_words"] / 2.0) \
+        * warp_steps_per_scheduler / (sm_mhz * 1e3)
+    return {**om, "sm_mhz": sm_mhz, "predicted_ms_serial": pred_ms, "measured_over_predicted": k_ms / pred_ms,
+            "perfect_overlap_bound_ms": bound_ms, "frac_of_overlap_bound": bound_ms / k_ms,
+            "note": "serial = no overlap between instructions of one scheduler; the bound = the busiest of issue, FMA pipe, XU pipe and "
+                    "operand bandwidth with perfect overlap"}
+
+
 def timed_steps(step_fn, n, stream, device, flush, before=None):
     """n steps, each bracketed by CUDA events on the launch stream (L2 flushed outside the events).  Returns ms[n]."""
     import torch
@@ -709,6 +725,7 @@ def run_native(args):
     except Exception:
         pass
     exe = prof.get("executed_flop_per_rollout_step")
+    clocks_mhz = clocks.summary().get("sm_mhz")         # median SM clock under load, sampled during the timed steps
     roofline = {"kernel": "rollout_cost_kernel", "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                 "frac": achieved / fp32_peak if fp32_peak else None, "traffic": prof.get("dram_bytes_per_launch"),
                 "peak_source": "FFMA probe measured in this run (mppi_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 entry; "
@@ -724,7 +741,11 @@ def run_native(args):
                 "issue_active_pct": prof.get("issue_active_pct"),
                 "executed_source": prof.get("source", "no ncu capture committed for this configuration (profiles/ncu_metrics.json)"),
                 "kernel_ms": k_ms, "share_of_step": k_ms / (k_ms + w_ms), "weighting_kernel_ms": w_ms,
-                "binding_limit": {"wb": "FP32 FMA pipe (FP32 + Philox IMAD.WIDE)", "arm": "FP32 FMA pipe (FP32 + Philox IMAD.WIDE)",
+                "operand_model": _operand_model(prof.get("operand_model"), K_loc, T, k_ms, clocks_mhz),
+                "binding_limit": {"wb": "register operand bandwidth + FMA pipe (FP32 + Philox IMAD.WIDE): 2 register source words per lane per cycle "
+                                        "(tools/probe_pipes2.cu), so a 3-register FFMA issues every 1.5 cycles and the 74 TFLOP/s FP32 peak needs "
+                                        "constant / uniform operands",
+                                  "arm": "register operand bandwidth + FMA pipe (FP32 + Philox IMAD.WIDE)",
                                   "quad": "dependent-issue latency of the per-step chain (Philox IMAD + MUFU Box-Muller + rigid-body step); FP32 is not the binding roofline for this model",
                                   "drone": "dependent-issue latency (Philox IMAD + MUFU); FP32 is not the binding roofline for this model"}[args.model]}
     # ---- HBM-bound weighting pass (re-read of a materialised [T][K][nu] noise tensor), timed alone.

@@ -60,7 +60,7 @@ constexpr int kNoiseStages = 4;
 #define MPPI_WB_UNROLL 1
 #endif
 #ifndef MPPI_ARM_UNROLL
-#define MPPI_ARM_UNROLL 1
+#define MPPI_ARM_UNROLL 2
 #endif
 #ifndef MPPI_SMALL_NB
 #define MPPI_SMALL_NB 4

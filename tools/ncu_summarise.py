@@ -19,6 +19,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 import ncu_flops  # noqa: E402
+import sass_operand_model  # noqa: E402
 
 # (kernel regex, grid) -> (bench key stem, rollout-steps per launch)
 CASES = [
@@ -124,6 +125,21 @@ def main():
                 entry["philox_pipe_share"] = a["philox_imad_pipe_share"]
                 entry["warp_instructions_per_warp_step"] = a["warp_instructions"] / (steps / 32) if "K32768" not in stem else None
                 entry["fma_pipe_cycles_model_per_warp_step"] = a["fma_pipe_cycles_model"] / (steps / 32) if "K32768" not in stem else None
+            # static register-operand model of the hot loop of the shipped library (tools/sass_operand_model.py):
+            # horizon steps per loop iteration = the noise batch (drone / quad 4) x the unroll factor (arm 2)
+            mm = re.search(r"<\\\(\?\(\?:int\\\)\)\?(\d), \\\(\?\(\?:int\\\)\)\?(\d)", rx)
+            try:
+                model_id, noise_id = int(mm.group(1)), int(mm.group(2))
+                pat = f"rollout_cost_kernel<{model_id}, {noise_id}, {'true' if model_id in (1, 3) else 'false'}, false, {rounds}>"
+                om = sass_operand_model.model(os.path.join(ROOT, "quadrotor_manipulator_mppi_b200", "libmppi_b200.so"), pat,
+                                              1 if (model_id == 1 and noise_id == 0) else 0)
+                per_iter = {(1, 0): 2, (2, 0): 4}.get((model_id, noise_id), 1)
+                entry["operand_model"] = {"serial_cost_cycles_per_warp_step": om["serial_cost_cycles"] / per_iter,
+                                          "issue_slots": om["instructions"] / per_iter, "fma_pipe_cycles": om["pipe"]["fma"] / per_iter,
+                                          "xu_pipe_cycles": om["pipe"]["xu"] / per_iter,
+                                          "register_source_words": om["register_source_words"] / per_iter}
+            except Exception as e:      # noqa: BLE001 -- the summary is still useful without the static model
+                entry["operand_model"] = {"error": str(e)}
             if stem.startswith("wb_injected"):
                 wn = [x for x in launches if "weighted_noise_kernel" in x["kernel"]]
                 if wn:

@@ -80,9 +80,8 @@ def source_words(text):
     return out
 
 
-def main():
-    path, pattern = sys.argv[1], sys.argv[2]
-    nth = int(sys.argv[sys.argv.index("--loop") + 1]) if "--loop" in sys.argv else 0
+def model(path, pattern, nth=0):
+    """Counts and cost sums of the nth-largest loop of the first function whose demangled name contains `pattern`."""
     name, blk = function_sass(path, pattern)
     ins = parse(blk)
     loops = []
@@ -93,22 +92,14 @@ def main():
     loops.sort(reverse=True)
     _, lo, hi = loops[nth]
     body = [(a, p, t) for a, p, t in ins if lo <= a <= hi]
-    issue = len(body)
-    pipe = Counter()
-    reads = 0
-    reads_by = Counter()
-    cost_max = 0.0
-    counts = Counter()
+    pipe, reads_by, counts, unknown = Counter(), Counter(), Counter(), Counter()
+    reads, cost_max = 0, 0.0
     reuse = {}                             # slot -> register kept in the reuse cache by the previous instruction
-    unknown = Counter()
     for a, p, t in body:
-        op = t.split(" ", 1)[0]
-        key = opcode_key(op)
+        key = opcode_key(t.split(" ", 1)[0])
         counts[key] += 1
-        srcs = source_words(t)
-        w = 0
-        new_reuse = {}
-        for slot, reg, words, sets in srcs:
+        w, new_reuse = 0, {}
+        for slot, reg, words, sets in source_words(t):
             if reuse.get(slot) != reg:
                 w += words
             if sets:
@@ -116,32 +107,36 @@ def main():
         reuse = new_reuse
         reads += w
         if key in FMA_PIPE:
-            pc = FMA_PIPE[key]
-            pipe["fma"] += pc
+            pipe["fma"] += FMA_PIPE[key]
             reads_by["fma"] += w
         elif key in XU:
-            pc = XU[key]
-            pipe["xu"] += pc
+            pipe["xu"] += XU[key]
             reads_by["xu"] += w
-            pc = 1
         elif key in ALU_PIPE:
-            pc = 2 if key != "MOV" else 1
             pipe["alu"] += 2
             reads_by["alu"] += w
         else:
-            pc = 1
             pipe["other"] += 1
             reads_by["other"] += w
             unknown[key] += 1
-        cost_max += max(pc if key in FMA_PIPE else 1, w / 2.0)
-    print(name[:100])
-    print(f"loop 0x{lo:x}..0x{hi:x}: {issue} instructions")
-    print("opcode counts:", dict(counts.most_common(16)))
-    print("other-pipe opcodes:", dict(unknown))
+        cost_max += max(FMA_PIPE.get(key, 1), w / 2.0)
+    return {"name": name, "loop": (lo, hi), "instructions": len(body), "counts": counts, "other": unknown, "pipe": pipe,
+            "register_source_words": reads, "words_by_pipe": reads_by, "serial_cost_cycles": cost_max}
+
+
+def main():
+    path, pattern = sys.argv[1], sys.argv[2]
+    nth = int(sys.argv[sys.argv.index("--loop") + 1]) if "--loop" in sys.argv else 0
+    m = model(path, pattern, nth)
+    pipe, reads = m["pipe"], m["register_source_words"]
+    print(m["name"][:100])
+    print(f"loop 0x{m['loop'][0]:x}..0x{m['loop'][1]:x}: {m['instructions']} instructions")
+    print("opcode counts:", dict(m["counts"].most_common(16)))
+    print("other-pipe opcodes:", dict(m["other"]))
     print(f"pipe cycles per iteration: fma {pipe['fma']}, alu {pipe['alu']} (half-rate pipe), xu {pipe['xu']}")
-    print(f"register source words per iteration: {reads}  -> {reads / 2:.0f} cycles at 2 words/lane/cycle   by pipe: {dict(reads_by)}")
-    print(f"sum over instructions of max(FMA-pipe cycles or 1 issue slot, words/2): {cost_max:.0f} cycles")
-    print(f"lower bounds per warp-iteration per scheduler: issue {issue}, fma pipe {pipe['fma']}, xu {pipe['xu']}, operand bandwidth {reads / 2:.0f}")
+    print(f"register source words per iteration: {reads}  -> {reads / 2:.0f} cycles at 2 words/lane/cycle   by pipe: {dict(m['words_by_pipe'])}")
+    print(f"sum over instructions of max(FMA-pipe cycles or 1 issue slot, words/2): {m['serial_cost_cycles']:.0f} cycles")
+    print(f"lower bounds per warp-iteration per scheduler: issue {m['instructions']}, fma pipe {pipe['fma']}, xu {pipe['xu']}, operand bandwidth {reads / 2:.0f}")
 
 
 if __name__ == "__main__":
