@@ -24,14 +24,19 @@ ALU_PIPE = {"LOP3", "SHF", "IADD3", "MOV", "SEL", "FSEL", "FMNMX", "ISETP", "FSE
 XU = {"MUFU": 8, "F2I": 4, "I2F": 4, "F2F": 4, "FRND": 4}
 
 
+_SASS = {}
+
+
 def function_sass(path, pattern):
-    txt = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True).stdout
-    for blk in txt.split("Function : ")[1:]:
-        mangled = blk.split("\n", 1)[0].strip()
-        name = subprocess.run(["c++filt", mangled], capture_output=True, text=True).stdout.strip()
+    if path not in _SASS:
+        txt = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True).stdout
+        blks = txt.split("Function : ")[1:]
+        names = subprocess.run(["c++filt"], input="\n".join(b.split("\n", 1)[0].strip() for b in blks), capture_output=True, text=True).stdout.split("\n")
+        _SASS[path] = list(zip(names, blks))
+    for name, blk in _SASS[path]:
         if pattern in name:
             return name, blk
-    raise SystemExit(f"no function matching {pattern!r}")
+    raise LookupError(f"no function matching {pattern!r}")
 
 
 def parse(blk):
