@@ -99,6 +99,10 @@ __device__ __forceinline__ float rollout_body(const StepParams &P, const DynBloc
 
     constexpr bool PHILOX = (NOISE == 0);
     constexpr bool FAST_TRIG = (MODEL == MPPI_MODEL_QUAD4 || MODEL == MPPI_MODEL_WB11);       // MUFU sin/cos: unpinned models only
+    // Unpinned whole body on the baked chain without the extra cost terms: the joints integrate as the state recurrence
+    // q += v dt + a dt^2/2, v += a dt (3 packed FMAs per joint pair) instead of the reference's two cumulative sums + q0
+    // (6 packed operations, kept bit for bit for the pinned arm).  Same discrete dynamics, different rounding (1e-7).
+    constexpr bool DIRECT = (MODEL == MPPI_MODEL_WB11) && BAKED && !EXTRA;
     extern __shared__ __align__(16) float s_unom[];              // [T][NU] | (NOISE == 2) noise tiles [kNoiseStages][128][NU]
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ __align__(8) uint64_t s_full[kNoiseStages];
@@ -120,7 +124,10 @@ __device__ __forceinline__ float rollout_body(const StepParams &P, const DynBloc
     // ---- injected noise through TMA: the block's samples [k0, k0 + nb) of row t are nb*NU contiguous floats
     const int k0_blk = blockIdx.x * kRolloutThreads;
     const int nb = min(kRolloutThreads, P.K - k0_blk);
-    float *s_tiles = s_unom + ((n_u + 3) & ~3);                  // 16-byte aligned behind the nominal sequence
+    // the same sequence once more in the pair layout the loop consumes: per step and chunk c one float4
+    // (u[4c], u[4c+2], u[4c+1], u[4c+3]), zero-padded -- one LDS.128 per chunk instead of nu scalar loads + pair moves
+    float *s_upair = s_unom + ((n_u + 3) & ~3);
+    float *s_tiles = s_upair + P.T * 4 * NCH;                    // 16-byte aligned behind both copies
     const uint32_t tile_bytes = static_cast<uint32_t>(nb) * NU * 4u;
     if constexpr (NOISE == 2) {
         if (threadIdx.x == 0) {
@@ -140,6 +147,12 @@ __device__ __forceinline__ float rollout_body(const StepParams &P, const DynBloc
         mbar_wait(&s_bar, 0);
     } else {
         for (int j = threadIdx.x; j < n_u; j += blockDim.x) s_unom[j] = u_nom[j];
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < P.T * 4 * NCH; j += blockDim.x) {
+        const int t = j / (4 * NCH), e = j - t * (4 * NCH);
+        const int i = (e & ~3) + ((e & 1) << 1) + ((e >> 1) & 1);          // slot (x, y, z, w) of chunk c <- input 4c + (0, 2, 1, 3)
+        s_upair[j] = i < NU ? s_unom[t * NU + i] : 0.f;
     }
     __syncthreads();
 
@@ -168,6 +181,7 @@ __device__ __forceinline__ float rollout_body(const StepParams &P, const DynBloc
             qd0p[i] = f2(D.state[QOFF + 7 + ja], jb >= 0 ? D.state[QOFF + 7 + jb] : 0.f);
             cum_v[i] = f2(0.f); cum_q[i] = f2(0.f);
             q0t[i] = FAST_TRIG ? whole_turns_removed(q0p[i]) : q0p[i];
+            if constexpr (DIRECT) { cum_q[i] = q0t[i]; cum_v[i] = qd0p[i]; }     // the state itself: (angle less whole turns, velocity)
         }
     }
     if constexpr (MODEL == MPPI_MODEL_ARM7) {
@@ -197,9 +211,12 @@ __device__ __forceinline__ float rollout_body(const StepParams &P, const DynBloc
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
             const int i0 = 4 * c, i1 = 4 * c + 1, i2 = 4 * c + 2, i3 = 4 * c + 3;
+            const float4 u4 = *reinterpret_cast<const float4 *>(s_upair + (t * NCH + c) * 4);
             if constexpr (PHILOX) {
                 f2 n02, n13;
                 normals_quad(unif, c, n02, n13);
+                // eps = sigma n is rounded on its own (it is a tensor in the reference, and the rollout on materialised noise
+                // must reproduce the in-kernel one bit for bit), then v = u + eps
                 a02[c] = vmul(f2(P.sigma[i0], i2 < NU ? P.sigma[i2] : 0.f), n02);
                 a13[c] = vmul(f2(i1 < NU ? P.sigma[i1] : 0.f, i3 < NU ? P.sigma[i3] : 0.f), n13);
             } else if constexpr (NOISE == 1) {
@@ -219,9 +236,8 @@ __device__ __forceinline__ float rollout_body(const StepParams &P, const DynBloc
                     a13[c] = f2(i1 < NU ? row[i1] : 0.f, i3 < NU ? row[i3] : 0.f);
                 }
             }
-            const float *un = s_unom + t * NU;
-            a02[c] = vadd(f2(un[i0], i2 < NU ? un[i2] : 0.f), a02[c]);
-            a13[c] = vadd(f2(i1 < NU ? un[i1] : 0.f, i3 < NU ? un[i3] : 0.f), a13[c]);
+            a02[c] = vadd(f2(u4.x, u4.y), a02[c]);
+            a13[c] = vadd(f2(u4.z, u4.w), a13[c]);
         }
         if constexpr (NOISE == 2) {
             __syncthreads();                       // every thread has taken its controls out of the stage
@@ -306,6 +322,12 @@ __device__ __forceinline__ float rollout_body(const StepParams &P, const DynBloc
             f2 qp[4], qt[4];                     // joint angles; the same less q0's whole turns (sin / cos arguments)
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
+                if constexpr (DIRECT) {
+                    cum_q[i] = vfma(aj[i], f2(0.5f * P.dt2), vfma(cum_v[i], f2(P.dt), cum_q[i]));
+                    cum_v[i] = vfma(aj[i], f2(P.dt), cum_v[i]);
+                    qp[i] = qt[i] = cum_q[i];
+                    continue;
+                }
                 const f2 vprev = vadd(cum_v[i], qd0p[i]);          // V_{t-1} (0 + qd0 at t = 0), rebuilt instead of carried
                 const f2 dq = vfma(vprev, f2(P.dt), vmul(aj[i], f2(0.5f * P.dt2)));   // (0.5 a) dt^2 exactly: halving is exact
                 cum_v[i] = vfma(aj[i], f2(P.dt), cum_v[i]);

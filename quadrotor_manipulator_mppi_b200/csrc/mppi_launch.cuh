@@ -41,8 +41,9 @@ mppi_status_t launch_rollout_variant(mppi_ctx *h, int variant, const float *d_u_
                                      cudaStream_t st)
 {
     constexpr int NU = ModelNu<MODEL>::value;
-    size_t smem = (size_t)h->P.T * NU * sizeof(float);
-    if (NOISE == 2) smem = ((smem + 15) & ~(size_t)15) + (size_t)kNoiseStages * kRolloutThreads * NU * sizeof(float);
+    constexpr int NUP = 4 * ((NU + 3) / 4);
+    size_t smem = ((((size_t)h->P.T * NU + 3) & ~(size_t)3) + (size_t)h->P.T * NUP) * sizeof(float);     // u_nom raw + in the pair layout
+    if (NOISE == 2) smem += (size_t)kNoiseStages * kRolloutThreads * NU * sizeof(float);
     const int grid = (h->P.K + kRolloutThreads - 1) / kRolloutThreads;
     auto launch = [&](auto kernel, size_t &tuned) -> mppi_status_t {
         if (tuned == 0) {
@@ -128,7 +129,7 @@ mppi_status_t launch_fused_variant(mppi_ctx *h, int slot, const float *d_u_nom, 
     const int grid = (K + kRolloutThreads - 1) / kRolloutThreads;
     const int R = kRolloutThreads / T;
     size_t floats = (size_t)2 * kRolloutThreads + (size_t)R * T * NUP;            // weights, indices, reduction
-    if (floats < (size_t)T * NU + 4) floats = (size_t)T * NU + 4;                  // staged nominal sequence
+    if (floats < (size_t)T * NU + 4 + (size_t)T * NUP) floats = (size_t)T * NU + 4 + (size_t)T * NUP;   // staged nominal sequence, raw + pair layout
     if (floats < (size_t)4 * T * NU + NU + 16) floats = (size_t)4 * T * NU + NU + 16;   // finalize scratch + smem hand-over of sums and u_nom
     const size_t smem = floats * sizeof(float);
     auto kernel = step_fused_kernel<MODEL, BAKED, EXTRA, ROUNDS>;
