@@ -53,8 +53,34 @@ def f(m, name):
         return float("nan")
 
 
+def refresh_static(rounds):
+    """--static R: re-derive the figures that need no GPU (operand model, FP32 FLOP of the hot loop) from the library as
+    built now, for kernels that changed after the last ncu capture; the ncu-measured fields keep their capture's values
+    and `static_refresh` says so."""
+    mpath = os.path.join(ROOT, "profiles", "ncu_metrics.json")
+    mj = json.load(open(mpath))
+    lib = os.path.join(ROOT, "quadrotor_manipulator_mppi_b200", "libmppi_b200.so")
+    for stem, model_id, per_iter, nth in (("wb_philox_K262144_T64", 3, 1, 0), ("wb_philox_K32768_T64", 3, 1, 0), ("quad_philox_K65536_T100", 2, 4, 0),
+                                          ("arm_philox_K1048576_T32", 1, 2, 1)):
+        key = f"{stem}_r{rounds}"
+        if key not in mj:
+            continue
+        om = sass_operand_model.model(lib, f"rollout_cost_kernel<{model_id}, 0, {'true' if model_id in (1, 3) else 'false'}, false, {rounds}>", nth)
+        mj[key]["operand_model"] = {"serial_cost_cycles_per_warp_step": om["serial_cost_cycles"] / per_iter, "issue_slots": om["instructions"] / per_iter,
+                                    "fma_pipe_cycles": om["pipe"]["fma"] / per_iter, "xu_pipe_cycles": om["pipe"]["xu"] / per_iter,
+                                    "register_source_words": om["register_source_words"] / per_iter}
+        if mj[key].get("executed_flop_per_rollout_step") is not None:
+            mj[key]["executed_flop_per_rollout_step_at_capture"] = mj[key].get("executed_flop_per_rollout_step_at_capture", mj[key]["executed_flop_per_rollout_step"])
+            mj[key]["executed_flop_per_rollout_step"] = om["fp32_flop_per_thread"] / per_iter
+        mj[key]["static_refresh"] = ("operand_model and executed_flop_per_rollout_step re-derived from the SASS of the final library "
+                                     "(tools/sass_operand_model.py: hot loop only, no GPU); pipe utilisation, registers and durations are those of the capture named in `source`")
+    json.dump(mj, open(mpath, "w"), indent=1, sort_keys=True)
+
+
 def main():
     args = sys.argv[1:]
+    if args and args[0] == "--static":
+        return refresh_static(int(args[1]))
     outdir = os.path.join(ROOT, "profiles", "r02")
     os.makedirs(outdir, exist_ok=True)
     mpath = os.path.join(ROOT, "profiles", "ncu_metrics.json")
