@@ -69,9 +69,10 @@ def refresh_static(rounds):
         mj[key]["operand_model"] = {"serial_cost_cycles_per_warp_step": om["serial_cost_cycles"] / per_iter, "issue_slots": om["instructions"] / per_iter,
                                     "fma_pipe_cycles": om["pipe"]["fma"] / per_iter, "xu_pipe_cycles": om["pipe"]["xu"] / per_iter,
                                     "register_source_words": om["register_source_words"] / per_iter}
-        if mj[key].get("executed_flop_per_rollout_step") is not None:
-            mj[key]["executed_flop_per_rollout_step_at_capture"] = mj[key].get("executed_flop_per_rollout_step_at_capture", mj[key]["executed_flop_per_rollout_step"])
+        if "K32768" not in stem:
             mj[key]["executed_flop_per_rollout_step"] = om["fp32_flop_per_thread"] / per_iter
+            imad = sum(sass_operand_model.FMA_PIPE[k] * v for k, v in om["counts"].items() if k.startswith("IMAD") and k in sass_operand_model.FMA_PIPE)
+            mj[key]["philox_pipe_share"] = imad / om["pipe"]["fma"]
         mj[key]["static_refresh"] = ("operand_model and executed_flop_per_rollout_step re-derived from the SASS of the final library "
                                      "(tools/sass_operand_model.py: hot loop only, no GPU); pipe utilisation, registers and durations are those of the capture named in `source`")
     json.dump(mj, open(mpath, "w"), indent=1, sort_keys=True)
