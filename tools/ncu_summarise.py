@@ -135,7 +135,8 @@ def main():
             if not hit:
                 continue
             m = hit[0]
-            entry = {"source": f"profiles/r02/{tag}_launches.csv (ncu --metrics, --clock-control none) and the SASS page of {tag}_full.ncu-rep (tools/ncu_flops.py)",
+            entry = {"source": f"profiles/r02/{tag}_launches.csv (ncu --metrics, --clock-control none)"
+                               + (f" and the SASS page of {tag}_full.ncu-rep (tools/ncu_flops.py)" if os.path.exists(rep) else ""),
                      "kernel_us_under_ncu": f(m, "gpu__time_duration.sum") / 1e3,
                      "fma_pipe_active_pct": f(m, "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
                      "issue_active_pct": f(m, "sm__issue_active.avg.pct_of_peak_sustained_active"),
