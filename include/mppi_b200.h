@@ -240,7 +240,10 @@ mppi_status_t mppi_step_p2p_sync(mppi_handle_t h, const float *state_host, int32
 
 /* Host-buffer form (what a non-torch caller uses; also the end-to-end timing path):
  * copies state (if given) and u_inout to the device, steps, copies u_new / out / costs back
- * and synchronises.  noise_host may be NULL (Philox).                                   */
+ * and synchronises.  noise_host may be NULL (Philox).  With host noise the [T][K][nu] device staging
+ * buffer is allocated on first use -- call mppi_reserve_host_noise() once after mppi_create to keep
+ * the allocation off the step path.                                                     */
+mppi_status_t mppi_reserve_host_noise(mppi_handle_t h);
 mppi_status_t mppi_step_host(mppi_handle_t h, const float *state_host, int32_t n_state,
                              float *u_inout_host, const float *noise_host, uint64_t step_counter,
                              float *cost_out_host, float *out_host);

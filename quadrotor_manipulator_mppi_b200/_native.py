@@ -29,7 +29,7 @@ EXPORTS = [
     "mppi_update_config", "mppi_set_joint_traj", "mppi_set_chain", "mppi_set_arm_inertia", "mppi_set_target", "mppi_set_state", "mppi_step", "mppi_rollout", "mppi_weight",
     "mppi_finalize", "mppi_rho_ptr", "mppi_wsum_ptr", "mppi_wsum_count", "mppi_cost_ptr",
     "mppi_p2p_export", "mppi_p2p_bind", "mppi_step_p2p", "mppi_step_p2p_sync", "mppi_step_sync", "mppi_step_host", "mppi_generate_noise", "mppi_measure_fp32_peak",
-    "mppi_algorithmic_flops_per_rollout_step", "mppi_set_option", "mppi_get_option", "mppi_get_kernel_times", "mppi_get_trace",
+    "mppi_algorithmic_flops_per_rollout_step", "mppi_set_option", "mppi_get_option", "mppi_get_kernel_times", "mppi_get_trace", "mppi_reserve_host_noise",
     "mppi_structural_flops_per_rollout_step",
 ]
 OPTION_PHILOX_ROUNDS, OPTION_FUSED_STEP, OPTION_TIME_PARALLEL, OPTION_PROFILE, OPTION_NVTX, OPTION_LAST_PATH = 1, 2, 3, 4, 5, 6
@@ -114,6 +114,7 @@ def load():
     lib.mppi_get_option.argtypes = [vp, i32, C.POINTER(i32)]
     lib.mppi_get_kernel_times.argtypes = [vp, _fp]
     lib.mppi_get_trace.argtypes = [vp, C.POINTER(C.c_uint64), i32]
+    lib.mppi_reserve_host_noise.argtypes = [vp]
     for name in EXPORTS:
         if name not in ("mppi_abi_version", "mppi_last_error", "mppi_rho_ptr", "mppi_wsum_ptr", "mppi_wsum_count",
                         "mppi_cost_ptr", "mppi_algorithmic_flops_per_rollout_step", "mppi_structural_flops_per_rollout_step"):

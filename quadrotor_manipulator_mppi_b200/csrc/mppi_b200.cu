@@ -782,6 +782,23 @@ mppi_status_t mppi_step_p2p_sync(mppi_handle_t h, const float *state_host, int32
     return wait_published(h, seq, (cudaStream_t)stream, out_host);
 }
 
+// device staging buffer for host-resident injected noise, [T][K][nu]
+static mppi_status_t reserve_noise_staging(mppi_handle_t h, size_t bytes)
+{
+    if (bytes <= h->d_noise_bytes) return MPPI_OK;
+    cudaFree(h->d_noise); h->d_noise = nullptr; h->d_noise_bytes = 0;
+    MPPI_CUDA(h, cudaMalloc(&h->d_noise, bytes));
+    h->d_noise_bytes = bytes;
+    return MPPI_OK;
+}
+
+mppi_status_t mppi_reserve_host_noise(mppi_handle_t h)
+{
+    if (!h) return MPPI_ERR_INVALID_ARG;
+    DeviceGuard guard(h->cfg.device);
+    return reserve_noise_staging(h, (size_t)h->P.T * h->nu * (size_t)h->P.K * sizeof(float));
+}
+
 mppi_status_t mppi_step_host(mppi_handle_t h, const float *state_host, int32_t n_state, float *u_inout_host,
                              const float *noise_host, uint64_t step_counter, float *cost_out_host, float *out_host)
 {
@@ -798,11 +815,8 @@ mppi_status_t mppi_step_host(mppi_handle_t h, const float *state_host, int32_t n
     const float *d_noise = nullptr;
     if (noise_host) {
         const size_t bytes = nu_floats * (size_t)h->P.K * sizeof(float);
-        if (bytes > h->d_noise_bytes) {
-            cudaFree(h->d_noise); h->d_noise = nullptr; h->d_noise_bytes = 0;
-            MPPI_CUDA(h, cudaMalloc(&h->d_noise, bytes));
-            h->d_noise_bytes = bytes;
-        }
+        const mppi_status_t rs = reserve_noise_staging(h, bytes);      // no-op after mppi_reserve_host_noise / the first call
+        if (rs != MPPI_OK) return rs;
         MPPI_CUDA(h, cudaMemcpyAsync(h->d_noise, noise_host, bytes, cudaMemcpyHostToDevice, st));
         d_noise = h->d_noise;
     }

@@ -434,6 +434,7 @@ def test_host_buffer_c_abi_matches_device_path(native, oracle):
         u = np.zeros((T, 7), np.float32)
         S = np.zeros(K, np.float32)
         out = np.zeros(native.MPPI_OUT_FLOATS, np.float32)
+        native.check(lib.mppi_reserve_host_noise(h), h)          # the [T][K][nu] staging buffer, off the step path
         native.check(lib.mppi_step_host(h, native.fptr(state), 21, native.fptr(u), native.fptr(noise), 0,
                                         native.fptr(S), native.fptr(out)), h)
         o = oracle.arm_step(noise, np.zeros((T, 7), np.float32), oracle.Q_HOME, np.zeros(7), [0, 0, 2.1, 0, 0, 0, 1])
