@@ -47,3 +47,27 @@ def test_register_budgets_of_the_hot_kernels():
     # streaming weighting pass: 3 blocks of 32*nu threads per SM
     assert _one(res, "weighted_noise_kernelILi3ELi4E")[0] <= 62          # nu = 11: 352 threads
     assert _one(res, "weighted_noise_kernelILi1ELi4E")[0] <= 97          # nu = 7: 224 threads
+
+
+def test_operand_model_of_the_whole_body_hot_loop():
+    """tools/sass_operand_model.py on the shipped library (cuobjdump -sass, no GPU): the whole-body rollout's horizon loop
+    priced at max(issue slot, FMA-pipe cycles, register source words / 2) per instruction tracked the measured kernel time
+    to +-1 % over four builds (667 / 634 / 622 / 578 cycles per warp-step against 323 / 308 / 300 / 282 us on B200).  A
+    change that silently puts work back into the loop (a per-step range reduction is 45 cycles, the cumulative-sum
+    integrators 44) shows up here before any GPU run."""
+    import os
+    import sys
+    from quadrotor_manipulator_mppi_b200 import build
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tools"))
+    import sass_operand_model
+    if not (shutil.which("cuobjdump") or os.path.exists("/usr/local/cuda/bin/cuobjdump")):
+        pytest.skip("cuobjdump unavailable")
+    lib = build.build()
+    unit = os.path.join(os.path.dirname(lib), "csrc", "_obj", "unit_m3_p0.o")        # the same code, 20x less SASS to dump
+    path = unit if os.path.exists(unit) and os.path.getmtime(unit) <= os.path.getmtime(lib) + 1 else lib
+    for rounds, cap in ((7, 600), (10, 660)):
+        m = sass_operand_model.model(path, f"rollout_cost_kernel<3, 0, true, false, {rounds}>")
+        assert 300 < m["instructions"] < 480, m["instructions"]                       # the horizon loop was found, not a helper loop
+        assert m["serial_cost_cycles"] <= cap, (rounds, m["serial_cost_cycles"])
+        assert m["pipe"]["xu"] <= 8 * 52                                              # MUFU: 24 Box-Muller + 20 sin/cos + 6 pose cost / rigid body
