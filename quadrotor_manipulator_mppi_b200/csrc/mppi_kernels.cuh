@@ -50,9 +50,16 @@ __host__ __device__ constexpr int pairB(int i) { return i == 0 ? 2 : i == 1 ? 3 
 //            step, kNoiseStages deep; needs K*nu % 4 == 0 and a 16-byte aligned tensor).
 constexpr int kNoiseStages = 4;
 
-// Models whose horizon step is a short dependent chain (point mass, rigid body: ~100 instructions behind one Philox
-// call) are latency-bound at any occupancy this path reaches; their noise is generated kNoiseBatch steps at a time so
-// the Philox / Box-Muller chains of several steps overlap (independent counters), then the steps run back to back.
+// Scheduling shape of the horizon loop, per model.  Each is a compile-time knob so that tools/build_variant.py can build the
+// alternatives side by side and tools/ab_variants.py can time them in one GPU call; the defaults are the measured best
+// (profiles/r02/README.md, "Experiments measured and not shipped"):
+//   *_NB        noise of NB horizon steps generated at a time, then the NB steps run back to back.  Point mass / rigid
+//               body: 4 -- their step is a short dependent chain behind one Philox call, so the chains of several steps
+//               overlap (2 / 6 / 8 measured slower).  Whole body: 1 (2 measured slower).
+//   SMALL_NOBREAK  the batch is ONE basic block: steps past a ragged horizon are computed and not accumulated (-4 %).
+//   *_PREFETCH  the noise of step t+1 is generated while step t runs.  Whole body: on (-2 %, -3.5 % at small shards);
+//               arm (+1.3 %) and the small models (+7 %): off.
+//   *_UNROLL    horizon loop unrolled: arm 2 (-1 %), whole body 1 (no change).
 #ifndef MPPI_WB_NB
 #define MPPI_WB_NB 1
 #endif
