@@ -15,7 +15,10 @@ Prints ONE JSON line (rank 0).  `value` = K*T*steps / device time (CUDA events a
 step, max over ranks, L2 flushed between steps outside the events).  `e2e` = the same metric
 through the public controller class with HOST state in / HOST controls out every step.
 `roofline` is measured live for the dominant kernel (fused rollout+cost) against an FP32 FFMA
-probe run in the same process.  `cpu_baseline` = the CPU oracle port (oracle/, C + OpenMP) on a
+probe run in the same process; next to the counted FLOP figure it carries the executed one, the
+ncu pipe utilisation and the register-operand model of the hot loop (profiles/ncu_metrics.json,
+tools/sass_operand_model.py) with the time that model predicts at the sampled SM clock.
+`cpu_baseline` = the CPU oracle port (oracle/, C + OpenMP) on a
 bounded sample of the same workload on this box's host cores.
 """
 from __future__ import annotations
